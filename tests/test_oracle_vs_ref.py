@@ -1,0 +1,146 @@
+"""Oracle restatement vs the UNMODIFIED reference compiled from /root/reference (oracle/_ref/*.so).
+
+Runs only where oracle/_ref exists (the build container, or the GPU box when the prebuilt files travelled).
+Every comparison is bit-exact: same inputs, same chunking, np.array_equal on the outputs.
+"""
+import numpy as np
+import pytest
+
+import pyoracle as po
+from tests.synth_ref import make_poes_capture
+
+pytestmark = pytest.mark.skipif(not po.ref_available("f32") or not po.ref_available("f64"),
+                                reason="oracle/_ref not built (needs /root/reference)")
+TWO_PI = 2.0 * np.pi
+
+
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_scalar_helpers(prec):
+    o, r = po.Oracle(prec), po.RefLib(prec)
+    rng = np.random.default_rng(5)
+    for y, x in rng.standard_normal((2000, 2)):
+        assert o.lib.pdto_arctan2(y, x) == r.lib.arctan2(y, x)
+    for x in np.abs(rng.standard_normal(2000)) * 10.0 ** rng.integers(-6, 3, 2000):
+        assert o.lib.pdto_q_rsqrt(x) == r.lib.Q_rsqrt(x)
+    assert o.lib.pdto_arctan2(0.0, 0.0) == r.lib.arctan2(0.0, 0.0)
+    assert o.lib.pdto_q_rsqrt(0.0) == r.lib.Q_rsqrt(0.0)
+
+
+@pytest.mark.parametrize("prec,seed", [("f32", 1), ("f32", 2), ("f64", 3)])
+def test_pll_chunked(prec, seed):
+    o, r = po.Oracle(prec), po.RefLib(prec)
+    fs = 50000 if prec == "f32" else 5000
+    pcm, _ = make_poes_capture(60000, fs, seed, esn0_db=10, doppler_hz=-2100 if prec == "f32" else 300,
+                               chip_rate=16640.3 if prec == "f32" else 800.0)
+    iq = o.pcm16_to_complex(pcm)
+    Fs = np.float32(fs) if prec == "f32" else float(fs)
+    if prec == "f32":
+        a = (fs, 4500.0, 0.08, 0.3979 * (TWO_PI / Fs), 127.3240 * (TWO_PI / Fs), 10.3451 * (TWO_PI / Fs))
+    else:
+        a = (fs, 550.0, 0.1, 3.1831 * (TWO_PI / Fs), 16 * (TWO_PI / Fs), 16 * (TWO_PI / Fs))
+    st = o.new_state("pll")
+    pos = 0
+    for n in (1, 9999, 10000, 7, 20000, 19993):          # ragged chunking, state carries over
+        x = iq[2 * pos: 2 * (pos + n)]
+        oo, ol, oa, _, _ = o.pll(st, x, *a, want_lock=True)
+        ro, rl, ra = r.pll(x, *a, want_lock=True)
+        assert np.array_equal(oo, ro) and np.array_equal(ol, rl) and oa == ra
+        pos += n
+
+
+def test_fir_interp_ragged():
+    o, r = po.Oracle("f32"), po.RefLib("f32")
+    rng = np.random.default_rng(11)
+    for L in (1, 2, 3, 5, 8):
+        r = po.RefLib("f32")
+        h = r.make_lpfir(26 * L, 11000.0, np.float32(150000.0), L)
+        assert np.array_equal(h, o.make_lpfir(26 * L, 11000.0, np.float32(150000.0), L))
+        st = o.new_state("fir")
+        for n in (1, 2, 25, 26, 27, 1000, 0, 333):
+            x = rng.standard_normal(n).astype(np.float32)
+            t = np.arange(n + 1, dtype=np.float32)
+            yo, to = o.fir_interp(st, t, x, h, L)
+            yr, tr = r.fir_interp(t, x, h, L)
+            assert np.array_equal(yo, yr) and np.array_equal(to, tr)
+
+
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_fir_agc_squelch_mm(prec):
+    o, r = po.Oracle(prec), po.RefLib(prec)
+    rng = np.random.default_rng(13)
+    h = r.make_lpfir(50, 700.0, 5000.0, 1)
+    fst, ast, mst = o.new_state("fir"), o.new_state("agc"), o.new_state("mm")
+    for n in (3, 49, 50, 51, 2400, 1):
+        x = (rng.standard_normal(n) * rng.choice([0.01, 1.0, 30.0])).astype(o.dt)
+        assert np.array_equal(o.fir(fst, x, h), r.fir(x, h))
+        ya, _ = o.agc(ast, x, 6.5, 0.1, 0.2)
+        assert np.array_equal(ya, r.agc(x, 6.5, 0.1, 0.2))
+        lock = rng.random(n).astype(o.dt) * 0.3
+        assert np.array_equal(o.squelch(x, lock, 0.15), r.squelch(x, lock, 0.15))
+    for n in (500, 2400, 2400):
+        buf = np.zeros(n + 16, o.dt)
+        buf[:n] = np.sin(np.arange(n) * 0.5) + 0.2 * rng.standard_normal(n)
+        assert np.array_equal(o.mm(mst, buf, n, 5000, 800.0, 3.0, 0.15), r.mm(buf, n, 5000, 800.0, 3.0, 0.15))
+
+
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_gardner_manchester_chunked(prec):
+    o, r = po.Oracle(prec), po.RefLib(prec)
+    rng = np.random.default_rng(17)
+    gst, mst = o.new_state("gardner"), o.new_state("manchester")
+    FsI, baud, sps = (150000, 16640.3, 9.014) if prec == "f32" else (5000, 800.0, 6.25)
+    cap = 30000 + 16
+    buf = np.zeros(cap, o.dt)                       # persistent buffer: stale tail is part of the semantics
+    pos = 0
+    for n in (30000, 30000, 29999, 12345, 30000, 17):
+        buf[:n] = np.sin(np.pi * (pos + np.arange(n)) / sps + 0.3) * (1.5 + 0.5 * np.sin(pos)) \
+            + 0.3 * rng.standard_normal(n)
+        so, io, _ = o.gardner(gst, buf, n, FsI, baud, 0.1, 3.0)
+        sr, ir = r.gardner(buf.copy(), n, FsI, baud, 0.1, 3.0)
+        assert np.array_equal(so, sr)
+        if prec == "f64":
+            assert np.array_equal(io, ir)            # float32 time axis cannot carry indices > 2^24 exactly
+        else:
+            assert np.array_equal(io, ir)
+        thr = 1.0 if prec == "f32" else 0.5
+        assert np.array_equal(o.manchester(mst, so, thr), r.manchester(sr, thr))
+        pos += n
+
+
+def test_bytesync_random_stream():
+    o, r = po.Oracle("f32"), po.RefLib("f32")
+    o64, r64 = po.Oracle("f64"), po.RefLib("f64")
+    rng = np.random.default_rng(19)
+    sync = np.frombuffer(po.POES_SYNC, np.uint8)
+    inv = (97 - sync).astype(np.uint8)               # '0'<->'1'
+    bits = (rng.integers(0, 2, 40000) + 48).astype(np.uint8)
+    for k, at in enumerate(range(100, 39000, 1500)):
+        bits[at:at + 19] = inv if k % 3 == 2 else sync
+    asy = np.frombuffer(po.ARGOS_SYNC, np.uint8)
+    abits = bits.copy()
+    for at in range(50, 39000, 700):
+        abits[at:at + 13] = asy
+    st, st64 = o.new_state("bytesync"), o64.new_state("bytesync")
+    pos = 0
+    for n in (1, 18, 19, 832, 5000, 13, 20000, 14117):
+        t = (np.arange(pos, pos + n + 1) * 1e-3).astype(np.float32)
+        assert o.bytesync(st, bits[pos:pos + n], "poes", t) == r.bytesync(bits[pos:pos + n], t)
+        t64 = t.astype(np.float64)
+        assert o64.bytesync(st64, abits[pos:pos + n], "argos", t64) == r64.bytesync(abits[pos:pos + n], t64)
+        pos += n
+    assert o.bytesync_text(st) == r.bytesync_text()
+    assert o64.bytesync_text(st64) == r64.bytesync_text()
+    assert "i " in o.bytesync_text(st)
+
+
+@pytest.mark.parametrize("fs,chunk", [(50000, 10000), (250000, 10000), (250000, 4096), (18750, 10000)])
+def test_chain_vs_ref_cli(tmp_path, fs, chunk):
+    """Whole chain (restated main.c loop) vs the reference executable on a synthetic WAV."""
+    from tests.golden.make_golden import write_wav
+    pcm, _ = make_poes_capture(int(1.2 * fs), fs, seed=fs % 97, esn0_db=11, doppler_hz=1500.0)
+    wav = str(tmp_path / "s.wav")
+    write_wav(wav, fs, pcm)
+    so, txt = po.run_ref_cli("POES", wav, ("-c", str(chunk)) if chunk != 10000 else ())
+    o = po.Oracle("f32")
+    res = o.chain(o.pcm16_to_complex(pcm), fs, chunk=chunk)
+    assert res["text"] == txt and len(txt) > 0
