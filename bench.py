@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py — IQ Msamples/s through the full demod chain (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N … bench.py --gpus N …
+
+A "step" is one pass of the fused chain kernel over one batch of synthetic POES-TIP captures that is already
+resident in HBM (weak scaling: every GPU owns `--captures` captures of `--samples` IQ samples; at N=1 this is
+BASELINE.json configs[3]'s 1024 x 1 M-sample batch @ 250 ksps on one GPU, with configs[1]'s signal parameters).
+`value` is whole-job Msamples/s from CUDA events on the launch stream (max over ranks); `e2e` is the same metric
+through the host-buffer C-ABI call (pdt_demod_host: pinned host IQ -> H2D -> kernel -> D2H of stats+frames).
+`roofline` is for the dominant (only) kernel of the step; `cpu_baseline` times the UNMODIFIED reference
+(oracle/_ref/libref_f32.so, one process per capture — the reference is single-threaded with static state) on a
+bounded sample of the same captures on the box's host cores.
+
+`--impl reference` times only that CPU reference arm (rank 0; other ranks exit) and prints the same JSON shape.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "oracle")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "IQ Msamples/s through full demod chain"
+UNIT = "Msamples/s"
+FS = 250_000
+
+
+# ----------------------------------------------------------------------------------------------------
+# CPU reference arm (also used for cpu_baseline)
+# ----------------------------------------------------------------------------------------------------
+def _cpu_worker_init(kind):
+    global _W
+    import pyoracle as po
+    devnull = os.open(os.devnull, os.O_WRONLY)      # the reference printf()s " : PLL locked at …" per capture
+    os.dup2(devnull, 1)
+    _W = {"kind": kind, "po": po}
+
+
+def _cpu_worker_run(path):
+    """One capture through the reference's per-chunk loop (POESTIPdemod/main.c:373-482), fresh state per capture."""
+    po = _W["po"]
+    iq = np.load(path, mmap_mode="r")
+    iq = np.ascontiguousarray(iq, np.float32)
+    t0 = time.perf_counter()
+    if _W["kind"] == "reference":
+        frames = po.ref_chain_poes(iq, FS)
+    else:
+        frames = po.Oracle("f32").chain(iq, FS)["total_frames"]
+    return time.perf_counter() - t0, int(frames)
+
+
+def cpu_arm(captures, steps, warmup, cores=None):
+    """captures: list of float32 [2n] arrays.  Returns dict(value Msamples/s, ms_per_step, cores, kind, frames)."""
+    import multiprocessing as mp
+    import pyoracle as po
+    kind = "reference" if po.ref_available("f32") else "port"
+    cores = cores or len(os.sched_getaffinity(0))
+    cores = max(1, min(cores, len(captures)))
+    tmp = tempfile.mkdtemp(prefix="pdtbench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    paths = []
+    for i, c in enumerate(captures):
+        p = os.path.join(tmp, f"cap{i}.npy")
+        np.save(p, np.ascontiguousarray(c, np.float32))
+        paths.append(p)
+    n_samples = sum(c.size // 2 for c in captures)
+    ctx = mp.get_context("spawn")
+    try:
+        with ctx.Pool(cores, initializer=_cpu_worker_init, initargs=(kind,)) as pool:
+            pool.map(_cpu_worker_run, paths[:cores])          # start-up + page-in, untimed
+            for _ in range(max(warmup - 1, 0)):
+                pool.map(_cpu_worker_run, paths)
+            t0 = time.perf_counter()
+            frames = 0
+            for _ in range(steps):
+                res = pool.map(_cpu_worker_run, paths, chunksize=1)
+                frames = sum(r[1] for r in res)
+            dt = time.perf_counter() - t0
+    finally:
+        for p in paths:
+            os.remove(p)
+        os.rmdir(tmp)
+    return dict(value=n_samples * steps / dt / 1e6, ms_per_step=dt / steps * 1e3, cores=cores, kind=kind,
+                frames=frames, n_captures=len(captures), n_samples=n_samples)
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    from tests.synth_ref import make_poes_capture
+    cores = len(os.sched_getaffinity(0))
+    n_caps = max(1, min(cores, args.ref_captures or cores))
+    n = args.ref_samples
+    caps = []
+    base, _ = make_poes_capture(n, FS, 4242, esn0_db=12.0, doppler_hz=-1500.0)
+    base = (base.astype(np.float32) / np.float32(32768.0))
+    for i in range(n_caps):       # distinct captures cheaply: rotate + conjugate-free phase spin keeps the statistics
+        ph = np.exp(1j * 0.37 * i).astype(np.complex64)
+        z = (base[0::2] + 1j * base[1::2]).astype(np.complex64) * ph
+        c = np.empty(2 * n, np.float32)
+        c[0::2], c[1::2] = z.real, z.imag
+        caps.append(c)
+    r = cpu_arm(caps, args.steps, args.warmup, cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"POES TIP chain, {n_caps} captures x {n} IQ samples @ {FS} sps per step on host cores "
+                               f"(bounded sample of the GPU arm's batch shape)", "sample_rate": FS,
+                   "captures_per_step": n_caps, "samples_per_capture": n},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                         "sample": f"{n_caps} captures x {n} samples per step, one process per capture"},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for t, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9 or not (t0 - 0.05 <= t <= t1 + 0.15):
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+class _Raw:
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--captures", type=int, default=1024, help="captures per GPU")
+    ap.add_argument("--samples", type=int, default=1_000_000, help="IQ samples per capture")
+    ap.add_argument("--pcm16", action="store_true", help="feed int16 PCM (4 B/sample) instead of cf32")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-captures", type=int, default=0)
+    ap.add_argument("--ref-captures", type=int, default=0)
+    ap.add_argument("--ref-samples", type=int, default=1_000_000)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    if args.impl == "reference":
+        return reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    pdt = importlib.import_module("project-desert-tortoise_b200")
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    L = pdt.load("f32")
+    if L.pdt_device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device - the product has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    L.pdt_set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    C_, n = args.captures, args.samples
+    elem = torch.int16 if args.pcm16 else torch.float32
+    bytes_per_sample = 4 if args.pcm16 else 8
+    d_iq = torch.empty(C_ * n * 2, dtype=elem, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    rc = L.pdt_synth_poes_device(d_iq.data_ptr(), int(args.pcm16), C_, n, n, float(FS), 20261017 + rank * 1_000_003, stream)
+    if rc != 0:
+        raise SystemExit("synth failed: " + L.pdt_last_error().decode())
+    params = pdt.default_params("f32", pdt.PDT_MODE_POES, FS)
+    max_frames = int(n / FS * 10) + 8
+    d = pdt.Demod("f32", params, C_, n, max_frames)
+    ds, df, _ = d.result_tables()
+    frames_t = torch.as_tensor(_Raw(df, C_ * max_frames * 120), device="cuda")
+    gathered = torch.empty(world * frames_t.numel(), dtype=torch.uint8, device="cuda") if world > 1 else None
+
+    def step():
+        d.demod_device(d_iq.data_ptr(), C_, n, pcm16=args.pcm16, stream=stream)
+        if world > 1:   # the only exchange on this path: gather the decoded minor frames (≤ 104 B x 10 frames/s/capture)
+            dist.all_gather_into_tensor(gathered, frames_t)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = L.pdt_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    launches = L.pdt_launch_count() - launches0
+    clocks = sampler.stop(t0, t1) if sampler else None
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_step = ms / args.steps
+    total_samples = C_ * n * world
+    value = total_samples / (ms_step * 1e-3) / 1e6
+
+    # ---- dominant kernel alone (events around each launch on the launch stream) -------------------
+    kt = []
+    for _ in range(min(args.steps, 5)):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        d.demod_device(d_iq.data_ptr(), C_, n, pcm16=args.pcm16, stream=stream)
+        b.record()
+        torch.cuda.synchronize()
+        kt.append(a.elapsed_time(b))
+    k_ms = float(np.mean(kt))
+    stats, frames = d.fetch(C_, stream)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    alg_bytes = C_ * n * bytes_per_sample
+    achieved = alg_bytes / (k_ms * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        key = f"{C_}x{n}x{'pcm16' if args.pcm16 else 'cf32'}"
+        traffic = tj.get(key, {}).get("dram_bytes_per_launch")
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "k_chain_exact", "kernel_ms": k_ms, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes,
+                "note": f"{bytes_per_sample} B per input IQ sample (whole chain fused; outputs are 104 B per 0.1 s)"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"batch of {C_} synthetic POES TIP captures x {n} IQ samples @ {FS} sps per GPU "
+                               f"(BASELINE configs[3] batch shape with configs[1] signal parameters), full chain "
+                               f"PLL->FIR->AGC->Gardner->Manchester->ByteSync fused in one kernel",
+                   "captures_per_gpu": C_, "samples_per_capture": n, "sample_rate": FS, "input": "pcm16" if args.pcm16 else "cf32",
+                   "interp": d.params.interp, "taps": d.params.taps, "chunk": d.params.chunk,
+                   "l2": f"inputs {alg_bytes / 1e9:.2f} GB per GPU, far larger than the 126 MB L2 (no flush needed)",
+                   "parallelism": f"one capture per CTA, {world} GPU(s), frames all-gathered over NCCL" if world > 1 else "one capture per CTA"},
+        "gpu_launches": int(launches), "roofline": roofline,
+        "check": {"frames_decoded": int(stats["n_frames"].sum()), "captures_locked": int(stats["locked"].sum()),
+                  "symbols": int(stats["n_symbols"].sum())},
+    }
+    if clocks:
+        line["clocks"] = clocks
+
+    # ---- e2e: host buffers through the C-ABI --------------------------------------------------------
+    if not args.no_e2e:
+        e2e_caps = C_
+        host = torch.empty(e2e_caps * n * 2, dtype=elem, pin_memory=True)
+        host.copy_(d_iq[: host.numel()])
+        torch.cuda.synchronize()
+        h_np = host.numpy()
+        for _ in range(1):
+            d.demod_host(h_np, e2e_caps, pcm16=args.pcm16)
+        if world > 1:
+            dist.barrier()
+        e2e_steps = max(2, min(args.steps, 3))
+        tt0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            st_h, fr_h = d.demod_host(h_np, e2e_caps, pcm16=args.pcm16)
+        tt = time.perf_counter() - tt0
+        if world > 1:
+            t = torch.tensor([tt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            tt = float(t.item())
+        line["e2e"] = {"value": e2e_caps * n * world * e2e_steps / tt / 1e6, "unit": UNIT,
+                       "h2d_bytes_per_step": int(e2e_caps * n * bytes_per_sample),
+                       "d2h_bytes_per_step": int(st_h.nbytes + fr_h.nbytes), "steps": e2e_steps,
+                       "api": "pdt_demod_host (pinned host IQ -> H2D -> fused kernel -> D2H stats+frames)"}
+        del host
+
+    # ---- CPU baseline on a bounded sample of the same captures (rank 0, N=1 only) --------------------
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = len(os.sched_getaffinity(0))
+        k = args.cpu_captures or min(C_, max(cores, 8))
+        k = min(k, 256)
+        caps = []
+        for c in range(k):
+            x = d_iq[c * n * 2:(c + 1) * n * 2].cpu().numpy()
+            caps.append(x.astype(np.float32) / np.float32(32768.0) if args.pcm16 else x)
+        r = cpu_arm(caps, 1, 1, cores)
+        line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                                "sample": f"first {k} captures of the GPU batch ({k} x {n} samples), one process per capture",
+                                "frames": r["frames"],
+                                "gpu_frames_same_captures": int(stats["n_frames"][:k].sum())}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

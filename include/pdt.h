@@ -1,0 +1,152 @@
+/*
+ * pdt.h — C-ABI of the B200-native IQ demodulation chain (batch / context API).
+ *
+ * This is the THROUGHPUT boundary: many independent IQ captures, device-resident, one fused sm_100a
+ * kernel per batch.  It replaces, for a whole capture at a time, the per-chunk loop body of the
+ * reference drivers:
+ *     POESTIPdemod/main.c:373-482   (StaticGain -> CarrierTrackPLL -> LowPassFilterInterp -> NormalizingAGC
+ *                                    -> GardenerClockRecovery -> ManchesterDecode -> ByteSyncOnSyncword)
+ *     ARGOSdemod/main.c:250-300     (… -> LowPassFilter -> NormalizingAGC -> Squelch -> … -> FindSyncWords)
+ * The drop-in LEGACY boundary (the reference's own function signatures, one call per stage per chunk)
+ * is declared in pdt_legacy.h; both live in the same shared objects:
+ *     libpdt_f32.so  — DECIMAL_TYPE float  (POESTIPdemod/config.h:4)
+ *     libpdt_f64.so  — DECIMAL_TYPE double (ARGOSdemod/config.h:4)
+ * Plain C types only; no torch / CUDA types in any signature (streams and device pointers are void*).
+ *
+ * Error behaviour: functions returning int give 0 on success, a negative PDT_E* code otherwise and
+ * record a message retrievable with pdt_last_error().  There is NO CPU fallback: without a usable CUDA
+ * device every compute entry point fails with PDT_ENODEV.
+ */
+#ifndef PDT_H
+#define PDT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PDT_OK        0
+#define PDT_ENODEV   -1   /* no CUDA device / driver */
+#define PDT_ECUDA    -2   /* a CUDA call or kernel failed */
+#define PDT_EINVAL   -3   /* bad argument */
+#define PDT_ENOMEM   -4
+
+#define PDT_MODE_POES  0
+#define PDT_MODE_ARGOS 1
+
+#define PDT_FRAME_MAX_BYTES 104
+
+/* All DSP constants of the reference drivers, in the units the reference uses (loop gains in rad/s,
+ * scaled by 2π/Fs at the call site in double and narrowed to DECIMAL_TYPE: POESTIPdemod/main.c:413,429). */
+typedef struct pdt_params {
+    int      mode;               /* PDT_MODE_POES | PDT_MODE_ARGOS */
+    double   sample_rate;        /* header.sample_rate (main.c:346) */
+    uint32_t chunk;              /* DEFAULT_CHUNKSIZE: 10000 (POES main.c:30) / 2400 (ARGOS main.c:27).
+                                    Part of the numerical behaviour (Gardner works in chunk-relative floats). */
+    int      interp;             /* L = rint(150000/Fs) (main.c:347); ARGOS 1 */
+    int      taps;               /* N = 26·L (main.c:348); ARGOS 50 */
+    int      force_min_interp1;  /* declared deviation for Fs >= 300 ksps where the reference emits nothing */
+    double   max_carrier_dev;    /* 4500 / 550 Hz */
+    double   pll_acq_gain, pll_track_gain, pll_lock_alpha;   /* rad/s */
+    double   pll_lock_thresh;
+    double   agc_attack, agc_decay;                          /* rad/s */
+    double   lpf_fc;             /* 11000 / 700 Hz */
+    double   baud;               /* symbol (chip) rate: 16640.3 / 800 */
+    double   gardner_err_lim, gardner_gain;                  /* 0.1, 3.0 */
+    double   manchester_resync;  /* 1.0 (POES main.c:445 passes the literal) / 0.5 */
+    double   squelch_thresh;     /* ARGOS 0.15; unused for POES */
+    double   norm_factor;        /* 0 = StaticGain of the first chunk (main.c:384-389), else override (-n) */
+    char     sync_word[32];      /* ASCII '0'/'1' */
+    int      sync_len;           /* 19 / 13 */
+} pdt_params;
+
+/* One decoded minor frame (POES, 104 bytes incl. the literal ED E2) or packet (ARGOS, 7 bytes). */
+typedef struct pdt_frame {
+    uint64_t sample_index;   /* absolute index, in interpolated samples, of the Gardner pick whose bit completed the sync word */
+    uint32_t bit_index;      /* absolute index of that bit in the capture's bit stream */
+    uint8_t  inverse;        /* 1 = matched the inverted sync word (POESTIPdemod/ByteSync.c:127) */
+    uint8_t  n_bytes;        /* bytes valid in `bytes` (104 / 7 when complete, fewer for a trailing partial frame) */
+    uint8_t  complete;
+    uint8_t  pad;
+    uint8_t  bytes[PDT_FRAME_MAX_BYTES];
+} pdt_frame;                 /* 120 bytes */
+
+/* Per-capture summary (what the reference prints on its progress line, main.c:461-481). */
+typedef struct pdt_capture_stats {
+    uint64_t n_samples, n_symbols, n_bits;
+    uint32_t n_frames;       /* sync words accepted (== frames incl. a trailing partial one) */
+    int32_t  locked;         /* PLL latch fired */
+    uint64_t lock_sample;    /* absolute input-sample index of the latch */
+    double   lock_freq_hz;   /* d_freq·Fs/2π at the latch (CarrierTrackingPLL.c:269) */
+    double   norm_factor;    /* StaticGain result */
+    double   avg_phase;      /* last CarrierTrackPLL return value */
+    double   final_phase, final_freq, final_gain, final_next;   /* loop states at the end (re-stitch / debugging) */
+} pdt_capture_stats;
+
+/* Optional per-capture trace taps (device pointers, any may be NULL).  REAL = float in libpdt_f32, double in f64. */
+typedef struct pdt_traces {
+    void     *pll_phase, *pll_freq, *pll_out;   /* REAL[n]      d_phase / d_freq BEFORE the update, and realDataOut */
+    void     *lock;                             /* REAL[n]      d_locksig stream */
+    void     *lpf, *agc;                        /* REAL[n·L]    FIR output, AGC (+squelch) output */
+    void     *sym, *gardner_err;                /* REAL[cap]    symbol values, clamped Gardner error */
+    uint64_t *gardner_idx;                      /* u64[cap]     absolute interp-sample index picked */
+    uint8_t  *bits;                             /* u8[cap]      ASCII '0'/'1' */
+    uint64_t  cap;
+} pdt_traces;
+
+typedef struct pdt_ctx pdt_ctx;
+
+const char *pdt_version(void);
+const char *pdt_last_error(void);
+int         pdt_real_size(void);                       /* 4 (libpdt_f32) or 8 (libpdt_f64) */
+int         pdt_device_count(void);                    /* <=0: no usable device */
+int         pdt_set_device(int ordinal);
+
+/* Reference defaults for a sample rate (mirrors the #defines at POESTIPdemod/main.c:30-104, ARGOSdemod/main.c:27-65). */
+int         pdt_params_default(pdt_params *p, int mode, double sample_rate);
+
+/* A context owns device workspaces for `max_captures` captures of up to `max_samples` IQ samples each and
+ * `max_frames` frame slots per capture. */
+pdt_ctx    *pdt_create(const pdt_params *p, uint32_t max_captures, uint64_t max_samples, uint32_t max_frames);
+void        pdt_destroy(pdt_ctx *ctx);
+int         pdt_get_params(const pdt_ctx *ctx, pdt_params *out);
+int         pdt_get_taps(const pdt_ctx *ctx, void *h_out /* REAL[taps] */);
+
+/* Demodulate a batch that is ALREADY in device memory.
+ *   d_iq        REAL[2·n] interleaved I,Q per capture; capture c starts at d_iq + 2·c·stride_samples
+ *               (pcm16 != 0: int16_t[2·n] raw PCM as in a WAV data chunk, normalised /32768 in-kernel, wave.c:141-166)
+ *   n_samples   host array [n_captures] (NULL: every capture has stride_samples samples)
+ *   traces      host array [n_captures] of device trace taps, or NULL
+ *   stream      cudaStream_t (NULL = default stream).  Asynchronous: results are valid after the stream is synchronised.
+ * Results stay on the device until pdt_fetch(). */
+int         pdt_demod_device(pdt_ctx *ctx, const void *d_iq, int pcm16, uint32_t n_captures, uint64_t stride_samples,
+                             const uint64_t *n_samples, const pdt_traces *traces, void *stream);
+
+/* Same from HOST buffers (pinned or pageable): H2D of the samples, the kernels, and D2H of stats+frames, synchronous. */
+int         pdt_demod_host(pdt_ctx *ctx, const void *h_iq, int pcm16, uint32_t n_captures, uint64_t stride_samples,
+                           const uint64_t *n_samples, pdt_capture_stats *stats_out, pdt_frame *frames_out /* [n_captures·max_frames] */);
+
+/* Copy results of the last pdt_demod_device() to the host (synchronises `stream`). */
+int         pdt_fetch(pdt_ctx *ctx, uint32_t n_captures, pdt_capture_stats *stats_out, pdt_frame *frames_out, void *stream);
+
+/* Device addresses of the result tables of the last batch (for NCCL gathers without a host bounce). */
+int         pdt_result_tables(pdt_ctx *ctx, void **d_stats, void **d_frames, uint32_t *max_frames);
+
+/* Render frames exactly like the reference's output file ("%.5f ED E2 XX …\n", POESTIPdemod/ByteSync.c:96-101,62,69).
+ * The time column emulates wave.c's float-accumulated axis.  Returns bytes written (excluding NUL) or <0. */
+long        pdt_format_frames(const pdt_ctx *ctx, const pdt_frame *frames, uint32_t n_frames, char *buf, size_t cap);
+
+/* Number of kernels launched by this library since load (bench.py reports it as gpu_launches). */
+uint64_t    pdt_launch_count(void);
+
+/* Seeded synthetic POES-TIP capture generator ON THE DEVICE (bench workloads; SURVEY §8d signal model).
+ * Writes REAL[2·n] (or int16 when pcm16) per capture at d_iq + 2·c·stride.  Per-capture SNR/Doppler are derived from seed+c. */
+int         pdt_synth_poes_device(void *d_iq, int pcm16, uint32_t n_captures, uint64_t stride_samples, uint64_t n_samples,
+                                  double sample_rate, uint64_t seed, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PDT_H */

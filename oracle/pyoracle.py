@@ -482,3 +482,47 @@ def read_wav_pcm16(path: str):
     assert ch == 2 and bits == 16, (ch, bits)
     data = np.frombuffer(raw, np.int16, count=min(size, len(raw) - 44) // 2, offset=44)
     return rate, data[: (data.size // 2) * 2]
+
+
+def ref_chain_poes(iq, fs, chunk=10000):
+    """The reference's POES per-chunk loop (POESTIPdemod/main.c:373-482) driven through the UNMODIFIED reference
+    library with preallocated buffers (bench.py's CPU arm).  Fresh static state per call.  Returns frames found."""
+    r = RefLib("f32")
+    lib = r.lib
+    iq = np.ascontiguousarray(iq, np.float32)
+    n = iq.size // 2
+    Fs = np.float32(fs)
+    L = int(np.rint(150000.0 / Fs))
+    N = 26 * L
+    if L < 1:
+        return 0
+    h = r.make_lpfir(N, 11000.0, np.float32(Fs * L), L)
+    TWO_PI = 2.0 * np.pi
+    w = TWO_PI / Fs
+    time_in = (np.arange(1, chunk + 2, dtype=np.float32) / Fs).astype(np.float32)
+    real_s = np.zeros(chunk, np.float32)
+    lpf = np.zeros(chunk * N, np.float32)
+    lpf_t = np.zeros(chunk * N, np.float32)
+    sym = np.zeros(chunk * L, np.float32)
+    bits = np.zeros(chunk * L, np.uint8)
+    fp = r.libc.fopen(b"/dev/null", b"w")
+    FsL = np.float32(Fs * L)
+    a_atk, a_dcy = 79.5775 * (TWO_PI / FsL), 159.1549 * (TWO_PI / FsL)
+    frames = 0
+    norm = 0.0
+    pos = 0
+    P = _ptr
+    while pos < n:
+        m = min(chunk, n - pos)
+        x = iq[2 * pos: 2 * (pos + m)]
+        if pos == 0:
+            norm = lib.StaticGain(P(x), m, 1.0)
+        lib.CarrierTrackPLL(P(x), P(real_s), None, m, Fs, 4500.0, 0.08, 0.3979 * w, 127.3240 * w, 10.3451 * w)
+        lib.LowPassFilterInterp(P(time_in), P(real_s), P(lpf), P(lpf_t), m, P(h), N, L)
+        lib.NormalizingAGC(P(lpf), m * L, norm, a_atk, a_dcy)
+        ns = lib.GardenerClockRecovery(P(lpf), P(lpf_t), m * L, P(sym), int(FsL), 16640.3, 0.1, 3.0)
+        nb = lib.ManchesterDecode(P(sym), P(lpf_t), ns, P(bits), 1.0)
+        frames += r._bs(P(bits), P(lpf_t), nb, POES_SYNC, 19, fp)
+        pos += m
+    r.libc.fclose(fp)
+    return frames

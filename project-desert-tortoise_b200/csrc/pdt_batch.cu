@@ -1,0 +1,395 @@
+// pdt_batch.cu — host side of the batch / context C-ABI (include/pdt.h).
+//
+// Mirrors, for whole captures, the driver loops of POESTIPdemod/main.c:346-482 and ARGOSdemod/main.c:244-300:
+// parameters are derived exactly as the reference call sites derive them (double expression narrowed to
+// DECIMAL_TYPE), the filter is designed once on the host (LowPassFilter.c:127-175), and the per-sample work
+// runs in ONE fused sm_100a kernel per batch (pdt_chain_kernel.cuh).  No CPU fallback exists.
+#include <cmath>
+#include <vector>
+#include <algorithm>
+#include <new>
+
+#include "pdt_chain_kernel.cuh"
+#include "pdt_synth.cuh"
+
+namespace pdt {
+
+thread_local char g_err[512] = "";
+std::atomic<unsigned long long> g_launches{0};
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+bool device_ok()
+{
+    static int state = -1;
+    if (state < 0) {
+        int n = 0;
+        cudaError_t e = cudaGetDeviceCount(&n);
+        state = (e == cudaSuccess && n > 0) ? 1 : 0;
+        if (!state) { fail(PDT_ENODEV, "no usable CUDA device (%s)", cudaGetErrorString(e)); cudaGetLastError(); }
+    }
+    return state == 1;
+}
+
+// LowPassFilter.c:127-175 — run once per context on the host with the host libm, exactly as the reference does.
+void make_lpfir_host(real_t *h, int N, real_t Fc, real_t Fs, int L)
+{
+    real_t T = 1.0 / Fs;
+    real_t wc = 2.0 * M_PI * Fc * T;
+    real_t tou = (N - 1.0) / 2.0;
+    for (int n = 0; n < N; n++) {
+#if PDT_USE_FLOATS
+        real_t hd = (sinf(wc * (n - tou))) / (M_PI * (n - tou));
+#else
+        real_t hd = (sin(wc * (n - tou))) / (M_PI * (n - tou));
+#endif
+        if ((n == tou) && ((int)((N / 2) * 2) != N)) hd = wc / M_PI;
+        real_t wn = 0.42 - 0.5 * cos((2 * M_PI * n) / (N - 1)) + 0.08 * cos((4 * M_PI * n) / (N - 1));
+        h[n] = hd * wn * (real_t)(L);
+    }
+}
+
+static uint32_t sync_bits(const char *w, int len)
+{
+    uint32_t v = 0;
+    for (int i = 0; i < len; i++) v = (v << 1) | (uint32_t)(w[i] == '1');
+    return v;
+}
+
+int build_chain_const(const pdt_params &p, ChainConst &cc)
+{
+    memset(&cc, 0, sizeof cc);
+    if (p.sync_len < 1 || p.sync_len > 31) return fail(PDT_EINVAL, "sync_len %d out of range", p.sync_len);
+    if (p.chunk < 64) return fail(PDT_EINVAL, "chunk %u too small", p.chunk);
+    const real_t Fs = (real_t)(unsigned int)p.sample_rate;          // main.c:346 (header.sample_rate is unsigned)
+    cc.argos = (p.mode == PDT_MODE_ARGOS);
+    cc.L = p.interp; cc.N = p.taps;
+    if (cc.L < 0 || cc.N > PDT_MAX_TAPS) return fail(PDT_EINVAL, "interp %d / taps %d unsupported", cc.L, cc.N);
+    if (cc.L > 0) {
+        if (cc.N % cc.L) return fail(PDT_EINVAL, "taps must be a multiple of interp");
+        cc.K = cc.argos ? cc.N : cc.N / cc.L;
+        if (cc.K < 1 || cc.K > 1024) return fail(PDT_EINVAL, "taps per branch %d unsupported", cc.K);
+    }
+    cc.chunk = p.chunk;
+    const double w = 2.0 * M_PI / Fs;                                // (2.0*M_PI/Fs), Fs is DECIMAL_TYPE
+    cc.pll.Fs = Fs;
+    cc.pll.freq_range = p.max_carrier_dev;
+    cc.pll.lock_thresh = p.pll_lock_thresh;
+    cc.pll.lock_alpha = p.pll_lock_alpha * w;                        // main.c:413
+    cc.pll.bw_acq = p.pll_acq_gain * w;
+    cc.pll.bw_track = p.pll_track_gain * w;
+    if (cc.argos) {
+        cc.agc_attack = p.agc_attack * (2.0 * M_PI / Fs);            // ARGOS main.c:270
+        cc.agc_decay  = p.agc_decay * (2.0 * M_PI / Fs);
+        cc.gardner_fs = (int)Fs;                                     // ARGOS main.c:278
+    } else {
+        const real_t FsL = Fs * cc.L;                                // Fs*dspLPFInterp in DECIMAL_TYPE
+        cc.agc_attack = p.agc_attack * (2.0 * M_PI / FsL);           // main.c:429
+        cc.agc_decay  = p.agc_decay * (2.0 * M_PI / FsL);
+        cc.gardner_fs = (int)FsL;                                    // main.c:438
+    }
+    cc.norm_override = p.norm_factor;
+    cc.baud = p.baud; cc.g_range = p.gardner_err_lim; cc.g_kp = p.gardner_gain;
+    cc.man_thresh = p.manchester_resync; cc.squelch = p.squelch_thresh;
+    cc.sync.len = p.sync_len;
+    cc.sync.word = sync_bits(p.sync_word, p.sync_len);
+    cc.sync.mask = (p.sync_len == 32) ? 0xffffffffu : ((1u << p.sync_len) - 1u);
+    cc.sync.last_idx = cc.argos ? 8 : 103;
+    cc.sync.carry_bits = cc.argos ? 0 : 3;
+    cc.sync.inverse_enabled = cc.argos ? 0 : 1;
+    cc.prefix_bytes = cc.argos ? 0 : 2;
+    return PDT_OK;
+}
+
+} // namespace pdt
+
+using namespace pdt;
+
+struct pdt_ctx {
+    pdt_params  params;
+    ChainConst  cc;
+    uint32_t    max_captures, max_frames;
+    uint64_t    max_samples;
+    real_t      taps_h[PDT_MAX_TAPS];
+    real_t     *d_taps = nullptr;
+    real_t     *d_ws = nullptr;          // global workspace (only when the chunk does not fit in shared memory)
+    size_t      ws_stride = 0;
+    int         use_smem = 1;
+    size_t      smem_bytes = 0;
+    int         grid = 0;
+    pdt_capture_stats *d_stats = nullptr;
+    pdt_frame  *d_frames = nullptr;
+    unsigned long long *d_nsamp = nullptr;
+    pdt_traces *d_traces = nullptr;
+    void       *d_stage = nullptr;       // staging for pdt_demod_host
+    size_t      stage_bytes = 0;
+    int         device = 0, sm_count = 0;
+};
+
+extern "C" {
+
+const char *pdt_version(void) { return "pdt-b200 0.1 (sm_100a, "
+#if PDT_USE_FLOATS
+    "f32"
+#else
+    "f64"
+#endif
+    ")"; }
+const char *pdt_last_error(void) { return g_err; }
+int pdt_real_size(void) { return (int)sizeof(real_t); }
+uint64_t pdt_launch_count(void) { return g_launches.load(); }
+
+int pdt_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int pdt_set_device(int ordinal)
+{
+    if (!device_ok()) return PDT_ENODEV;
+    PDT_CUDA(cudaSetDevice(ordinal));
+    return PDT_OK;
+}
+
+int pdt_params_default(pdt_params *p, int mode, double sample_rate)
+{
+    if (!p || sample_rate < 1) return fail(PDT_EINVAL, "bad arguments");
+    memset(p, 0, sizeof *p);
+    p->mode = mode; p->sample_rate = sample_rate;
+    const real_t Fs = (real_t)(unsigned int)sample_rate;
+    if (mode == PDT_MODE_POES) {                      // POESTIPdemod/main.c:30-104
+        p->chunk = 10000;
+        p->interp = (int)rint(150000.0 / Fs);         // main.c:347
+        p->taps = 26 * p->interp;                     // main.c:348
+        p->max_carrier_dev = 4500.0;
+        p->pll_acq_gain = 127.3240; p->pll_track_gain = 10.3451; p->pll_lock_alpha = 0.3979;
+        p->pll_lock_thresh = 0.08;
+        p->agc_attack = 79.5775; p->agc_decay = 159.1549;
+        p->lpf_fc = 11000.0;
+        p->baud = 8320 * 2 + 0.3;
+        p->gardner_err_lim = 0.1; p->gardner_gain = 3.0;
+        p->manchester_resync = 1.0;                   // main.c:445 passes the literal, not DSP_MCHSTR_RESYNC_LVL
+        strcpy(p->sync_word, "1110110111100010000"); p->sync_len = 19;
+    } else if (mode == PDT_MODE_ARGOS) {              // ARGOSdemod/main.c:27-65
+        p->chunk = 2400;
+        p->interp = 1; p->taps = 50;
+        p->max_carrier_dev = 550.0;
+        p->pll_acq_gain = 16; p->pll_track_gain = 16; p->pll_lock_alpha = 3.1831;
+        p->pll_lock_thresh = 0.1;
+        p->agc_attack = 79.5775; p->agc_decay = 159.1549;
+        p->lpf_fc = 700;
+        p->baud = 400 * 2.0;
+        p->gardner_err_lim = 0.1; p->gardner_gain = 3.0;
+        p->manchester_resync = 0.5;
+        p->squelch_thresh = 0.15;
+        strcpy(p->sync_word, "0001011110000"); p->sync_len = 13;
+    } else return fail(PDT_EINVAL, "unknown mode %d", mode);
+    return PDT_OK;
+}
+
+pdt_ctx *pdt_create(const pdt_params *p, uint32_t max_captures, uint64_t max_samples, uint32_t max_frames)
+{
+    if (!p || !max_captures || !max_samples || !max_frames) { fail(PDT_EINVAL, "bad arguments"); return nullptr; }
+    if (!device_ok()) return nullptr;
+    pdt_ctx *c = new (std::nothrow) pdt_ctx();
+    if (!c) { fail(PDT_ENOMEM, "out of host memory"); return nullptr; }
+    c->params = *p;
+    if (c->params.force_min_interp1 && c->params.mode == PDT_MODE_POES && c->params.interp < 1) {
+        c->params.interp = 1; c->params.taps = 26;
+    }
+    c->max_captures = max_captures; c->max_samples = max_samples; c->max_frames = max_frames;
+    if (build_chain_const(c->params, c->cc) != PDT_OK) { delete c; return nullptr; }
+    c->cc.max_frames = max_frames;
+    auto bail = [&](cudaError_t e, const char *what) -> pdt_ctx * {
+        fail(PDT_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+        pdt_destroy(c);
+        return nullptr;
+    };
+    cudaError_t e;
+    if ((e = cudaGetDevice(&c->device)) != cudaSuccess) return bail(e, "cudaGetDevice");
+    cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device);
+    if (c->cc.L > 0) {
+        const real_t Fs = (real_t)(unsigned int)c->params.sample_rate;
+        if (c->cc.argos) make_lpfir_host(c->taps_h, c->cc.N, (real_t)c->params.lpf_fc, Fs, 1);            // ARGOS main.c:248
+        else             make_lpfir_host(c->taps_h, c->cc.N, (real_t)c->params.lpf_fc, Fs * c->cc.L, c->cc.L);   // main.c:369
+        if ((e = cudaMalloc(&c->d_taps, sizeof(real_t) * c->cc.N)) != cudaSuccess) return bail(e, "cudaMalloc taps");
+        if ((e = cudaMemcpy(c->d_taps, c->taps_h, sizeof(real_t) * c->cc.N, cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "taps H2D");
+        // shared-memory plan
+        int max_optin = 0;
+        cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device);
+        c->smem_bytes = chain_ws_reals(c->cc) * sizeof(real_t);
+        const size_t static_smem = sizeof(ChainState) + sizeof(real_t) * PDT_MAX_TAPS + 1024;
+        c->use_smem = (c->smem_bytes + static_smem <= (size_t)max_optin);
+        int per_sm = 1;
+        if (c->use_smem) {
+            if ((e = cudaFuncSetAttribute(k_chain_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes)) != cudaSuccess)
+                return bail(e, "cudaFuncSetAttribute");
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_chain_exact, CHAIN_THREADS, c->smem_bytes);
+        } else {
+            c->smem_bytes = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_chain_exact, CHAIN_THREADS, 0);
+            per_sm = std::min(per_sm, 4);
+        }
+        if (per_sm < 1) per_sm = 1;
+        c->grid = (int)std::min<uint64_t>(max_captures, (uint64_t)c->sm_count * per_sm);
+        if (!c->use_smem) {
+            c->ws_stride = (chain_ws_reals(c->cc) + 31) & ~(size_t)31;
+            if ((e = cudaMalloc(&c->d_ws, c->ws_stride * sizeof(real_t) * c->grid)) != cudaSuccess) return bail(e, "cudaMalloc workspace");
+        }
+    }
+    if ((e = cudaMalloc(&c->d_stats, sizeof(pdt_capture_stats) * max_captures)) != cudaSuccess) return bail(e, "cudaMalloc stats");
+    if ((e = cudaMalloc(&c->d_frames, sizeof(pdt_frame) * (size_t)max_captures * max_frames)) != cudaSuccess) return bail(e, "cudaMalloc frames");
+    if ((e = cudaMalloc(&c->d_nsamp, sizeof(unsigned long long) * max_captures)) != cudaSuccess) return bail(e, "cudaMalloc nsamp");
+    if ((e = cudaMalloc(&c->d_traces, sizeof(pdt_traces) * max_captures)) != cudaSuccess) return bail(e, "cudaMalloc traces");
+    return c;
+}
+
+void pdt_destroy(pdt_ctx *c)
+{
+    if (!c) return;
+    cudaFree(c->d_taps); cudaFree(c->d_ws); cudaFree(c->d_stats); cudaFree(c->d_frames);
+    cudaFree(c->d_nsamp); cudaFree(c->d_traces); cudaFree(c->d_stage);
+    delete c;
+}
+
+int pdt_get_params(const pdt_ctx *c, pdt_params *out)
+{
+    if (!c || !out) return fail(PDT_EINVAL, "bad arguments");
+    *out = c->params;
+    return PDT_OK;
+}
+
+int pdt_get_taps(const pdt_ctx *c, void *h_out)
+{
+    if (!c || !h_out) return fail(PDT_EINVAL, "bad arguments");
+    memcpy(h_out, c->taps_h, sizeof(real_t) * (size_t)std::max(c->cc.N, 0));
+    return PDT_OK;
+}
+
+int pdt_demod_device(pdt_ctx *c, const void *d_iq, int pcm16, uint32_t n_captures, uint64_t stride_samples,
+                     const uint64_t *n_samples, const pdt_traces *traces, void *stream)
+{
+    if (!c || !d_iq || !n_captures || n_captures > c->max_captures) return fail(PDT_EINVAL, "bad arguments");
+    if (!device_ok()) return PDT_ENODEV;
+    cudaStream_t s = (cudaStream_t)stream;
+    PDT_CUDA(cudaMemsetAsync(c->d_stats, 0, sizeof(pdt_capture_stats) * n_captures, s));
+    PDT_CUDA(cudaMemsetAsync(c->d_frames, 0, sizeof(pdt_frame) * (size_t)n_captures * c->max_frames, s));
+    if (n_samples) {
+        for (uint32_t i = 0; i < n_captures; i++)
+            if (n_samples[i] > c->max_samples || n_samples[i] > stride_samples) return fail(PDT_EINVAL, "capture %u too long", i);
+        PDT_CUDA(cudaMemcpyAsync(c->d_nsamp, n_samples, sizeof(uint64_t) * n_captures, cudaMemcpyHostToDevice, s));
+    } else if (stride_samples > c->max_samples) return fail(PDT_EINVAL, "captures longer than the context allows");
+    if (traces) PDT_CUDA(cudaMemcpyAsync(c->d_traces, traces, sizeof(pdt_traces) * n_captures, cudaMemcpyHostToDevice, s));
+    if (c->cc.L <= 0) {
+        // Fs >= 300 ksps: L = rint(150000/Fs) = 0 and the reference silently emits nothing. Same here.
+        return PDT_OK;
+    }
+    ChainArgs a;
+    a.cc = c->cc; a.taps = c->d_taps; a.iq = d_iq; a.pcm16 = pcm16; a.stride = stride_samples;
+    a.n_samples = n_samples ? c->d_nsamp : nullptr; a.n_uniform = stride_samples; a.n_captures = n_captures;
+    a.workspace = c->d_ws; a.ws_stride = c->ws_stride; a.use_smem = c->use_smem;
+    a.stats = c->d_stats; a.frames = c->d_frames; a.traces = traces ? c->d_traces : nullptr;
+    const int grid = (int)std::min<uint32_t>(n_captures, (uint32_t)c->grid);
+    k_chain_exact<<<grid, CHAIN_THREADS, c->smem_bytes, s>>>(a);
+    count_launch();
+    PDT_CUDA(cudaGetLastError());
+    return PDT_OK;
+}
+
+int pdt_fetch(pdt_ctx *c, uint32_t n_captures, pdt_capture_stats *stats_out, pdt_frame *frames_out, void *stream)
+{
+    if (!c || n_captures > c->max_captures) return fail(PDT_EINVAL, "bad arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (stats_out) PDT_CUDA(cudaMemcpyAsync(stats_out, c->d_stats, sizeof(pdt_capture_stats) * n_captures, cudaMemcpyDeviceToHost, s));
+    if (frames_out) PDT_CUDA(cudaMemcpyAsync(frames_out, c->d_frames, sizeof(pdt_frame) * (size_t)n_captures * c->max_frames, cudaMemcpyDeviceToHost, s));
+    PDT_CUDA(cudaStreamSynchronize(s));
+    return PDT_OK;
+}
+
+int pdt_result_tables(pdt_ctx *c, void **d_stats, void **d_frames, uint32_t *max_frames)
+{
+    if (!c) return fail(PDT_EINVAL, "bad arguments");
+    if (d_stats) *d_stats = c->d_stats;
+    if (d_frames) *d_frames = c->d_frames;
+    if (max_frames) *max_frames = c->max_frames;
+    return PDT_OK;
+}
+
+int pdt_demod_host(pdt_ctx *c, const void *h_iq, int pcm16, uint32_t n_captures, uint64_t stride_samples,
+                   const uint64_t *n_samples, pdt_capture_stats *stats_out, pdt_frame *frames_out)
+{
+    if (!c || !h_iq) return fail(PDT_EINVAL, "bad arguments");
+    if (!device_ok()) return PDT_ENODEV;
+    const size_t elem = pcm16 ? 2 * sizeof(int16_t) : 2 * sizeof(real_t);
+    const size_t bytes = elem * stride_samples * n_captures;
+    if (bytes > c->stage_bytes) {
+        cudaFree(c->d_stage); c->d_stage = nullptr; c->stage_bytes = 0;
+        PDT_CUDA(cudaMalloc(&c->d_stage, bytes));
+        c->stage_bytes = bytes;
+    }
+    PDT_CUDA(cudaMemcpyAsync(c->d_stage, h_iq, bytes, cudaMemcpyHostToDevice, 0));
+    int rc = pdt_demod_device(c, c->d_stage, pcm16, n_captures, stride_samples, n_samples, nullptr, nullptr);
+    if (rc != PDT_OK) return rc;
+    return pdt_fetch(c, n_captures, stats_out, frames_out, nullptr);
+}
+
+long pdt_format_frames(const pdt_ctx *c, const pdt_frame *frames, uint32_t n_frames, char *buf, size_t cap)
+{
+    if (!c || !frames || !buf) return fail(PDT_EINVAL, "bad arguments");
+    // time column: wave.c:91-167 accumulates `time += Ts` in DECIMAL_TYPE per sample; emulate up to the last frame.
+    const ChainConst &cc = c->cc;
+    const int L = cc.L > 0 ? cc.L : 1;
+    std::vector<uint64_t> want(n_frames);
+    uint64_t last = 0;
+    for (uint32_t i = 0; i < n_frames; i++) {
+        uint64_t in_idx = frames[i].sample_index / L;
+        // POES: LowPassFilterInterp hands out the NEXT input's time (LowPassFilter.c:68); ARGOS passes waveDataTime through.
+        want[i] = cc.argos ? in_idx : in_idx + 1;
+        last = std::max(last, want[i]);
+    }
+    std::vector<real_t> tval(n_frames, 0);
+    {
+        std::vector<uint32_t> order(n_frames);
+        for (uint32_t i = 0; i < n_frames; i++) order[i] = i;
+        std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return want[a] < want[b]; });
+        real_t t = 0; const real_t Ts = 1.0 / (real_t)(unsigned int)c->params.sample_rate;
+        uint64_t g = 0; size_t oi = 0;
+        while (oi < order.size()) {
+            const uint64_t target = want[order[oi]];
+            while (g <= target) { t += Ts; g++; }          // sample g (0-based) carries the time after g+1 additions
+            tval[order[oi]] = t; oi++;
+        }
+    }
+    size_t pos = 0;
+    auto put = [&](const char *fmt, auto v) {
+        if (pos < cap) { int k = snprintf(buf + pos, cap - pos, fmt, v); if (k > 0) pos += (size_t)k; }
+    };
+    for (uint32_t i = 0; i < n_frames; i++) {
+        const pdt_frame &f = frames[i];
+        put(f.inverse ? "%.5fi " : "%.5f ", (double)tval[i]);
+        for (int b = 0; b < f.n_bytes; b++) put("%.2X ", (unsigned)f.bytes[b]);
+        if (f.complete) put("%s", "\n");
+    }
+    if (pos >= cap) return fail(PDT_EINVAL, "buffer too small");
+    buf[pos] = 0;
+    return (long)pos;
+}
+
+int pdt_synth_poes_device(void *d_iq, int pcm16, uint32_t n_captures, uint64_t stride_samples, uint64_t n_samples,
+                          double sample_rate, uint64_t seed, void *stream)
+{
+    if (!d_iq || !n_captures || n_samples > stride_samples) return fail(PDT_EINVAL, "bad arguments");
+    if (!device_ok()) return PDT_ENODEV;
+    return synth_poes_launch(d_iq, pcm16, n_captures, stride_samples, n_samples, sample_rate, seed, (cudaStream_t)stream);
+}
+
+} // extern "C"

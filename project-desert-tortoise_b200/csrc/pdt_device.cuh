@@ -1,0 +1,364 @@
+// pdt_device.cuh — device-side stage state and EXACT-ORDER stage arithmetic (sm_100a).
+//
+// Every function here reproduces the floating-point operation order of the reference stage it cites
+// (file:line relative to the reference repo), so that with -fmad=false the float build is bit-identical
+// to the reference compiled with -O2 -ffp-contract=off on x86-64.  The fast block-parallel
+// reformulations live in pdt_parallel.cuh and are validated against these.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#ifndef PDT_USE_FLOATS
+#define PDT_USE_FLOATS 1
+#endif
+#if PDT_USE_FLOATS
+typedef float real_t;
+#else
+typedef double real_t;
+#endif
+
+#define PDT_PI 3.14159265358979323846
+#define PDT_MAX_TAPS 1024
+#define PDT_MAX_PHASE_TAPS 64   // taps per polyphase branch (N / L); the reference uses 26 (main.c:104) or 50
+
+#define PDT_DEV __device__ __forceinline__
+
+// ---------------------------------------------------------------------------------------------------
+// small overload helpers
+// ---------------------------------------------------------------------------------------------------
+PDT_DEV float  r_fabs(float x)  { return fabsf(x); }
+PDT_DEV double r_fabs(double x) { return fabs(x); }
+PDT_DEV float  r_rint(float x)  { return rintf(x); }
+PDT_DEV double r_rint(double x) { return rint(x); }
+
+// ---------------------------------------------------------------------------------------------------
+// sinf/cosf that match glibc >= 2.28 bit for bit (float build).
+// glibc's sinf/cosf (sysdeps/ieee754/flt-32/s_sincosf.h, from ARM Optimized Routines) evaluate a short
+// double-precision polynomial after a fast quadrant reduction and round once to float.  The algorithm
+// and its published constants are restated here; double arithmetic on the GPU is IEEE, so the result
+// equals the host libm's for |x| < 120 (the PLL phase lives in [-2π, 2π]).  tests/test_gpu_parity.py
+// checks this against the oracle over the whole phase range.
+// ---------------------------------------------------------------------------------------------------
+struct SinCosTab { double c0, c1, c2, c3, c4, s1, s2, s3; };
+
+PDT_DEV double sc_poly(double x, double x2, double flip, int n)
+{
+    // flip = +1 (quadrants 0,1) or -1 (quadrants 2,3): negates the cosine coefficients only
+    const double s1 = -0x1.555545995a603p-3, s2 = 0x1.1107605230bc4p-7, s3 = -0x1.994eb3774cf24p-13;
+    const double c0 = 0x1p0, c1 = -0x1.ffffffd0c621cp-2, c2 = 0x1.55553e1068f19p-5,
+                 c3 = -0x1.6c087e89a359dp-10, c4 = 0x1.99343027bf8c3p-16;
+    if ((n & 1) == 0) {
+        double x3 = x * x2;
+        double t1 = s2 + x2 * s3;
+        double x7 = x3 * x2;
+        double s  = x + x3 * s1;
+        return s + x7 * t1;
+    } else {
+        double x4 = x2 * x2;
+        double t2 = (flip * c3) + x2 * (flip * c4);
+        double t1 = (flip * c0) + x2 * (flip * c1);
+        double x6 = x4 * x2;
+        double c  = t1 + x4 * (flip * c2);
+        return c + x6 * t2;
+    }
+}
+
+PDT_DEV uint32_t abstop12(float x) { return (__float_as_uint(x) >> 20) & 0x7ffu; }
+
+PDT_DEV void sincos_exact(float y, float &s, float &c)
+{
+    double x = (double)y;
+    if (abstop12(y) < 0x3f4u) {                 // |y| < top12(pi/4)
+        double x2 = x * x;
+        if (abstop12(y) < 0x398u) { s = y; c = 1.0f; return; }      // |y| < 2^-12
+        s = (float)sc_poly(x, x2, 1.0, 0);
+        c = (float)sc_poly(x, x2, 1.0, 1);
+        return;
+    }
+    if (abstop12(y) < 0x42fu) {                 // |y| < 120
+        const double hpi_inv = 0x1.45F306DC9C883p+23, hpi = 0x1.921FB54442D18p0;
+        double r = x * hpi_inv;
+        int n = (__double2int_rz(r) + 0x800000) >> 24;
+        x = x - (double)n * hpi;
+        const double sgn  = ((n & 3) == 0 || (n & 3) == 3) ? 1.0 : -1.0;
+        const double flip = (n & 2) ? -1.0 : 1.0;
+        const double xs = x * sgn, x2 = x * x;
+        s = (float)sc_poly(xs, x2, flip, n);
+        c = (float)sc_poly(xs, x2, flip, n ^ 1);
+        return;
+    }
+    s = sinf(y); c = cosf(y);                   // never reached by the PLL (phase is wrapped to ±2π)
+}
+PDT_DEV void sincos_exact(double y, double &s, double &c) { sincos(y, &s, &c); }
+
+// hypot as glibc's cabsf()/cabs() compute it (AGC.c:58,66)
+PDT_DEV float  hypot_exact(float re, float im)  { return (float)sqrt((double)re * (double)re + (double)im * (double)im); }
+PDT_DEV double hypot_exact(double re, double im)
+{
+    // sqrt(x²+y²) with one exact-residual correction step (error < 0.51 ulp, like glibc's hypot)
+    double ax = fabs(re), ay = fabs(im);
+    if (ax < ay) { double t = ax; ax = ay; ay = t; }
+    if (ay == 0.0) return ax;
+    double h  = sqrt(fma(ax, ax, ay * ay));
+    double h2 = h * h, hx = fma(h, h, -h2);
+    double x2 = ax * ax, xx = fma(ax, ax, -x2);
+    double y2 = ay * ay, yy = fma(ay, ay, -y2);
+    double res = ((x2 - h2) + y2) + ((xx + yy) - hx);
+    return h + res / (2.0 * h);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// CarrierTrackingPLL.c:15-40 (first-order atan2) and :43-52 (Q_rsqrt)
+// ---------------------------------------------------------------------------------------------------
+PDT_DEV real_t arctan2_approx(real_t y, real_t x)
+{
+    real_t abs_y = r_fabs(y) + 1e-10;                 // double add, narrowed (:21)
+    real_t r, angle;
+    if (x >= 0) { r = (x - abs_y) / (x + abs_y); angle = 0.78539816339744825 - 0.78539816339744825 * r; }
+    else        { r = (x + abs_y) / (abs_y - x); angle = 2.35619449019234475 - 0.78539816339744825 * r; }
+    return (y < 0) ? -angle : angle;
+}
+
+PDT_DEV float q_rsqrt(float x)
+{
+    float half = 0.5f * x;
+    int bits = __float_as_int(x);
+    bits = 0x5f3759df - (bits >> 1);
+    x = __int_as_float(bits);
+    x = x * (1.5f - half * x * x);
+    x = x * (1.5f - half * x * x);
+    return x;
+}
+
+PDT_DEV int sign_of(real_t x) { return (x > 0) - (x < 0); }
+
+// ---------------------------------------------------------------------------------------------------
+// PLL — CarrierTrackingPLL.c:54-278
+// ---------------------------------------------------------------------------------------------------
+struct PllParams { real_t Fs, freq_range, lock_thresh, lock_alpha, bw_acq, bw_track; };
+
+struct PllState {
+    int      stage;          // 0 = uninitialised (firstLock==-2), 1 = searching (-1), 2 = locked
+    real_t   damp, alpha, beta, phase, freq, max_freq, min_freq, avg_phase, locksig, sweep;
+    double   lock_freq_hz;
+    unsigned long long samples_seen, lock_sample;
+    int      lock_event;     // set when the latch fires during the current call (host prints the message)
+};
+
+PDT_DEV void pll_reset(PllState &s) { s = PllState(); s.damp = 0.999; }
+
+PDT_DEV void pll_begin(PllState &s, const PllParams &p)
+{
+    if (s.stage != 0) return;                            // :88-100
+    const real_t bw = p.bw_acq;
+    s.alpha = (4 * s.damp * bw) / (1 + 2 * s.damp * bw + bw * bw);
+    s.beta  = (4 * bw * bw) / (1 + 2 * s.damp * bw + bw * bw);
+    s.phase = 0.1;
+    s.freq  = 2.0 * PDT_PI * 0 / p.Fs;
+    s.max_freq = 2.0 * PDT_PI * p.freq_range / p.Fs;
+    s.min_freq = -2.0 * PDT_PI * p.freq_range / p.Fs;
+    s.stage = 1;
+    s.avg_phase = PDT_PI / 2.0;
+    s.sweep = 0.2 * (2.0 * PDT_PI / p.Fs);
+}
+
+// one sample; `abs_index` = absolute sample index (for the lock record)
+PDT_DEV void pll_step(PllState &s, const PllParams &p, real_t a, real_t b, real_t &out, real_t &lock,
+                      unsigned long long abs_index)
+{
+    const real_t avg_alpha = 0.00005;
+    real_t ti, tr;
+    sincos_exact(s.phase, ti, tr);                       // :106-107
+    const real_t nti = -ti;
+    const real_t mre = a * tr - b * nti;                 // :110, four separately rounded products
+    const real_t mim = a * nti + b * tr;
+    out = mim;                                           // :113
+
+    const real_t out_phase = arctan2_approx(mim, mre);   // :117
+    s.avg_phase = s.avg_phase * (1.0 - avg_alpha) + avg_alpha * r_fabs(out_phase);   // :124
+
+    const real_t sample_phase = arctan2_approx(b, a);    // :128
+    real_t err;                                          // :165-170
+    if ((sample_phase - s.phase) > PDT_PI)        err = (sample_phase - s.phase) - 2 * PDT_PI;
+    else if ((sample_phase - s.phase) < -PDT_PI)  err = (sample_phase - s.phase) + 2 * PDT_PI;
+    else                                          err = sample_phase - s.phase;
+
+    s.freq  = s.freq + s.beta * err;                     // :174
+    s.phase = s.phase + s.freq + s.alpha * err;          // :175
+    while (s.phase > 2 * PDT_PI)  s.phase = s.phase - 2.0 * PDT_PI;    // :178-182
+    while (s.phase < -2 * PDT_PI) s.phase = s.phase + 2.0 * PDT_PI;
+    if (s.freq > s.max_freq)      s.freq = s.max_freq;   // :185-188
+    else if (s.freq < s.min_freq) s.freq = s.min_freq;
+
+    real_t nre = a, nim = b;                             // :193-220
+    const real_t mag2 = nre * nre + nim * nim;
+    const real_t inv  = q_rsqrt((float)mag2);
+    nre *= inv; nim *= inv;
+    s.locksig = s.locksig * (1.0 - p.lock_alpha) + p.lock_alpha * (nre * tr + nim * ti);
+    lock = s.locksig;
+
+#if PDT_USE_FLOATS
+    const bool noise_like = fabsf((float)(PDT_PI / 2.0 - s.avg_phase)) < 0.05;      // :232
+#else
+    const bool noise_like = fabs(PDT_PI / 2.0 - s.avg_phase) < 0.05;                // :248
+#endif
+    if (noise_like && s.stage == 1) {
+        s.freq = s.freq + s.sweep;
+        if (s.freq >= s.max_freq)       s.sweep = s.sweep * -1.0;
+        else if (s.freq <= s.min_freq)  s.sweep = s.sweep * -1.0;
+        else if (s.freq >= 0)           s.sweep = r_fabs(s.sweep);
+        else                            s.sweep = r_fabs(s.sweep) * -1.0;
+    }
+    if (s.locksig > p.lock_thresh && s.stage == 1) {     // :266-274
+        s.lock_freq_hz = s.freq * p.Fs / (2.0 * PDT_PI);
+        s.stage = 2;
+        s.lock_sample = abs_index;
+        s.lock_event = 1;
+        const real_t bw = p.bw_track;
+        s.alpha = (4.0 * s.damp * bw) / (1.0 + 2.0 * s.damp * bw + bw * bw);
+        s.beta  = (4.0 * bw * bw) / (1.0 + 2.0 * s.damp * bw + bw * bw);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// AGC — AGC.c:78-132 (NormalizingAGC), :48-75 (StaticGain)
+// ---------------------------------------------------------------------------------------------------
+struct AgcState { int init; real_t gain; };
+
+PDT_DEV real_t agc_step(AgcState &s, real_t x, real_t attack, real_t decay)
+{
+    const real_t reference = 1.0, max_gain = 5000;
+    x *= s.gain;
+    real_t err  = r_fabs(x) - reference;
+    real_t rate = decay;
+    if (r_fabs(err) > s.gain) rate = attack;
+    s.gain -= err * rate;
+    if (s.gain < 0.0) s.gain = 10e-5;
+    if (max_gain > 0.0 && s.gain > max_gain) s.gain = max_gain;
+    return x;
+}
+
+PDT_DEV real_t static_gain_serial(const real_t *iq, unsigned long long n, real_t desired)
+{
+    real_t level = hypot_exact(iq[0], iq[1]);
+    for (unsigned long long i = 0; i < n; i++) {
+        level += hypot_exact(iq[2 * i], iq[2 * i + 1]);
+        level /= 2.0;
+    }
+    return desired / level;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// FIR — LowPassFilter.c:13-71 (zero-stuffing interpolator) and :76-125 (plain)
+//
+// The reference keeps an N-slot ring and, for every output t (global counter), sums only the slots
+// that hold real samples, IN RING-SLOT ORDER.  Restated without the ring: with p = t mod L,
+// j = t div L (index of the newest real sample) and K = N/L taps per branch,
+//     y[t] = Σ_k h[N-1-p-kL] · x[j-k]   summed in the order k = k0, k0-1, …, 0, K-1, …, k0+1,  k0 = j mod K
+// starting from +0 (x[<0] = 0).  `xh` points at x[j] inside a buffer that has K-1 history samples
+// in front of it.
+// ---------------------------------------------------------------------------------------------------
+PDT_DEV real_t fir_interp_exact(const real_t *__restrict__ h, const real_t *__restrict__ xh, int N, int L, int K,
+                                int p, int k0)
+{
+    real_t acc = 0;
+    const real_t *hp = h + (N - 1 - p);
+    for (int k = k0; k >= 0; k--)      acc += hp[-k * L] * xh[-k];
+    for (int k = K - 1; k > k0; k--)   acc += hp[-k * L] * xh[-k];
+    return acc;
+}
+
+// plain FIR: y = Σ_{k=0}^{N-1} h[k]·x[o-(N-1)+k], oldest first (:113-116); xh points at x[o]
+PDT_DEV real_t fir_plain_exact(const real_t *__restrict__ h, const real_t *__restrict__ xh, int N)
+{
+    real_t acc = 0;
+    for (int k = 0; k < N; k++) acc += h[k] * xh[k - (N - 1)];
+    return acc;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Gardner — GardenerClockRecovery.c:5-114 ; Manchester — ManchesterDecode.c:10-100
+// ---------------------------------------------------------------------------------------------------
+struct GardnerState { int init; real_t next, prev, half, step; };
+struct ManchesterState { unsigned clockmod; real_t cur, prev, prevprev; unsigned char even_odd; };
+
+PDT_DEV void gardner_begin(GardnerState &s, int Fs, real_t baud) { if (!s.init) { s.step = Fs / baud; s.init = 1; } }
+
+// one symbol; returns the picked index, symbol value in `sym`, clamped error in `err`
+PDT_DEV unsigned gardner_step(GardnerState &s, const real_t *x, real_t range, real_t kp, real_t &sym, real_t &err)
+{
+    const unsigned at = (unsigned)(r_rint(s.next));
+    const real_t cur = x[at];
+    s.half = x[(unsigned)(r_rint(s.half))];              // index-then-value reuse (:28)
+    real_t e = kp * (cur - s.prev) * (s.half);           // :43
+    if (e > range) e = range; else if (e < -range) e = -range;
+    s.next = (s.next - e);
+    s.half = s.next + s.step / 2.0;                      // :59
+    s.next = s.next + s.step;
+    s.prev = cur;
+    sym = cur; err = e;
+    return at;
+}
+
+// one symbol; returns 1 and sets `bit` ('0'/'1') when a bit is produced
+PDT_DEV int manchester_step(ManchesterState &s, real_t v, real_t thresh, unsigned char &bit)
+{
+    int produced = 0;
+    s.prevprev = s.prev; s.prev = s.cur; s.cur = v;
+    if ((unsigned)(s.even_odd % 2) != s.clockmod) {
+        if (sign_of(s.prevprev) == sign_of(s.prev))
+            if (r_fabs(s.prevprev) > thresh && r_fabs(s.prev) > thresh) s.clockmod = (s.even_odd % 2);
+    }
+    if ((unsigned)(s.even_odd % 2) == s.clockmod) {
+        if (r_fabs(s.prev) > r_fabs(s.cur)) bit = (s.prev > 0) ? '1' : '0';
+        else                                 bit = (s.cur > 0) ? '0' : '1';
+        produced = 1;
+    }
+    s.even_odd++;
+    return produced;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// ByteSync — POESTIPdemod/ByteSync.c:16-150, ARGOSdemod/ByteSync.c:17-150
+// The circular ASCII history is restated as a 32-bit shift register (newest bit = LSB); a sync hit is
+// (hist & mask) == word, the inverse hit (~hist & mask) == word.
+// ---------------------------------------------------------------------------------------------------
+struct SyncParams {
+    uint32_t word, mask; int len;
+    int last_idx;        // 103 (POES) / 8 (ARGOS): frame ends when frame_byte_idx > last_idx
+    int carry_bits;      // bitIdx after accept: 3 (POES: 19 = 16 + 3) / 0 (ARGOS)
+    int inverse_enabled; // POES 1 / ARGOS 0 (:115)
+};
+struct SyncState { uint32_t hist; int in_frame, frame_byte_idx, bit_idx; unsigned char zero, one, byte; };
+
+enum { EV_NONE = 0, EV_SYNC = 1, EV_SYNC_INV = 2 };
+
+// one bit; returns EV_* for an accepted sync; `emit` = 1 when a byte was completed (value in out_byte),
+// `eol` = 1 when that byte closed the frame.  Byte emission precedes sync detection, as in the reference.
+PDT_DEV int sync_step(SyncState &s, const SyncParams &p, unsigned char bit, int &emit, unsigned char &out_byte, int &eol)
+{
+    emit = 0; eol = 0;
+    if (s.in_frame == 1) {
+        s.byte = (unsigned char)(s.byte << 1);
+        s.byte |= (bit == '0') ? s.zero : s.one;
+        s.bit_idx++;
+        if (s.bit_idx > 7) {
+            emit = 1; out_byte = s.byte;
+            s.byte = 0; s.bit_idx = 0; s.frame_byte_idx++;
+            if (s.frame_byte_idx > p.last_idx) { s.in_frame = 0; eol = 1; }
+        }
+    }
+    s.hist = (s.hist << 1) | (uint32_t)(bit != '0');     // anything that is not '0' compares unequal to '0'
+    int ev = EV_NONE;
+    // NB: a non-'0'/'1' byte can never equal a sync character; '0'/'1' streams are all the chain produces.
+    if (((s.hist & p.mask) == p.word) && s.in_frame == 0) {
+        s.frame_byte_idx = 2; s.in_frame = 1; s.bit_idx = p.carry_bits; s.byte = 0; s.zero = 0; s.one = 1;
+        ev = EV_SYNC;
+    }
+    if (p.inverse_enabled && ((~s.hist & p.mask) == p.word) && s.in_frame == 0) {
+        s.frame_byte_idx = 2; s.in_frame = 1; s.bit_idx = p.carry_bits; s.byte = 0; s.zero = 1; s.one = 0;
+        ev = EV_SYNC_INV;
+    }
+    return ev;
+}

@@ -76,14 +76,14 @@ def make_poes_capture(n_samples: int, fs: float, seed: int, esn0_db: float = 12.
     rng = np.random.default_rng(seed)
     sps = fs / chip_rate
     n_chips = int(np.ceil(n_samples / sps)) + 4
-    n_frames = n_chips // (2 * 8 * FRAME_BYTES) + 2
+    n_frames = n_chips // (2 * 8 * FRAME_BYTES) + 4
     if counter0 is None:
         counter0 = int(rng.integers(0, 320))
     frames = tip_frames(n_frames, seed + 1000003, spacecraft, counter0)
     bits = frames_to_bits(frames)
-    # random frame phase so that captures do not all start on a frame boundary
-    start = int(rng.integers(0, bits.size // 2))
-    bits = np.roll(bits, -start)
+    # random frame phase so that captures do not all start on a frame boundary (counter stays continuous)
+    start = int(rng.integers(0, 2 * 8 * FRAME_BYTES))
+    bits = bits[start:]
     chips = np.empty(2 * bits.size, np.int8)
     chips[0::2] = np.where(bits == 1, 1, -1)
     chips[1::2] = -chips[0::2]

@@ -1,0 +1,325 @@
+"""GPU parity tests proper (run on the B200 box: pytest -m gpu).  Everything goes through the C-ABI of
+libpdt_f32.so / libpdt_f64.so and is compared with the CPU oracle on the same inputs, and with the golden
+vectors generated from the unmodified reference.  /root/reference is NOT needed here.
+
+Tolerances: integer / byte / index outputs are bit-exact.  The float (POES) exact-order path is bit-exact at
+every stage (the kernels restate glibc's sinf/cosf and never contract FMAs).  The double (ARGOS) path uses
+CUDA's sin/cos (<= 2 ulp from glibc), so its PLL output is compared with rtol 1e-12 and everything decided
+downstream (symbol picks, bits, packets) is bit-exact on the fixtures.
+"""
+import ctypes as C
+import importlib
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import pyoracle as po
+from tests.synth_ref import check_parity, frame_counter, make_argos_capture, make_poes_capture, parse_frames_text
+
+pdt = importlib.import_module("project-desert-tortoise_b200")
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TWO_PI = 2.0 * np.pi
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "these tests need a CUDA device"
+    return torch
+
+
+def _golden(golden_dir, name):
+    return os.path.join(golden_dir, name)
+
+
+def _frames_text_equal_bytes(text_a, text_b):
+    a, b = parse_frames_text(text_a), parse_frames_text(text_b)
+    assert len(a) == len(b)
+    for x, y in zip(a, b):
+        assert x[1] == y[1] and np.array_equal(x[2], y[2])
+
+
+class DevTraces:
+    """Device trace taps for one capture, allocated with torch."""
+
+    def __init__(self, torch, dt, n, L, cap):
+        self.torch, self.dt = torch, dt
+        tdt = torch.float32 if dt == np.float32 else torch.float64
+        z = lambda m, t=tdt: torch.zeros(m, dtype=t, device="cuda")
+        self.t = dict(pll_phase=z(n), pll_freq=z(n), pll_out=z(n), lock=z(n), lpf=z(n * L), agc=z(n * L), sym=z(cap),
+                      gardner_err=z(cap), gardner_idx=z(cap, torch.int64), bits=z(cap, torch.uint8))
+        self.cap = cap
+
+    def struct(self):
+        s = pdt.Traces()
+        for k, v in self.t.items():
+            setattr(s, k, v.data_ptr())
+        s.cap = self.cap
+        return s
+
+    def host(self, k, n=None):
+        a = self.t[k].cpu().numpy()
+        return a if n is None else a[:n]
+
+
+def _run_batch_with_traces(torch, prec, mode, fs, iq, chunk=None, force_l1=False):
+    p = pdt.default_params(prec, mode, fs)
+    if chunk:
+        p.chunk = chunk
+    p.force_min_interp1 = int(force_l1)
+    dt = np.float32 if prec == "f32" else np.float64
+    iq = np.ascontiguousarray(iq, dt)
+    n = iq.size // 2
+    d = pdt.Demod(prec, p, 1, n, 128)
+    L = max(d.params.interp, 1)
+    cap = n * L // 4 + 64
+    tr = DevTraces(torch, dt, n, L, cap)
+    d_iq = torch.from_numpy(iq).cuda()
+    d.demod_device(d_iq.data_ptr(), 1, n, traces=[tr.struct()])
+    stats, frames = d.fetch(1)
+    return d, stats[0], frames[0], tr
+
+
+# ------------------------------------------------------------------------------------------------------
+# whole chain, batch API, with every intermediate stream compared against the oracle
+# ------------------------------------------------------------------------------------------------------
+def test_poes_5sec_clip_bit_exact_all_stages(torch_cuda, oracle32, golden_dir):
+    rate, pcm = po.read_wav_pcm16(_golden(golden_dir, "5sec_clip.wav"))
+    iq = oracle32.pcm16_to_complex(pcm)
+    want = oracle32.chain(iq, rate, trace=True)
+    d, st, fr, tr = _run_batch_with_traces(torch_cuda, "f32", pdt.PDT_MODE_POES, rate, iq)
+    assert (st["n_symbols"], st["n_bits"], st["n_frames"]) == (want["total_symbols"], want["total_bits"], want["total_frames"])
+    assert st["locked"] == 1 and st["lock_sample"] == want["lock_sample"]
+    assert np.float32(st["norm_factor"]) == np.float32(want["norm_factor"])
+    ns, nb = int(st["n_symbols"]), int(st["n_bits"])
+    for k_dev, k_or in (("pll_phase", "tr_phase"), ("pll_freq", "tr_freq"), ("pll_out", "tr_pll_out"), ("lpf", "tr_lpf"),
+                        ("agc", "tr_agc")):
+        assert np.array_equal(tr.host(k_dev), want[k_or]), k_dev
+    assert np.array_equal(tr.host("sym", ns), want["tr_sym"])
+    assert np.array_equal(tr.host("gardner_err", ns), want["tr_gerr"])
+    assert np.array_equal(tr.host("gardner_idx", ns).astype(np.uint64), want["tr_gidx"])
+    assert np.array_equal(tr.host("bits", nb), want["tr_bits"])
+    # frame bytes + the time column against the file the unmodified reference wrote
+    text = d.format_frames(fr, int(st["n_frames"]))
+    golden = open(_golden(golden_dir, "poes_5sec_clip_frames.txt")).read()
+    _frames_text_equal_bytes(text, golden)
+    assert text == golden
+    meta = json.load(open(_golden(golden_dir, "cli_meta.json")))
+    assert f"{st['lock_freq_hz']:.2f}" == f"{meta['poes_lock_hz']:.2f}"
+
+
+def test_poes_pcm16_ingest_equals_float_ingest(torch_cuda, golden_dir):
+    """int16 PCM straight from the WAV data chunk (4 B/sample) must give the same frames as normalised floats."""
+    rate, pcm = po.read_wav_pcm16(_golden(golden_dir, "5sec_clip.wav"))
+    p = pdt.default_params("f32", pdt.PDT_MODE_POES, rate)
+    d = pdt.Demod("f32", p, 1, pcm.size // 2, 64)
+    st, fr = d.demod_host(pcm, 1, pcm16=True)
+    text = d.format_frames(fr[0], int(st[0]["n_frames"]))
+    assert text == open(_golden(golden_dir, "poes_5sec_clip_frames.txt")).read()
+
+
+def test_argos_wav_packets(torch_cuda, oracle64, golden_dir):
+    rate, pcm = po.read_wav_pcm16(_golden(golden_dir, "argos_401650kHz.wav"))
+    iq = oracle64.pcm16_to_complex(pcm)
+    want = oracle64.chain(iq, rate, argos=True, trace=True)
+    d, st, fr, tr = _run_batch_with_traces(torch_cuda, "f64", pdt.PDT_MODE_ARGOS, rate, iq)
+    text = d.format_frames(fr, int(st["n_frames"]))
+    golden = open(_golden(golden_dir, "argos_packets.txt")).read()
+    _frames_text_equal_bytes(text, golden)
+    assert text == golden
+    assert (st["n_symbols"], st["n_bits"], st["n_frames"]) == (want["total_symbols"], want["total_bits"], want["total_frames"])
+    assert st["lock_sample"] == want["lock_sample"]
+    ns, nb = int(st["n_symbols"]), int(st["n_bits"])
+    # double path: CUDA sin/cos vs glibc differ by <= 2 ulp -> tolerance on the analogue streams, exact decisions
+    np.testing.assert_allclose(tr.host("pll_out"), want["tr_pll_out"], rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(tr.host("pll_phase"), want["tr_phase"], rtol=1e-12, atol=1e-15)
+    np.testing.assert_allclose(tr.host("agc"), want["tr_agc"], rtol=1e-9, atol=1e-12)
+    assert np.array_equal(tr.host("gardner_idx", ns).astype(np.uint64), want["tr_gidx"])
+    assert np.array_equal(tr.host("bits", nb), want["tr_bits"])
+
+
+@pytest.mark.parametrize("fs,chunk,seed", [(250000, 10000, 7), (250000, 4096, 8), (50000, 10000, 9), (18750, 10000, 10)])
+def test_poes_synthetic_vs_oracle(torch_cuda, oracle32, fs, chunk, seed):
+    """L = 1 / 3 / 8 (the historical 8x interpolator), ragged last chunk, non-default chunk length."""
+    pcm, info = make_poes_capture(int(1.3 * fs) + 123, fs, seed, esn0_db=11.0, doppler_hz=-2000.0 + 300 * seed)
+    iq = oracle32.pcm16_to_complex(pcm)
+    want = oracle32.chain(iq, fs, chunk=chunk, trace=True)
+    d, st, fr, tr = _run_batch_with_traces(torch_cuda, "f32", pdt.PDT_MODE_POES, fs, iq, chunk=chunk)
+    assert d.params.interp == {250000: 1, 50000: 3, 18750: 8}[fs]
+    assert want["total_frames"] >= 8
+    ns, nb = int(st["n_symbols"]), int(st["n_bits"])
+    assert (ns, nb, st["n_frames"]) == (want["total_symbols"], want["total_bits"], want["total_frames"])
+    assert np.array_equal(tr.host("pll_out"), want["tr_pll_out"])
+    assert np.array_equal(tr.host("agc"), want["tr_agc"])
+    assert np.array_equal(tr.host("gardner_idx", ns).astype(np.uint64), want["tr_gidx"])
+    assert np.array_equal(tr.host("bits", nb), want["tr_bits"])
+    text = d.format_frames(fr, int(st["n_frames"]))
+    _frames_text_equal_bytes(text, want["text"])
+    full = [f for f in parse_frames_text(text) if f[2].size == 104]
+    cnt = [frame_counter(f[2]) for f in full]
+    if fs >= 50000:        # at 18.75 ksps (1.13 samples per chip before the 8x interpolator) the link itself makes bit errors
+        assert all((b - a) % 320 == 1 for a, b in zip(cnt, cnt[1:]))
+        assert sum(check_parity(f[2]) for f in full) >= len(full) - 1
+
+
+def test_poes_golden_synth_c2(torch_cuda, golden_dir):
+    g = np.load(_golden(golden_dir, "synth_poes_c2_small.npz"))
+    p = pdt.default_params("f32", pdt.PDT_MODE_POES, int(g["fs"]))
+    d = pdt.Demod("f32", p, 1, g["pcm"].size // 2, 64)
+    st, fr = d.demod_host(g["pcm"], 1, pcm16=True)
+    assert d.format_frames(fr[0], int(st[0]["n_frames"])) == str(g["frames_text"])
+
+
+def test_batch_many_ragged_captures(torch_cuda, oracle32):
+    """Several independent captures of different length / Doppler / SNR in ONE launch; empty tail capture too."""
+    fs = 250000
+    lens = [260000, 123457, 10000, 9999, 300001, 64]
+    stride = max(lens)
+    pcm = np.zeros((len(lens), stride, 2), np.int16)
+    texts = []
+    for c, n in enumerate(lens):
+        x, _ = make_poes_capture(n, fs, 100 + c, esn0_db=9.0 + 2 * c, doppler_hz=-3000.0 + 1100 * c, amplitude=0.08 + 0.07 * c)
+        pcm[c, :n] = x.reshape(-1, 2)
+        texts.append(oracle32.chain(oracle32.pcm16_to_complex(x), fs))
+    p = pdt.default_params("f32", pdt.PDT_MODE_POES, fs)
+    d = pdt.Demod("f32", p, len(lens), stride, 64)
+    st, fr = d.demod_host(pcm, len(lens), pcm16=True, n_samples=lens)
+    for c, n in enumerate(lens):
+        w = texts[c]
+        assert (st[c]["n_samples"], st[c]["n_symbols"], st[c]["n_bits"], st[c]["n_frames"]) == \
+            (n, w["total_symbols"], w["total_bits"], w["total_frames"]), c
+        _frames_text_equal_bytes(d.format_frames(fr[c], int(st[c]["n_frames"])), w["text"])
+
+
+def test_l0_reference_emits_nothing_and_declared_deviation(torch_cuda, oracle32):
+    rng = np.random.default_rng(0)
+    pcm, _ = make_poes_capture(400000, 2_000_000, 3, esn0_db=14.0, doppler_hz=900.0)
+    p = pdt.default_params("f32", pdt.PDT_MODE_POES, 2_000_000)
+    d = pdt.Demod("f32", p, 1, 400000, 16)
+    st, fr = d.demod_host(pcm, 1, pcm16=True)
+    assert st[0]["n_symbols"] == 0 and st[0]["n_frames"] == 0          # like the reference (L = 0)
+    p.force_min_interp1 = 1
+    d = pdt.Demod("f32", p, 1, 400000, 16)
+    st, fr = d.demod_host(pcm, 1, pcm16=True)
+    want = oracle32.chain(oracle32.pcm16_to_complex(pcm), 2_000_000, force_min_L1=True)
+    assert (st[0]["n_symbols"], st[0]["n_bits"], st[0]["n_frames"]) == (want["total_symbols"], want["total_bits"], want["total_frames"])
+
+
+def test_argos_synthetic_bursts(torch_cuda, oracle64):
+    pcm, info = make_argos_capture(120000, 5000.0, seed=5, n_bursts=6, snr_db=18.0)
+    iq = oracle64.pcm16_to_complex(pcm)
+    want = oracle64.chain(iq, 5000, argos=True)
+    p = pdt.default_params("f64", pdt.PDT_MODE_ARGOS, 5000)
+    d = pdt.Demod("f64", p, 1, 120000, 32)
+    st, fr = d.demod_host(iq, 1)
+    assert (st[0]["n_symbols"], st[0]["n_bits"], st[0]["n_frames"]) == (want["total_symbols"], want["total_bits"], want["total_frames"])
+    _frames_text_equal_bytes(d.format_frames(fr[0], int(st[0]["n_frames"])), want["text"])
+
+
+# ------------------------------------------------------------------------------------------------------
+# legacy ABI: the reference's own function signatures, stage by stage, against the golden stage vectors
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_legacy_stage_vectors(torch_cuda, prec, golden_dir, tmp_path):
+    v = np.load(_golden(golden_dir, f"stage_vectors_{prec}.npz"))
+    lg = pdt.Legacy(prec)
+    lg.reset()
+    dt = lg.dt
+    exact = prec == "f32"
+    iq = v["iq"]
+    n = iq.size // 4
+    sg = lg.StaticGain(iq[: 2 * n])
+    assert sg == float(v["static_gain"]) if exact else abs(sg / float(v["static_gain"]) - 1) < 1e-15
+    a = [float(x) for x in v["pll_args"]]
+    o1, l1, a1 = lg.CarrierTrackPLL(iq[: 2 * n], *a, want_lock=True)
+    o2, l2, a2 = lg.CarrierTrackPLL(iq[2 * n:], *a, want_lock=True)
+    got_o, got_l = np.concatenate([o1, o2]), np.concatenate([l1, l2])
+    if exact:
+        assert np.array_equal(got_o, v["pll_out"]) and np.array_equal(got_l, v["pll_lock"])
+        assert [a1, a2] == list(v["pll_avg"])
+    else:
+        np.testing.assert_allclose(got_o, v["pll_out"], rtol=1e-12, atol=1e-15)
+        np.testing.assert_allclose(got_l, v["pll_lock"], rtol=1e-12, atol=1e-15)
+    x = v["fir_x"]
+    if prec == "f32":
+        for L in (1, 3, 8):
+            lg.reset()
+            h = lg.MakeLPFIR(26 * L, 11000.0, np.float32(150000.0), L)
+            assert np.array_equal(h, v[f"h_L{L}"])
+            tin = np.arange(2 * n + 1, dtype=dt)
+            ya, ta = lg.LowPassFilterInterp(tin[: n + 1], x[:n], h, L)
+            yb, tb = lg.LowPassFilterInterp(tin[n:], x[n:], h, L)
+            assert np.array_equal(np.concatenate([ya, yb]), v[f"fir_interp_L{L}"])
+            assert np.array_equal(ta, np.repeat(tin[1: n + 1], L))
+    lg.reset()
+    h = lg.MakeLPFIR(50, 700.0, 5000.0, 1)
+    assert np.array_equal(h, v["h_argos"])
+    assert np.array_equal(np.concatenate([lg.LowPassFilter(x[:n], h), lg.LowPassFilter(x[n:], h)]), v["fir_plain"])
+    ya = lg.NormalizingAGC(v["agc_x"][:n], 17.5, 0.0033, 0.0067)
+    yb = lg.NormalizingAGC(v["agc_x"][n:], 17.5, 0.0033, 0.0067)
+    assert np.array_equal(np.concatenate([ya, yb]), v["agc_y"])
+    FsI, baud, rng_, kp = v["gar_args"]
+    buf = np.zeros(n + 16, dt)
+    syms, idxs = [], []
+    for k in range(2):
+        buf[:n] = v["gar_x"][k * n:(k + 1) * n]
+        s, i = lg.GardenerClockRecovery(buf, n, int(FsI), float(baud), float(rng_), float(kp))
+        syms.append(s)
+        idxs.append(i.astype(np.int64) + k * n)
+    assert np.array_equal(np.concatenate(syms), v["gar_sym"])
+    assert np.array_equal(np.concatenate(idxs), v["gar_idx"])
+    thr = 1.0 if prec == "f32" else 0.5
+    bits = np.concatenate([lg.ManchesterDecode(v["man_sym"][:1777], thr), lg.ManchesterDecode(v["man_sym"][1777:], thr)])
+    assert np.array_equal(bits, v["man_bits"])
+
+
+@pytest.mark.parametrize("name", ["kat_line8", "kat_line10"])
+def test_legacy_bytesync_kat(torch_cuda, golden_dir, tmp_path, name):
+    kat = json.load(open(_golden(golden_dir, "bytesync_kat.json")))[name]
+    lg = pdt.Legacy("f32")
+    lg.reset()
+    bits = np.frombuffer(kat["bits"].encode(), np.uint8)
+    out = str(tmp_path / "frames.txt")
+    n = 0
+    for lo, hi in ((0, 1), (1, 777), (777, 778), (778, bits.size)):
+        n += lg.ByteSync(bits[lo:hi], out)
+    assert n == kat["frames"]
+    assert open(out).read() == kat["text"]
+
+
+def test_legacy_squelch_mm_agcc(torch_cuda, oracle64):
+    lg = pdt.Legacy("f64")
+    lg.reset()
+    rng = np.random.default_rng(23)
+    x = rng.standard_normal(5000)
+    lock = rng.random(5000) * 0.3
+    assert np.array_equal(lg.Squelch(x, lock, 0.15), oracle64.squelch(x, lock, 0.15))
+    st = oracle64.new_state("mm")
+    for n in (500, 2400):
+        buf = np.zeros(n + 16)
+        buf[:n] = np.sin(np.arange(n) * 0.5) + 0.2 * rng.standard_normal(n)
+        got, _ = lg.GardenerClockRecovery(buf, n, 5000, 800.0, 3.0, 0.15, mm=True)
+        assert np.array_equal(got, oracle64.mm(st, buf, n, 5000, 800.0, 3.0, 0.15))
+
+
+# ------------------------------------------------------------------------------------------------------
+# drop-in proof: the reference's UNMODIFIED main.c + wave.c linked against libpdt (built in the container)
+# ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("app,wav,golden", [("POES", "5sec_clip.wav", "poes_5sec_clip_frames.txt"),
+                                            ("ARGOS", "argos_401650kHz.wav", "argos_packets.txt")])
+def test_reference_main_linked_against_shim(torch_cuda, golden_dir, tmp_path, app, wav, golden):
+    exe = os.path.join(ROOT, "build", f"demod{app}_pdt")
+    if not os.path.exists(exe):
+        pytest.skip("drop-in driver not prebuilt (needs /root/reference at build time)")
+    r = subprocess.run([exe, _golden(golden_dir, wav)], cwd=tmp_path, capture_output=True, text=True, errors="replace",
+                       timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    outs = [f for f in os.listdir(tmp_path) if f.startswith(("minorFrames_", "packets_"))]
+    assert outs, r.stdout[-2000:]
+    text = open(tmp_path / outs[0]).read()
+    assert text == open(_golden(golden_dir, golden)).read()
+    assert "PLL locked at" in r.stdout
