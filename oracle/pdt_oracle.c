@@ -495,17 +495,21 @@ pdto_chain *pdto_chain_new(int argos, double Fs_hz, unsigned long chunk, int for
         c->N = POES_LPF_ORDER * c->L;
     }
     const int Lb = c->L > 0 ? c->L : 1, Nb = c->N > 0 ? c->N : 1;
+    /* Gardner reads its first mid-sample of every chunk up to step/2 past the end of the chunk
+     * (GardenerClockRecovery.c:28); the reference's buffers are over-allocated (chunk*N,
+     * main.c:356) and never written there, i.e. zero.  Keep a zero pad of at least one symbol. */
+    const size_t pad = 16 + (size_t)((double)Fs * Lb / (argos ? ARGOS_BAUD : POES_BAUD));
     pdto_pll_reset(&c->pll); pdto_fir_reset(&c->fir); pdto_agc_reset(&c->agc);
     pdto_gardner_reset(&c->gardner); pdto_manchester_reset(&c->man); pdto_bytesync_reset(&c->sync);
     c->wave_time = 0; c->wave_ts = 1.0 / (pdto_real)(unsigned int)Fs_hz;   /* wave.c:96-97 */
     c->h        = (pdto_real *)calloc((size_t)Nb, sizeof(pdto_real));
-    c->time_in  = (pdto_real *)calloc(chunk + 16, sizeof(pdto_real));
-    c->real_s   = (pdto_real *)calloc(chunk + 16, sizeof(pdto_real));
+    c->time_in  = (pdto_real *)calloc(chunk + pad, sizeof(pdto_real));
+    c->real_s   = (pdto_real *)calloc(chunk + pad, sizeof(pdto_real));
     c->lock     = (pdto_real *)calloc(chunk + 16, sizeof(pdto_real));
-    c->lpf      = (pdto_real *)calloc(chunk * (size_t)Lb + 16, sizeof(pdto_real));
-    c->lpf_time = (pdto_real *)calloc(chunk * (size_t)Lb + 16, sizeof(pdto_real));
-    c->sym      = (pdto_real *)calloc(chunk * (size_t)Lb + 16, sizeof(pdto_real));
-    c->bits     = (unsigned char *)calloc(chunk * (size_t)Lb + 16, 1);
+    c->lpf      = (pdto_real *)calloc(chunk * (size_t)Lb + pad, sizeof(pdto_real));
+    c->lpf_time = (pdto_real *)calloc(chunk * (size_t)Lb + pad, sizeof(pdto_real));
+    c->sym      = (pdto_real *)calloc(chunk * (size_t)Lb + pad, sizeof(pdto_real));
+    c->bits     = (unsigned char *)calloc(chunk * (size_t)Lb + pad, 1);
     if (argos) pdto_make_lpfir(c->h, c->N, ARGOS_LPF_FC, Fs, 1);                     /* ARGOS main.c:248 */
     else if (c->L > 0) pdto_make_lpfir(c->h, c->N, POES_LPF_FC, Fs * c->L, c->L);   /* POES main.c:369 */
     return c;

@@ -105,6 +105,7 @@ int build_chain_const(const pdt_params &p, ChainConst &cc)
     cc.sync.carry_bits = cc.argos ? 0 : 3;
     cc.sync.inverse_enabled = cc.argos ? 0 : 1;
     cc.prefix_bytes = cc.argos ? 0 : 2;
+    cc.ypad = 16 + 4 * (int)((double)cc.gardner_fs / p.baud / 4.0 + 1.0);
     return PDT_OK;
 }
 

@@ -46,10 +46,10 @@ struct ChainArgs {
 constexpr int CHAIN_THREADS = 256;
 constexpr int IQ_TILE = 1024;       // samples staged per PLL tile
 
-// reals needed: Rext[K-1+chunk] + LOCK[chunk] (ARGOS only) + Y[chunk*L+16] + IQ tile[2*IQ_TILE]
+// reals needed: Rext[K-1+chunk] + LOCK[chunk] (ARGOS only) + Y[chunk*L+ypad] + IQ tile[2*IQ_TILE]
 __host__ __device__ inline size_t chain_ws_reals(const ChainConst &cc)
 {
-    return (size_t)(cc.K - 1 + cc.chunk) + (cc.argos ? cc.chunk : 0) + (size_t)cc.chunk * cc.L + 16 + 2 * IQ_TILE;
+    return (size_t)(cc.K - 1 + cc.chunk) + (cc.argos ? cc.chunk : 0) + (size_t)cc.chunk * cc.L + cc.ypad + 2 * IQ_TILE;
 }
 
 PDT_DEV void load_iq(const void *base, int pcm16, unsigned long long idx, real_t &a, real_t &b)
@@ -106,9 +106,9 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_chain_exact(const ChainArgs a
     real_t *ws = args.use_smem ? reinterpret_cast<real_t *>(smem_raw) : args.workspace + (size_t)blockIdx.x * args.ws_stride;
     real_t *Rext = ws;                                   // [K-1 + chunk]
     real_t *LOCK = Rext + (cc.K - 1 + cc.chunk);         // [chunk] (ARGOS)
-    real_t *Y    = LOCK + (cc.argos ? cc.chunk : 0);     // [chunk*L + 16]
-    real_t *IQT  = Y + (size_t)cc.chunk * cc.L + 16;     // [2*IQ_TILE]
-    const size_t y_cap = (size_t)cc.chunk * cc.L + 16;
+    real_t *Y    = LOCK + (cc.argos ? cc.chunk : 0);     // [chunk*L + ypad]
+    real_t *IQT  = Y + (size_t)cc.chunk * cc.L + cc.ypad;     // [2*IQ_TILE]
+    const size_t y_cap = (size_t)cc.chunk * cc.L + cc.ypad;
 
     for (int i = tid; i < cc.N; i += CHAIN_THREADS) taps_s[i] = args.taps[i];
 

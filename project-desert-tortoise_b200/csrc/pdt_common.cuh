@@ -39,6 +39,8 @@ struct ChainConst {
     SyncParams sync;
     uint32_t max_frames;
     int      prefix_bytes;              // 2 for POES (literal ED E2), 0 for ARGOS
+    int      ypad;                      // zero pad behind the interpolated chunk: Gardner's first mid-sample of a chunk reads up
+                                        // to step/2 past its end (GardenerClockRecovery.c:28; the reference's buffer is chunk*N long)
 };
 
 int  build_chain_const(const pdt_params &p, ChainConst &cc);
