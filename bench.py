@@ -266,34 +266,60 @@ def main():
     total_samples = C_ * n * world
     value = total_samples / (ms_step * 1e-3) / 1e6
 
-    # ---- dominant kernel alone (events around each launch on the launch stream) -------------------
-    kt = []
-    for _ in range(min(args.steps, 5)):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        d.demod_device(d_iq.data_ptr(), C_, n, pcm16=args.pcm16, stream=stream)
-        b.record()
-        torch.cuda.synchronize()
-        kt.append(a.elapsed_time(b))
-    k_ms = float(np.mean(kt))
+    # ---- per-kernel device times of one more step (CUDA events on the launch stream, recorded by the library) ----
+    tiled = d.engine == pdt.PDT_ENGINE_TILED
+    kernels = []
+    if tiled:
+        d.set_profiling(True)
+        acc = {}
+        reps = min(args.steps, 3)
+        for _ in range(reps):
+            d.demod_device(d_iq.data_ptr(), C_, n, pcm16=args.pcm16, stream=stream)
+            torch.cuda.synchronize()
+            for name, t_ms in d.kernel_times():
+                acc[name] = acc.get(name, 0.0) + t_ms / reps
+        d.set_profiling(False)
+        kernels = sorted(acc.items(), key=lambda kv: -kv[1])
+        counters = d.tiled_counters(stream)
+    else:
+        kt = []
+        for _ in range(min(args.steps, 5)):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            d.demod_device(d_iq.data_ptr(), C_, n, pcm16=args.pcm16, stream=stream)
+            b.record()
+            torch.cuda.synchronize()
+            kt.append(a.elapsed_time(b))
+        kernels = [("k_chain_exact", float(np.mean(kt)))]
+        counters = None
     stats, frames = d.fetch(C_, stream)
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    alg_bytes = C_ * n * bytes_per_sample
+    Lf = max(d.params.interp, 1)
+    # algorithmic bytes per input sample of each kernel: what it must read + write once
+    alg = {"k_chain_exact": bytes_per_sample, "k_sp": bytes_per_sample + 4, "k_front": bytes_per_sample + 4 + 4 * Lf,
+           "k_pll_core": 8, "k_agc_core": 8 * Lf, "k_back": 4 * Lf, "k_acquire": bytes_per_sample + 8}
+    dom_name, k_ms = kernels[0]
+    alg_bytes = C_ * n * alg.get(dom_name, bytes_per_sample)
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
-        key = f"{C_}x{n}x{'pcm16' if args.pcm16 else 'cf32'}"
+        key = f"{dom_name}:{C_}x{n}x{'pcm16' if args.pcm16 else 'cf32'}"
         traffic = tj.get(key, {}).get("dram_bytes_per_launch")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "k_chain_exact", "kernel_ms": k_ms, "peak_source": peak_src,
+                "traffic": traffic, "kernel": dom_name, "kernel_ms": k_ms, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes,
-                "note": f"{bytes_per_sample} B per input IQ sample (whole chain fused; outputs are 104 B per 0.1 s)"}
+                "note": "dominant kernel by device time; per-kernel table in `kernels` (ms, GB/s algorithmic, fraction of HBM peak)"}
+    ktable = [{"kernel": nm, "ms": round(t_ms, 4),
+               "alg_GBps": round(C_ * n * alg[nm] / (t_ms * 1e-3) / 1e9, 1) if nm in alg and t_ms > 0 else None,
+               "hbm_frac": round(C_ * n * alg[nm] / (t_ms * 1e-3) / 1e9 / peak, 4) if nm in alg and t_ms > 0 else None}
+              for nm, t_ms in kernels]
+    chain_gbps = C_ * n * bytes_per_sample / (ms_step * 1e-3) / 1e9
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -301,14 +327,22 @@ def main():
         "data": "synthetic",
         "config": {"workload": f"batch of {C_} synthetic POES TIP captures x {n} IQ samples @ {FS} sps per GPU "
                                f"(BASELINE configs[3] batch shape with configs[1] signal parameters), full chain "
-                               f"PLL->FIR->AGC->Gardner->Manchester->ByteSync fused in one kernel",
+                               f"StaticGain->PLL->FIR->AGC->Gardner->Manchester->ByteSync, "
+                               f"{'tiled engine (time-parallel recurrences, verified bit-identical to the serial order)' if tiled else 'exact engine (one CTA per capture)'}",
+                   "engine": "tiled" if tiled else "exact",
                    "captures_per_gpu": C_, "samples_per_capture": n, "sample_rate": FS, "input": "pcm16" if args.pcm16 else "cf32",
                    "interp": d.params.interp, "taps": d.params.taps, "chunk": d.params.chunk,
                    "l2": f"inputs {alg_bytes / 1e9:.2f} GB per GPU, far larger than the 126 MB L2 (no flush needed)",
-                   "parallelism": f"one capture per CTA, {world} GPU(s), frames all-gathered over NCCL" if world > 1 else "one capture per CTA"},
-        "gpu_launches": int(launches), "roofline": roofline,
+                   "parallelism": f"captures sharded over {world} GPU(s), frames all-gathered over NCCL" if world > 1 else "one GPU"},
+        "gpu_launches": int(launches), "roofline": roofline, "kernels": ktable,
+        "chain_level": {"algorithmic_GBps": chain_gbps, "hbm_frac": chain_gbps / peak,
+                        "note": f"{bytes_per_sample} B per input IQ sample over the whole step"},
         "check": {"frames_decoded": int(stats["n_frames"].sum()), "captures_locked": int(stats["locked"].sum()),
-                  "symbols": int(stats["n_symbols"].sum())},
+                  "symbols": int(stats["n_symbols"].sum()),
+                  "lock_sample_median": int(np.median(stats["lock_sample"][stats["locked"] == 1])) if stats["locked"].any() else None,
+                  "lock_sample_max": int(stats["lock_sample"].max()),
+                  "speculation": None if counters is None else {"pll_tiles_rerun": counters[0], "agc_tiles_rerun": counters[1],
+                                                                "acq_restarts": counters[2], "pll_tiles_per_capture": counters[3]}},
     }
     if clocks:
         line["clocks"] = clocks

@@ -38,6 +38,14 @@ extern "C" {
 
 #define PDT_FRAME_MAX_BYTES 104
 
+/* PDT_ENGINE_EXACT: one CTA per capture, every recurrence strictly serial (any mode / precision).
+ * PDT_ENGINE_TILED: float POES chain only; recurrences parallelised in time with warm-up tiles that are accepted
+ *                   only when bit-identical to the serial continuation (re-run otherwise) -> same results.
+ * PDT_ENGINE_AUTO : TILED where it applies, else EXACT. */
+#define PDT_ENGINE_AUTO  0
+#define PDT_ENGINE_EXACT 1
+#define PDT_ENGINE_TILED 2
+
 /* All DSP constants of the reference drivers, in the units the reference uses (loop gains in rad/s,
  * scaled by 2π/Fs at the call site in double and narrowed to DECIMAL_TYPE: POESTIPdemod/main.c:413,429). */
 typedef struct pdt_params {
@@ -60,6 +68,10 @@ typedef struct pdt_params {
     double   norm_factor;        /* 0 = StaticGain of the first chunk (main.c:384-389), else override (-n) */
     char     sync_word[32];      /* ASCII '0'/'1' */
     int      sync_len;           /* 19 / 13 */
+    /* engine selection (not in the reference; results are identical, only the speed differs) */
+    int      engine;             /* PDT_ENGINE_AUTO | PDT_ENGINE_EXACT | PDT_ENGINE_TILED */
+    uint32_t pll_warm, pll_tile; /* tiled engine: PLL warm-up / tile length in samples (0 = derived from the loop bandwidth) */
+    uint32_t agc_min_tile;       /* tiled engine: smallest AGC tile in interpolated samples (0 = default) */
 } pdt_params;
 
 /* One decoded minor frame (POES, 104 bytes incl. the literal ED E2) or packet (ARGOS, 7 bytes). */
@@ -137,6 +149,18 @@ int         pdt_result_tables(pdt_ctx *ctx, void **d_stats, void **d_frames, uin
 /* Render frames exactly like the reference's output file ("%.5f ED E2 XX …\n", POESTIPdemod/ByteSync.c:96-101,62,69).
  * The time column emulates wave.c's float-accumulated axis.  Returns bytes written (excluding NUL) or <0. */
 long        pdt_format_frames(const pdt_ctx *ctx, const pdt_frame *frames, uint32_t n_frames, char *buf, size_t cap);
+
+/* Engine that the context resolved to (PDT_ENGINE_EXACT / PDT_ENGINE_TILED) and, for the tiled engine, the
+ * speculation counters of the last batch (valid after the stream is synchronised):
+ *   out[0] PLL tiles re-run, out[1] AGC tiles re-run, out[2] acquisition restarts, out[3] PLL tiles per capture (max). */
+int         pdt_engine(const pdt_ctx *ctx);
+int         pdt_tiled_counters(pdt_ctx *ctx, uint32_t out[4], void *stream);
+
+/* Per-kernel device times of the tiled engine: when enabled, a CUDA event is recorded on the launch stream after
+ * every kernel of a batch; pdt_kernel_times() synchronises and returns how many kernels the last batch launched,
+ * their names (static strings) and durations in milliseconds. */
+int         pdt_set_profiling(pdt_ctx *ctx, int enable);
+int         pdt_kernel_times(pdt_ctx *ctx, const char **names, float *ms, int cap);
 
 /* Number of kernels launched by this library since load (bench.py reports it as gpu_launches). */
 uint64_t    pdt_launch_count(void);

@@ -24,6 +24,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 
 PDT_MODE_POES, PDT_MODE_ARGOS = 0, 1
+PDT_ENGINE_AUTO, PDT_ENGINE_EXACT, PDT_ENGINE_TILED = 0, 1, 2
 FRAME_MAX = 104
 
 
@@ -38,7 +39,8 @@ class Params(C.Structure):
                 ("pll_lock_thresh", C.c_double), ("agc_attack", C.c_double), ("agc_decay", C.c_double),
                 ("lpf_fc", C.c_double), ("baud", C.c_double), ("gardner_err_lim", C.c_double),
                 ("gardner_gain", C.c_double), ("manchester_resync", C.c_double), ("squelch_thresh", C.c_double),
-                ("norm_factor", C.c_double), ("sync_word", C.c_char * 32), ("sync_len", C.c_int)]
+                ("norm_factor", C.c_double), ("sync_word", C.c_char * 32), ("sync_len", C.c_int),
+                ("engine", C.c_int), ("pll_warm", C.c_uint32), ("pll_tile", C.c_uint32), ("agc_min_tile", C.c_uint32)]
 
 
 class Frame(C.Structure):
@@ -111,6 +113,10 @@ def load(prec: str = "f32"):
     L.pdt_format_frames.restype = C.c_long
     L.pdt_format_frames.argtypes = [vp, vp, u32, C.c_char_p, C.c_size_t]
     L.pdt_launch_count.restype = u64
+    L.pdt_set_profiling.argtypes = [vp, C.c_int]
+    L.pdt_kernel_times.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]
+    L.pdt_engine.argtypes = [vp]
+    L.pdt_tiled_counters.argtypes = [vp, C.POINTER(C.c_uint32 * 4), vp]
     L.pdt_synth_poes_device.argtypes = [vp, C.c_int, u32, u64, u64, C.c_double, u64, vp]
     # legacy ABI (reference names)
     L.StaticGain.restype = R
@@ -151,7 +157,8 @@ EXPORTED_SYMBOLS = [
     # include/pdt.h
     "pdt_version", "pdt_last_error", "pdt_real_size", "pdt_device_count", "pdt_set_device", "pdt_params_default",
     "pdt_create", "pdt_destroy", "pdt_get_params", "pdt_get_taps", "pdt_demod_device", "pdt_demod_host", "pdt_fetch",
-    "pdt_result_tables", "pdt_format_frames", "pdt_launch_count", "pdt_synth_poes_device",
+    "pdt_result_tables", "pdt_format_frames", "pdt_launch_count", "pdt_synth_poes_device", "pdt_engine",
+    "pdt_tiled_counters", "pdt_set_profiling", "pdt_kernel_times",
     # include/pdt_legacy.h
     "FindSignalAmplitude", "Squelch", "StaticGain", "NormalizingAGC", "NormalizingAGCC", "CarrierTrackPLL", "arctan2",
     "Q_rsqrt", "LowPassFilter", "LowPassFilterInterp", "MakeLPFIR", "GardenerClockRecovery", "MMClockRecovery", "sign",
@@ -224,6 +231,28 @@ class Demod:
         frames = np.zeros((n_captures, self.max_frames), FRAME_DTYPE) if want_frames else None
         _check(self.L, self.L.pdt_fetch(self.ctx, n_captures, _p(stats), _p(frames), stream))
         return stats, frames
+
+    @property
+    def engine(self) -> int:
+        return int(self.L.pdt_engine(self.ctx))
+
+    def tiled_counters(self, stream: int = 0):
+        """(PLL tiles re-run, AGC tiles re-run, acquisition restarts, max PLL tiles per capture) of the last batch."""
+        out = (C.c_uint32 * 4)()
+        _check(self.L, self.L.pdt_tiled_counters(self.ctx, C.byref(out), stream))
+        return tuple(int(v) for v in out)
+
+    def set_profiling(self, on: bool = True):
+        _check(self.L, self.L.pdt_set_profiling(self.ctx, int(on)))
+
+    def kernel_times(self):
+        """[(kernel name, ms)] of the last batch (tiled engine with profiling enabled), in launch order."""
+        names = (C.c_char_p * 24)()
+        ms = (C.c_float * 24)()
+        k = self.L.pdt_kernel_times(self.ctx, names, ms, 24)
+        if k < 0:
+            raise PdtError(self.L.pdt_last_error().decode())
+        return [(names[i].decode(), float(ms[i])) for i in range(k)]
 
     def result_tables(self):
         ds, df, mf = C.c_void_p(), C.c_void_p(), C.c_uint32()

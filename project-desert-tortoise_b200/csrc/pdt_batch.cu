@@ -11,6 +11,9 @@
 
 #include "pdt_chain_kernel.cuh"
 #include "pdt_synth.cuh"
+#if PDT_USE_FLOATS
+#include "pdt_tiled_kernels.cuh"
+#endif
 
 namespace pdt {
 
@@ -132,7 +135,202 @@ struct pdt_ctx {
     void       *d_stage = nullptr;       // staging for pdt_demod_host
     size_t      stage_bytes = 0;
     int         device = 0, sm_count = 0;
+    int         engine = PDT_ENGINE_EXACT;
+#if PDT_USE_FLOATS
+    tiled::TiledArgs ta;                 // workspace pointers + plans of the tiled engine (engine == PDT_ENGINE_TILED)
+    tiled::TapsRev   taps_rev;
+    size_t      front_smem = 0;
+    static constexpr int MAX_GROUPS = 8;
+    cudaStream_t gstream[MAX_GROUPS] = {};
+    cudaEvent_t  ev_fork = nullptr, ev_join[MAX_GROUPS] = {};
+    int         profiling = 0, n_marks = 0;
+    cudaEvent_t marks[24] = {};
+    const char *mark_names[24] = {};
+#endif
 };
+
+#if PDT_USE_FLOATS
+// ---- tiled engine: eligibility, workspace, launch sequence -----------------------------------------------
+static bool tiled_applicable(const pdt_params &p, const ChainConst &cc, uint32_t max_captures)
+{
+    if (cc.argos || cc.L < 1 || cc.L > tiled::FIR_MAX_L || cc.N != tiled::FIR_K * cc.L) return false;
+    if (max_captures > 65535u) return false;
+    if ((double)cc.chunk * cc.L > 1e9) return false;
+    // one 2π wrap per sample must suffice (pdt_tiled.cuh::pll_track_step): |Δphase| <= max_freq + (alpha+beta)·3π < 2π
+    PllState ps; pll_reset(ps); pll_begin(ps, cc.pll);
+    if (!((double)ps.max_freq + 10.0 * ((double)ps.alpha + (double)ps.beta) < 6.0)) return false;
+    if (!(cc.pll.bw_track > 0) || !(cc.agc_decay > 0)) return false;
+    return true;
+}
+
+static int tiled_setup(pdt_ctx *c)
+{
+    using namespace tiled;
+    TiledArgs &t = c->ta;
+    memset(&t, 0, sizeof t);
+    t.cc = c->cc;
+    const ChainConst &cc = c->cc;
+    const u64 stride = c->max_samples;
+    // PLL plan: the track loop is critically damped with time constant 2/alpha ≈ 1/(2·bw) samples; 34 time
+    // constants take a (2 Hz, 0.2 rad) carrier guess down to a bit-identical state (measured).
+    u64 W = c->params.pll_warm ? c->params.pll_warm : (u64)(17.0 / (double)cc.pll.bw_track);
+    W = (W + 3) & ~3ull; if (W < 1024) W = 1024;
+    u64 T = c->params.pll_tile ? c->params.pll_tile : W / 2;
+    T = (T + 3) & ~3ull; if (T < 1024) T = 1024;
+    t.pll.W = W; t.pll.T = T; t.pll.T0 = W + T;
+    t.pll.max_tiles = 1 + (unsigned)((stride + T - 1) / T);
+    t.agc_min_tile = c->params.agc_min_tile ? ((c->params.agc_min_tile + 3) & ~3u) : 4096u * (unsigned)cc.L;
+    t.agc_max_tiles = 1 + (unsigned)((stride * cc.L + t.agc_min_tile - 1) / t.agc_min_tile);
+    t.est_fmax = (float)c->params.max_carrier_dev + 600.0f;
+    int D = (int)((double)cc.pll.Fs / (2.5 * (double)t.est_fmax));
+    t.est_decim = D < 1 ? 1 : D;
+    t.ws_stride = (stride + 3) & ~3ull;
+    const size_t nin = (size_t)c->max_captures * t.ws_stride, nout = nin * cc.L;
+    cudaError_t e;
+#define TA(ptr, bytes) if ((e = cudaMalloc((void **)&(ptr), (bytes))) != cudaSuccess) return fail(PDT_ENOMEM, "tiled workspace (%zu bytes): %s", (size_t)(bytes), cudaGetErrorString(e))
+    TA(t.sp, nin * sizeof(float)); TA(t.ph, nin * sizeof(float));
+    TA(t.y, nout * sizeof(float)); TA(t.z, nout * sizeof(float));
+    TA(t.acq, sizeof(AcqResult) * c->max_captures);
+    const size_t np = (size_t)c->max_captures * t.pll.max_tiles, na = (size_t)c->max_captures * t.agc_max_tiles;
+    TA(t.guess, np * sizeof(LoopState2)); TA(t.pll_start, np * sizeof(LoopState2)); TA(t.pll_end, np * sizeof(LoopState2));
+    TA(t.agc_start, na * sizeof(LoopState2)); TA(t.agc_end, na * sizeof(LoopState2));
+    TA(t.counters, 4 * sizeof(uint32_t));
+#undef TA
+    for (int u = 0; u < cc.N; u++) c->taps_rev.hr[u] = c->taps_h[cc.N - 1 - u];
+    c->front_smem = sizeof(float) * ((size_t)FRONT_SPAN + FIR_K + 2 + (size_t)FRONT_SPAN * cc.L);
+    void (*kf)(const TiledArgs, const TapsRev) = cc.L == 1 ? k_front<1> : cc.L == 2 ? k_front<2> : cc.L == 3 ? k_front<3> : k_front<4>;
+    if ((e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->front_smem)) != cudaSuccess)
+        return fail(PDT_ECUDA, "cudaFuncSetAttribute(k_front): %s", cudaGetErrorString(e));
+    return PDT_OK;
+}
+
+static void tiled_free(pdt_ctx *c)
+{
+    tiled::TiledArgs &t = c->ta;
+    cudaFree(t.sp); cudaFree(t.ph); cudaFree(t.y); cudaFree(t.z); cudaFree(t.acq); cudaFree(t.guess);
+    cudaFree(t.pll_start); cudaFree(t.pll_end); cudaFree(t.agc_start); cudaFree(t.agc_end); cudaFree(t.counters);
+}
+
+// the kernel sequence for captures [c0, c0+cnt) of the batch on stream s
+static int tiled_run_group(pdt_ctx *c, const tiled::TiledArgs &base, uint32_t c0, uint32_t cnt, tiled::u64 n_max, cudaStream_t s, bool marks)
+{
+    using namespace tiled;
+    TiledArgs t = base;
+    const int L = c->cc.L;
+    const size_t elem = t.pcm16 ? 2 * sizeof(int16_t) : 2 * sizeof(float);
+    t.iq = (const char *)base.iq + (size_t)c0 * t.stride * elem;
+    if (t.n_samples) t.n_samples += c0;
+    t.n_captures = cnt;
+    t.sp += (size_t)c0 * t.ws_stride; t.ph += (size_t)c0 * t.ws_stride;
+    t.y += (size_t)c0 * t.ws_stride * L; t.z += (size_t)c0 * t.ws_stride * L;
+    t.acq += c0;
+    t.guess += (size_t)c0 * t.pll.max_tiles; t.pll_start += (size_t)c0 * t.pll.max_tiles; t.pll_end += (size_t)c0 * t.pll.max_tiles;
+    t.agc_start += (size_t)c0 * t.agc_max_tiles; t.agc_end += (size_t)c0 * t.agc_max_tiles;
+    t.stats += c0; t.frames += (size_t)c0 * c->max_frames;
+    if (t.traces) t.traces += c0;
+    auto blocks = [](u64 items, unsigned per) { return (unsigned)((items + per - 1) / per); };
+    auto mark = [&](const char *name) {
+        if (!marks || c->n_marks >= 24) return;
+        if (!c->marks[c->n_marks]) cudaEventCreate(&c->marks[c->n_marks]);
+        cudaEventRecord(c->marks[c->n_marks], s);
+        c->mark_names[c->n_marks++] = name;
+    };
+    mark("begin");
+    k_norm<<<blocks((u64)cnt * 32, 128), 128, 0, s>>>(t);
+    mark("k_norm");
+    {
+        dim3 g(std::min<unsigned>(blocks(n_max, 1024), 4096), cnt);
+        k_sp<<<g, 256, 0, s>>>(t);
+    }
+    mark("k_sp");
+    k_acquire<<<cnt, ACQ_THREADS, 0, s>>>(t);
+    mark("k_acquire");
+    if (t.pll.max_tiles > 1)
+        k_estimate<<<blocks((u64)cnt * (t.pll.max_tiles - 1), EST_WARPS), EST_WARPS * 32, 0, s>>>(t);
+    mark("k_estimate");
+    k_pll_core<<<blocks((u64)cnt * t.pll.max_tiles, 128), 128, 0, s>>>(t);
+    mark("k_pll_core");
+    k_pll_fix_par<<<blocks((u64)cnt * t.pll.max_tiles, 128), 128, 0, s>>>(t);
+    k_pll_fix_par<<<blocks((u64)cnt * t.pll.max_tiles, 128), 128, 0, s>>>(t);
+    mark("k_pll_fix_par");
+    k_pll_fix<<<blocks(cnt, 128), 128, 0, s>>>(t);
+    mark("k_pll_fix");
+    {
+        dim3 g(blocks(n_max, FRONT_SPAN), cnt);
+        switch (L) {
+        case 1: k_front<1><<<g, FRONT_THREADS, c->front_smem, s>>>(t, c->taps_rev); break;
+        case 2: k_front<2><<<g, FRONT_THREADS, c->front_smem, s>>>(t, c->taps_rev); break;
+        case 3: k_front<3><<<g, FRONT_THREADS, c->front_smem, s>>>(t, c->taps_rev); break;
+        default: k_front<4><<<g, FRONT_THREADS, c->front_smem, s>>>(t, c->taps_rev); break;
+        }
+    }
+    mark("k_front");
+    k_agc_plan<<<blocks((u64)cnt * 32, 128), 128, 0, s>>>(t);
+    mark("k_agc_plan");
+    k_agc_core<<<blocks((u64)cnt * t.agc_max_tiles, 128), 128, 0, s>>>(t);
+    mark("k_agc_core");
+    k_agc_fix_par<<<blocks((u64)cnt * t.agc_max_tiles, 128), 128, 0, s>>>(t);
+    mark("k_agc_fix_par");
+    k_agc_fix<<<blocks(cnt, 128), 128, 0, s>>>(t);
+    mark("k_agc_fix");
+    k_back<<<blocks(cnt, BACK_WARPS), BACK_WARPS * 32, 0, s>>>(t);
+    mark("k_back");
+    count_launch(t.pll.max_tiles > 1 ? 14 : 13);
+    PDT_CUDA(cudaGetLastError());
+    return PDT_OK;
+}
+
+// Captures are independent, and the kernels that carry the serial recurrences (k_acquire, k_pll_core, k_agc_core,
+// k_back) are latency-bound with few warps, while k_sp / k_front are throughput-bound.  The batch is therefore cut
+// into groups that run the same kernel sequence on internal streams, forked from and joined to the caller's
+// stream: one group's serial kernels overlap another group's bulk kernels, and a capture that takes long to
+// acquire lock only delays its own group.
+static int tiled_run(pdt_ctx *c, const void *d_iq, int pcm16, uint32_t n_captures, uint64_t stride, const uint64_t *n_samples,
+                     const pdt_traces *traces, cudaStream_t s)
+{
+    using namespace tiled;
+    TiledArgs t = c->ta;
+    t.iq = d_iq; t.pcm16 = pcm16; t.stride = stride; t.n_captures = n_captures;
+    t.n_samples = n_samples ? c->d_nsamp : nullptr; t.n_uniform = stride;
+    t.stats = c->d_stats; t.frames = c->d_frames; t.traces = traces ? c->d_traces : nullptr;
+    u64 n_max = stride;
+    if (n_samples) { n_max = 0; for (uint32_t i = 0; i < n_captures; i++) n_max = std::max<u64>(n_max, n_samples[i]); }
+    if (n_max == 0) return PDT_OK;
+    const int L = c->cc.L;
+    PDT_CUDA(cudaMemsetAsync(t.counters, 0, 4 * sizeof(uint32_t), s));
+    c->n_marks = 0;
+    int groups = (int)std::min<uint32_t>(pdt_ctx::MAX_GROUPS, (n_captures + 63) / 64);
+    if (c->profiling || traces || groups < 2) {
+        const int rc = tiled_run_group(c, t, 0, n_captures, n_max, s, c->profiling != 0);
+        if (rc != PDT_OK) return rc;
+    } else {
+        if (!c->ev_fork) PDT_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        PDT_CUDA(cudaEventRecord(c->ev_fork, s));
+        const uint32_t per = (n_captures + groups - 1) / groups;
+        for (int g = 0; g < groups; g++) {
+            const uint32_t c0 = (uint32_t)g * per;
+            if (c0 >= n_captures) break;
+            const uint32_t cnt = std::min<uint32_t>(per, n_captures - c0);
+            if (!c->gstream[g]) PDT_CUDA(cudaStreamCreateWithFlags(&c->gstream[g], cudaStreamNonBlocking));
+            if (!c->ev_join[g]) PDT_CUDA(cudaEventCreateWithFlags(&c->ev_join[g], cudaEventDisableTiming));
+            PDT_CUDA(cudaStreamWaitEvent(c->gstream[g], c->ev_fork, 0));
+            const int rc = tiled_run_group(c, t, c0, cnt, n_max, c->gstream[g], false);
+            if (rc != PDT_OK) return rc;
+            PDT_CUDA(cudaEventRecord(c->ev_join[g], c->gstream[g]));
+            PDT_CUDA(cudaStreamWaitEvent(s, c->ev_join[g], 0));
+        }
+    }
+    if (traces) {      // trace taps that are whole workspaces: copy them out (test/debug path)
+        for (uint32_t i = 0; i < n_captures; i++) {
+            const u64 n = n_samples ? n_samples[i] : stride;
+            if (traces[i].pll_phase) PDT_CUDA(cudaMemcpyAsync(traces[i].pll_phase, t.ph + (size_t)i * t.ws_stride, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+            if (traces[i].lpf) PDT_CUDA(cudaMemcpyAsync(traces[i].lpf, t.y + (size_t)i * t.ws_stride * L, n * L * sizeof(float), cudaMemcpyDeviceToDevice, s));
+            if (traces[i].agc) PDT_CUDA(cudaMemcpyAsync(traces[i].agc, t.z + (size_t)i * t.ws_stride * L, n * L * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        }
+    }
+    return PDT_OK;
+}
+#endif
 
 extern "C" {
 
@@ -218,6 +416,15 @@ pdt_ctx *pdt_create(const pdt_params *p, uint32_t max_captures, uint64_t max_sam
     cudaError_t e;
     if ((e = cudaGetDevice(&c->device)) != cudaSuccess) return bail(e, "cudaGetDevice");
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device);
+    c->engine = PDT_ENGINE_EXACT;
+#if PDT_USE_FLOATS
+    if (c->params.engine != PDT_ENGINE_EXACT && tiled_applicable(c->params, c->cc, max_captures)) c->engine = PDT_ENGINE_TILED;
+#endif
+    if (c->params.engine == PDT_ENGINE_TILED && c->engine != PDT_ENGINE_TILED) {
+        fail(PDT_EINVAL, "the tiled engine needs the float POES chain with 1 <= interp <= 4 and taps = 26*interp");
+        delete c;
+        return nullptr;
+    }
     if (c->cc.L > 0) {
         const real_t Fs = (real_t)(unsigned int)c->params.sample_rate;
         if (c->cc.argos) make_lpfir_host(c->taps_h, c->cc.N, (real_t)c->params.lpf_fc, Fs, 1);            // ARGOS main.c:248
@@ -247,6 +454,9 @@ pdt_ctx *pdt_create(const pdt_params *p, uint32_t max_captures, uint64_t max_sam
             if ((e = cudaMalloc(&c->d_ws, c->ws_stride * sizeof(real_t) * c->grid)) != cudaSuccess) return bail(e, "cudaMalloc workspace");
         }
     }
+#if PDT_USE_FLOATS
+    if (c->engine == PDT_ENGINE_TILED && tiled_setup(c) != PDT_OK) { pdt_destroy(c); return nullptr; }
+#endif
     if ((e = cudaMalloc(&c->d_stats, sizeof(pdt_capture_stats) * max_captures)) != cudaSuccess) return bail(e, "cudaMalloc stats");
     if ((e = cudaMalloc(&c->d_frames, sizeof(pdt_frame) * (size_t)max_captures * max_frames)) != cudaSuccess) return bail(e, "cudaMalloc frames");
     if ((e = cudaMalloc(&c->d_nsamp, sizeof(unsigned long long) * max_captures)) != cudaSuccess) return bail(e, "cudaMalloc nsamp");
@@ -259,6 +469,13 @@ void pdt_destroy(pdt_ctx *c)
     if (!c) return;
     cudaFree(c->d_taps); cudaFree(c->d_ws); cudaFree(c->d_stats); cudaFree(c->d_frames);
     cudaFree(c->d_nsamp); cudaFree(c->d_traces); cudaFree(c->d_stage);
+#if PDT_USE_FLOATS
+    if (c->engine == PDT_ENGINE_TILED) tiled_free(c);
+    for (cudaEvent_t e : c->marks) if (e) cudaEventDestroy(e);
+    for (cudaStream_t gs : c->gstream) if (gs) cudaStreamDestroy(gs);
+    for (cudaEvent_t e : c->ev_join) if (e) cudaEventDestroy(e);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+#endif
     delete c;
 }
 
@@ -294,6 +511,13 @@ int pdt_demod_device(pdt_ctx *c, const void *d_iq, int pcm16, uint32_t n_capture
         // Fs >= 300 ksps: L = rint(150000/Fs) = 0 and the reference silently emits nothing. Same here.
         return PDT_OK;
     }
+#if PDT_USE_FLOATS
+    if (c->engine == PDT_ENGINE_TILED) {
+        bool needs_exact = false;      // per-sample frequency / lock-detector taps only exist in the exact engine
+        if (traces) for (uint32_t i = 0; i < n_captures; i++) needs_exact |= (traces[i].pll_freq || traces[i].lock);
+        if (!needs_exact) return tiled_run(c, d_iq, pcm16, n_captures, stride_samples, n_samples, traces, s);
+    }
+#endif
     ChainArgs a;
     a.cc = c->cc; a.taps = c->d_taps; a.iq = d_iq; a.pcm16 = pcm16; a.stride = stride_samples;
     a.n_samples = n_samples ? c->d_nsamp : nullptr; a.n_uniform = stride_samples; a.n_captures = n_captures;
@@ -314,6 +538,48 @@ int pdt_fetch(pdt_ctx *c, uint32_t n_captures, pdt_capture_stats *stats_out, pdt
     if (frames_out) PDT_CUDA(cudaMemcpyAsync(frames_out, c->d_frames, sizeof(pdt_frame) * (size_t)n_captures * c->max_frames, cudaMemcpyDeviceToHost, s));
     PDT_CUDA(cudaStreamSynchronize(s));
     return PDT_OK;
+}
+
+int pdt_engine(const pdt_ctx *c) { return c ? c->engine : PDT_EINVAL; }
+
+int pdt_tiled_counters(pdt_ctx *c, uint32_t out[4], void *stream)
+{
+    if (!c || !out) return fail(PDT_EINVAL, "bad arguments");
+    out[0] = out[1] = out[2] = out[3] = 0;
+#if PDT_USE_FLOATS
+    if (c->engine == PDT_ENGINE_TILED) {
+        PDT_CUDA(cudaMemcpyAsync(out, c->ta.counters, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+        PDT_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+        out[3] = c->ta.pll.max_tiles;
+    }
+#endif
+    return PDT_OK;
+}
+
+int pdt_set_profiling(pdt_ctx *c, int enable)
+{
+    if (!c) return fail(PDT_EINVAL, "bad arguments");
+#if PDT_USE_FLOATS
+    c->profiling = enable;
+#endif
+    return PDT_OK;
+}
+
+int pdt_kernel_times(pdt_ctx *c, const char **names, float *ms, int cap)
+{
+    if (!c || !names || !ms) return fail(PDT_EINVAL, "bad arguments");
+#if PDT_USE_FLOATS
+    if (c->engine != PDT_ENGINE_TILED || c->n_marks < 2) return 0;
+    PDT_CUDA(cudaEventSynchronize(c->marks[c->n_marks - 1]));
+    int k = 0;
+    for (int i = 1; i < c->n_marks && k < cap; i++, k++) {
+        names[k] = c->mark_names[i];
+        PDT_CUDA(cudaEventElapsedTime(&ms[k], c->marks[i - 1], c->marks[i]));
+    }
+    return k;
+#else
+    return 0;
+#endif
 }
 
 int pdt_result_tables(pdt_ctx *c, void **d_stats, void **d_frames, uint32_t *max_frames)

@@ -22,7 +22,36 @@ typedef double real_t;
 #define PDT_MAX_TAPS 1024
 #define PDT_MAX_PHASE_TAPS 64   // taps per polyphase branch (N / L); the reference uses 26 (main.c:104) or 50
 
-#define PDT_DEV __device__ __forceinline__
+// Every stage function is __host__ __device__: the device build is the product; the host build of the very same
+// code is used only by tests/host_emul (CPU emulation of the tiled engine's logic, checked against the oracle).
+#define PDT_DEV __host__ __device__ __forceinline__
+
+#include <cmath>
+#include <cstring>
+PDT_DEV uint32_t pdt_f2u(float x)
+{
+#ifdef __CUDA_ARCH__
+    return __float_as_uint(x);
+#else
+    uint32_t u; memcpy(&u, &x, 4); return u;
+#endif
+}
+PDT_DEV float pdt_u2f(uint32_t u)
+{
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    float x; memcpy(&x, &u, 4); return x;
+#endif
+}
+PDT_DEV int pdt_d2i_rz(double x)
+{
+#ifdef __CUDA_ARCH__
+    return __double2int_rz(x);
+#else
+    return (int)x;
+#endif
+}
 
 // ---------------------------------------------------------------------------------------------------
 // small overload helpers
@@ -64,7 +93,7 @@ PDT_DEV double sc_poly(double x, double x2, double flip, int n)
     }
 }
 
-PDT_DEV uint32_t abstop12(float x) { return (__float_as_uint(x) >> 20) & 0x7ffu; }
+PDT_DEV uint32_t abstop12(float x) { return (pdt_f2u(x) >> 20) & 0x7ffu; }
 
 PDT_DEV void sincos_exact(float y, float &s, float &c)
 {
@@ -79,7 +108,7 @@ PDT_DEV void sincos_exact(float y, float &s, float &c)
     if (abstop12(y) < 0x42fu) {                 // |y| < 120
         const double hpi_inv = 0x1.45F306DC9C883p+23, hpi = 0x1.921FB54442D18p0;
         double r = x * hpi_inv;
-        int n = (__double2int_rz(r) + 0x800000) >> 24;
+        int n = (pdt_d2i_rz(r) + 0x800000) >> 24;
         x = x - (double)n * hpi;
         const double sgn  = ((n & 3) == 0 || (n & 3) == 3) ? 1.0 : -1.0;
         const double flip = (n & 2) ? -1.0 : 1.0;
@@ -90,7 +119,14 @@ PDT_DEV void sincos_exact(float y, float &s, float &c)
     }
     s = sinf(y); c = cosf(y);                   // never reached by the PLL (phase is wrapped to ±2π)
 }
-PDT_DEV void sincos_exact(double y, double &s, double &c) { sincos(y, &s, &c); }
+PDT_DEV void sincos_exact(double y, double &s, double &c)
+{
+#ifdef __CUDA_ARCH__
+    sincos(y, &s, &c);
+#else
+    s = sin(y); c = cos(y);
+#endif
+}
 
 // hypot as glibc's cabsf()/cabs() compute it (AGC.c:58,66)
 PDT_DEV float  hypot_exact(float re, float im)  { return (float)sqrt((double)re * (double)re + (double)im * (double)im); }
@@ -123,9 +159,9 @@ PDT_DEV real_t arctan2_approx(real_t y, real_t x)
 PDT_DEV float q_rsqrt(float x)
 {
     float half = 0.5f * x;
-    int bits = __float_as_int(x);
+    int bits = (int)pdt_f2u(x);
     bits = 0x5f3759df - (bits >> 1);
-    x = __int_as_float(bits);
+    x = pdt_u2f((uint32_t)bits);
     x = x * (1.5f - half * x * x);
     x = x * (1.5f - half * x * x);
     return x;
@@ -228,14 +264,16 @@ struct AgcState { int init; real_t gain; };
 
 PDT_DEV real_t agc_step(AgcState &s, real_t x, real_t attack, real_t decay)
 {
+    // AGC.c:98-131, written so that the compiler emits selects instead of branches (both rate products are formed,
+    // the one the reference would use is selected): the gain recurrence is the serial bottleneck of this stage.
     const real_t reference = 1.0, max_gain = 5000;
     x *= s.gain;
-    real_t err  = r_fabs(x) - reference;
-    real_t rate = decay;
-    if (r_fabs(err) > s.gain) rate = attack;
-    s.gain -= err * rate;
-    if (s.gain < 0.0) s.gain = 10e-5;
-    if (max_gain > 0.0 && s.gain > max_gain) s.gain = max_gain;
+    const real_t err = r_fabs(x) - reference;
+    const real_t da = err * attack, dd = err * decay;
+    real_t g = s.gain - ((r_fabs(err) > s.gain) ? da : dd);
+    g = (g < 0.0) ? (real_t)10e-5 : g;
+    g = (g > max_gain) ? max_gain : g;
+    s.gain = g;
     return x;
 }
 

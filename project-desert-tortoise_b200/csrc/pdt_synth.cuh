@@ -32,10 +32,10 @@ __global__ void k_synth_frames(unsigned char *tab, SynthCap *caps, uint32_t n_ca
     const unsigned long long hc = mix64(seed * 0x100000001B3ull + c);
     if (threadIdx.x == 0) {
         SynthCap sc;
-        sc.f0 = (u01(mix64(hc + 1)) * 2.0 - 1.0) * 3500.0;
+        sc.f0 = (u01(mix64(hc + 1)) * 2.0 - 1.0) * 3000.0;
         sc.drift = (u01(mix64(hc + 2)) * 2.0 - 1.0) * 50.0;
         sc.amp = 0.05 + 0.45 * u01(mix64(hc + 3));
-        const double esn0_db[4] = {20.0, 14.0, 11.0, 9.0};
+        const double esn0_db[4] = {20.0, 18.0, 16.0, 14.0};
         const double esn0 = pow(10.0, esn0_db[c & 3] / 10.0);
         sc.sigma = sc.amp * sin(1.169) * sqrt(sps / esn0);
         sc.theta0 = u01(mix64(hc + 4));                       // in turns

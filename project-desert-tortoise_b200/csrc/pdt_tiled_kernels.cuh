@@ -1,0 +1,773 @@
+// pdt_tiled_kernels.cuh — sm_100a kernels of the tiled engine (see pdt_tiled.cuh for the arithmetic and the design).
+//
+// Launch order per batch (one stream, no host synchronisation in between):
+//   k_norm      StaticGain of the first chunk                                  warp per capture
+//   k_sp        sample_phase = approx-atan2(Q, I) for every sample             data-parallel, float4
+//   k_acquire   PLL acquisition (sweep + lock detector) up to the lock latch   CTA per capture, block-speculative
+//   k_estimate  carrier frequency/phase guess per tile (decimate + 1024-FFT)   warp per tile
+//   k_pll_core  track-mode phase/frequency recurrence, warm-up + main           lane per tile
+//   k_pll_fix   accept tiles whose warm-up state is bit-identical, else re-run  thread per capture
+//   k_front<L>  NCO sincos + derotation + ×L interpolating FIR (exact order)    CTA per 3328-sample span
+//   k_agc_core  AGC gain recurrence, warm-up + main                             lane per tile
+//   k_agc_fix   same verification for the AGC                                   thread per capture
+//   k_back      Gardner -> Manchester -> ByteSync -> frame table                warp per capture
+#pragma once
+
+#include "pdt_tiled.cuh"
+
+namespace pdt {
+namespace tiled {
+
+struct TiledArgs {
+    ChainConst  cc;
+    const void *iq; int pcm16; u64 stride; const u64 *n_samples; u64 n_uniform; uint32_t n_captures;
+    u64         ws_stride;   // samples between captures in the workspaces below (multiple of 4: float4 alignment)
+    // workspaces (device)
+    float      *sp;          // [captures][stride]      sample_phase
+    float      *ph;          // [captures][stride]      PLL phase used to derotate each sample
+    float      *y;           // [captures][stride·L]    FIR output
+    float      *z;           // [captures][stride·L]    AGC output
+    AcqResult  *acq;         // [captures]
+    LoopState2 *guess, *pll_start, *pll_end;     // [captures][pll.max_tiles]
+    LoopState2 *agc_start, *agc_end;             // [captures][agc_max_tiles]
+    uint32_t   *counters;    // [0] PLL tiles re-run, [1] AGC tiles re-run, [2] acquisition flag restarts
+    TilePlan    pll;         // in input samples
+    u64         agc_min_tile; unsigned agc_max_tiles;   // in interpolated samples
+    int         est_decim;   // D
+    float       est_fmax;    // peak search limit (Hz)
+    TrackConst  acq_gains;   // unused (acquisition gains come from pll_begin) — kept for alignment of the struct
+    pdt_capture_stats *stats; pdt_frame *frames; const pdt_traces *traces;
+};
+
+PDT_DEV u64 cap_len(const TiledArgs &a, uint32_t c) { return a.n_samples ? a.n_samples[c] : a.n_uniform; }
+
+PDT_DEV TrackConst track_const(const TiledArgs &a, const AcqResult &acq)
+{
+    TrackConst k;
+    k.alpha = acq.alpha; k.beta = acq.beta;
+    k.max_freq = 2.0 * PDT_PI * a.cc.pll.freq_range / a.cc.pll.Fs;       // CarrierTrackingPLL.c:93-94
+    k.min_freq = -2.0 * PDT_PI * a.cc.pll.freq_range / a.cc.pll.Fs;
+    return k;
+}
+
+// AGC tile plan of one capture, in interpolated samples.  The AGC loop contracts with time constant gain/decay
+// samples (AGC.c:120: gain -= (|x·gain| - 1)·rate); ~16 of them bring a 1/mean|y| guess down to a bit-identical
+// gain (measured), 22 are used.  The gain the loop will settle at is 1/mean|y|, measured by k_agc_plan
+// on the FIR output; an estimate that is off only costs a re-run in k_agc_fix.
+PDT_DEV TilePlan agc_plan(const TiledArgs &a, const AcqResult &acq)
+{
+    TilePlan p;
+    float g = acq.agc_gain_est; if (!(g > 0.25f)) g = 0.25f;
+    double w = 22.0 * (double)g / (double)a.cc.agc_decay;
+    if (w < (double)a.agc_min_tile) w = (double)a.agc_min_tile;
+    if (w > 1e15) w = 1e15;
+    p.W = ((u64)w + 3) & ~3ull;
+    p.T = p.W; p.T0 = 2 * p.W; p.max_tiles = a.agc_max_tiles;
+    return p;
+}
+
+__global__ void __launch_bounds__(128) k_agc_plan(const TiledArgs a)
+{
+    const uint32_t cap = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (cap >= a.n_captures) return;
+    const u64 nL = cap_len(a, cap) * a.cc.L;
+    const float *y = a.y + (u64)cap * a.ws_stride * a.cc.L;
+    // 32 evenly spread segments of 256 samples (lane = segment); the largest segment mean bounds the smallest gain,
+    // the smallest mean the largest gain: use the median-ish robust choice = overall mean
+    float sum = 0.0f; unsigned cnt = 0;
+    if (nL > 0) {
+        const u64 seg = nL / 32;
+        const u64 b0 = (u64)lane * seg;
+        const u64 len = seg < 256 ? seg : 256;
+        for (u64 i = 0; i < len; i++) { sum += fabsf(y[b0 + i]); cnt++; }
+    }
+    for (int o = 16; o; o >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); cnt += __shfl_xor_sync(0xffffffffu, cnt, o); }
+    if (lane == 0) a.acq[cap].agc_gain_est = (sum > 0.0f) ? (float)cnt / sum : a.acq[cap].norm;
+}
+
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_norm(const TiledArgs a)
+{
+    const uint32_t cap = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (cap >= a.n_captures) return;
+    AcqResult *r = &a.acq[cap];
+    if (a.cc.norm_override != 0) { if (lane == 0) r->norm = a.cc.norm_override; return; }
+    const u64 n = cap_len(a, cap), first = (u64)cap * a.stride;
+    const u64 m = n < a.cc.chunk ? n : a.cc.chunk;
+    if (m == 0) { if (lane == 0) r->norm = 1.0f; return; }
+    float x0, y0;
+    load_iq1(a.iq, a.pcm16, first, x0, y0);
+    float level = hypot_exact(x0, y0);                                   // AGC.c:58
+    for (u64 base = 0; base < m; base += 32) {
+        const u64 i = base + lane;
+        float h = 0.0f;
+        if (i < m) { float p, q; load_iq1(a.iq, a.pcm16, first + i, p, q); h = hypot_exact(p, q); }
+        const int cnt = (int)((m - base < 32) ? (m - base) : 32);
+        for (int j = 0; j < cnt; j++) {                                  // AGC.c:62-71, strictly serial
+            const float hj = __shfl_sync(0xffffffffu, h, j);
+            level += hj;
+            level /= 2.0;
+        }
+    }
+    if (lane == 0) r->norm = (float)1.0 / level;
+}
+
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_sp(const TiledArgs a)
+{
+    const uint32_t cap = blockIdx.y;
+    const u64 n = cap_len(a, cap), first = (u64)cap * a.stride;
+    float *sp = a.sp + (u64)cap * a.ws_stride;
+    const bool vec = !a.pcm16 && !(first & 1) && !(reinterpret_cast<uintptr_t>(a.iq) & 15);
+    for (u64 i = ((u64)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += (u64)gridDim.x * blockDim.x * 4) {
+        if (i + 4 <= n && vec) {
+            const float4 v0 = ld4(reinterpret_cast<const float *>(a.iq) + 2 * (first + i));
+            const float4 v1 = ld4(reinterpret_cast<const float *>(a.iq) + 2 * (first + i) + 4);
+            float4 o;
+            o.x = arctan2_approx(v0.y, v0.x); o.y = arctan2_approx(v0.w, v0.z);     // CarrierTrackingPLL.c:128
+            o.z = arctan2_approx(v1.y, v1.x); o.w = arctan2_approx(v1.w, v1.z);
+            st4(sp + i, o);
+        } else {
+            for (u64 j = i; j < n && j < i + 4; j++) {
+                float p, q;
+                load_iq1(a.iq, a.pcm16, first + j, p, q);
+                sp[j] = arctan2_approx(q, p);
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Acquisition.  Per sample the reference does (CarrierTrackingPLL.c:102-275)
+//   [A] derotate with the current phase, EMA of |output phase|  -> avg_phase            (feeds [C])
+//   [B] phase/frequency update from the raw sample phase        (11 dependent flops)
+//   [C] while avg_phase looks like noise: frequency += sweep     (feeds the next [B])
+//   [D] EMA lock detector; first crossing of the threshold latches the loop into track mode.
+// The feedback [A]->[C] is ~300 cycles long but its outcome (a boolean) changes a handful of times per
+// capture, so a block of ACQ_B samples is run with the boolean SPECULATED constant: [B]+[C] serially on one
+// lane, [A]'s transcendental part on all threads, the two EMAs serially on two lanes of different warps, then
+// the booleans are compared; on the first difference the block restarts from that sample with the corrected
+// flag.  The committed trajectory is exactly the serial one.
+// ---------------------------------------------------------------------------------------------------
+constexpr int ACQ_B = 512;
+constexpr int ACQ_THREADS = 256;
+
+struct AcqSmem {
+    float sp[2][ACQ_B], a[2][ACQ_B], b[2][ACQ_B];               // inputs of the current and the next block
+    float ph[2][ACQ_B + 1], fr[2][ACQ_B + 1], sw[2][ACQ_B + 1]; // state BEFORE each sample (and after the last)
+    float aterm[ACQ_B], lterm[ACQ_B];
+    float avg[ACQ_B + 1], lks[ACQ_B + 1];
+    unsigned char nl[2][ACQ_B], nl_true[ACQ_B];
+    int mism, latch;
+};
+
+// [B]+[C]: serial core over samples [r, m) of one block with the flags nl[]
+PDT_DEV void acq_core(float *ph, float *fr, float *sw, const float *sp, const unsigned char *nl, int r, int m, const TrackConst &k)
+{
+    float phase = ph[r], freq = fr[r], sweep = sw[r];
+#pragma unroll 4
+    for (int i = r; i < m; i++) {
+        ph[i] = phase; fr[i] = freq; sw[i] = sweep;
+        pll_track_step(phase, freq, sp[i], k);
+        const float f2 = freq + sweep;                                          // CarrierTrackingPLL.c:232-246
+        float s2 = (f2 >= 0) ? fabsf(sweep) : -fabsf(sweep);
+        s2 = (f2 <= k.min_freq) ? -sweep : s2;
+        s2 = (f2 >= k.max_freq) ? -sweep : s2;
+        const bool on = nl[i] != 0;
+        freq = on ? f2 : freq;
+        sweep = on ? s2 : sweep;
+    }
+    ph[m] = phase; fr[m] = freq; sw[m] = sweep;
+}
+
+__global__ void __launch_bounds__(ACQ_THREADS) k_acquire(const TiledArgs a)
+{
+    __shared__ AcqSmem s;
+    const uint32_t cap = blockIdx.x;
+    const int tid = threadIdx.x;
+    const u64 n = cap_len(a, cap), first = (u64)cap * a.stride;
+    const PllParams &pp = a.cc.pll;
+    AcqResult *res = &a.acq[cap];
+    const u64 wfirst = (u64)cap * a.ws_stride;
+    float *ph_out = a.ph + wfirst;
+
+    PllState ps;
+    pll_reset(ps);
+    pll_begin(ps, pp);
+    TrackConst kacq; kacq.alpha = ps.alpha; kacq.beta = ps.beta; kacq.max_freq = ps.max_freq; kacq.min_freq = ps.min_freq;
+    const float avg_alpha = 0.00005f;
+    uint32_t restarts = 0;
+
+    auto load_inputs = [&](int buf, u64 i0) {
+        const int m = (int)((n - i0 < ACQ_B) ? (n - i0) : ACQ_B);
+        for (int i = tid; i < m; i += ACQ_THREADS) {
+            float p, q;
+            load_iq1(a.iq, a.pcm16, first + i0 + i, p, q);
+            s.a[buf][i] = p; s.b[buf][i] = q; s.sp[buf][i] = a.sp[wfirst + i0 + i];
+        }
+    };
+
+    if (n == 0) {
+        if (tid == 0) {
+            res->locked = 0; res->lock_sample = 0; res->track_begin = 0; res->phase = ps.phase; res->freq = ps.freq;
+            res->sweep = ps.sweep; res->avg_phase = ps.avg_phase; res->locksig = ps.locksig; res->lock_freq_hz = 0;
+            res->alpha = kacq.alpha; res->beta = kacq.beta;
+        }
+        return;
+    }
+    load_inputs(0, 0);
+    {
+        const int m0 = (int)(n < ACQ_B ? n : ACQ_B);
+        for (int i = tid; i < m0; i += ACQ_THREADS) s.nl[0][i] = 1;      // |π/2 - avg_phase| < 0.05 holds for the initial avg_phase = π/2
+    }
+    if (tid == 0) {
+        s.ph[0][0] = ps.phase; s.fr[0][0] = ps.freq; s.sw[0][0] = ps.sweep; s.avg[0] = ps.avg_phase; s.lks[0] = ps.locksig;
+    }
+    __syncthreads();
+    if (tid == 0) acq_core(s.ph[0], s.fr[0], s.sw[0], s.sp[0], s.nl[0], 0, (int)(n < ACQ_B ? n : ACQ_B), kacq);
+    __syncthreads();
+
+    int r = 0;
+    bool next_loaded = false;
+    for (u64 i0 = 0; i0 < n;) {
+        const int cur = (int)((i0 / ACQ_B) & 1), nxt = cur ^ 1;
+        const int m = (int)((n - i0 < ACQ_B) ? (n - i0) : ACQ_B);
+        const bool has_next = i0 + ACQ_B < n;
+        const int m_next = has_next ? (int)((n - i0 - ACQ_B < ACQ_B) ? (n - i0 - ACQ_B) : ACQ_B) : 0;
+        // ---- [A],[D] feed-forward parts of block `cur` from r; stage the next block's inputs -------------
+        for (int i = r + tid; i < m; i += ACQ_THREADS) {
+            float ti, tr;
+            sincos_exact(s.ph[cur][i], ti, tr);                                     // :106-107
+            const float p = s.a[cur][i], q = s.b[cur][i], nti = -ti;
+            const float mre = p * tr - q * nti, mim = p * nti + q * tr;            // :110
+            s.aterm[i] = avg_alpha * fabsf(arctan2_approx(mim, mre));               // :117,:124
+            const float mag2 = p * p + q * q;                                       // :193-220
+            const float inv = q_rsqrt(mag2);
+            const float nre = p * inv, nim = q * inv;
+            s.lterm[i] = pp.lock_alpha * (nre * tr + nim * ti);
+        }
+        if (has_next && !next_loaded) load_inputs(nxt, i0 + ACQ_B);
+        next_loaded = true;
+        __syncthreads();
+        // ---- serial phase: the two EMAs of block `cur`, and SPECULATIVELY the core of the next block -------
+        if (tid == 0) {
+            if (has_next) {
+                const unsigned char f = s.nl[cur][m - 1];
+                for (int i = 0; i < m_next; i++) s.nl[nxt][i] = f;
+                s.ph[nxt][0] = s.ph[cur][m]; s.fr[nxt][0] = s.fr[cur][m]; s.sw[nxt][0] = s.sw[cur][m];
+                acq_core(s.ph[nxt], s.fr[nxt], s.sw[nxt], s.sp[nxt], s.nl[nxt], 0, m_next, kacq);
+            }
+        } else if (tid == 32) {
+            float avg = s.avg[r];
+            int mism = m;
+            for (int i = r; i < m; i++) {
+                avg = (float)((double)avg * (1.0 - avg_alpha) + (double)s.aterm[i]);               // :124
+                s.avg[i + 1] = avg;
+                const unsigned char t = (double)fabsf((float)(PDT_PI / 2.0 - (double)avg)) < 0.05;   // :232
+                s.nl_true[i] = t;
+                if (t != s.nl[cur][i] && mism == m) mism = i;
+            }
+            s.mism = mism;
+        } else if (tid == 64) {
+            float lk = s.lks[r];
+            int latch = m;
+            for (int i = r; i < m; i++) {
+                lk = (float)((double)lk * (1.0 - pp.lock_alpha) + (double)s.lterm[i]);             // :220
+                s.lks[i + 1] = lk;
+                if (lk > pp.lock_thresh && latch == m) latch = i;                                  // :266
+            }
+            s.latch = latch;
+        }
+        __syncthreads();
+        const int mism = s.mism, latch = s.latch;
+        if (latch < mism) {
+            // every flag up to and including the latch sample was right: commit and leave acquisition
+            const int cnt = latch + 1;
+            for (int i = tid; i < cnt; i += ACQ_THREADS) ph_out[i0 + i] = s.ph[cur][i];
+            if (tid == 0) {
+                const float freq = s.fr[cur][cnt];
+                res->locked = 1; res->lock_sample = i0 + latch; res->track_begin = i0 + cnt;
+                res->phase = s.ph[cur][cnt]; res->freq = freq; res->sweep = s.sw[cur][cnt];
+                res->avg_phase = s.avg[cnt]; res->locksig = s.lks[cnt];
+                res->lock_freq_hz = freq * pp.Fs / (2.0 * PDT_PI);                                  // :269
+                const float bw = pp.bw_track, damp = ps.damp;                                       // :272-273
+                res->alpha = (4.0 * damp * bw) / (1.0 + 2.0 * damp * bw + bw * bw);
+                res->beta  = (4.0 * bw * bw) / (1.0 + 2.0 * damp * bw + bw * bw);
+                if (restarts) atomicAdd(&a.counters[2], restarts);
+            }
+            return;
+        }
+        if (mism < m) {
+            // a speculated flag was wrong at sample `mism`: redo the core of THIS block from there (the speculative
+            // next block is discarded).  New speculation for the rest of the block: the flags the EMA just produced.
+            // They were computed from phases that are about to change, but avg_phase moves by < 2e-4 per sample
+            // whatever the phase is, so they are almost always right (a constant guess dithers near the threshold).
+            for (int i = mism + tid; i < m; i += ACQ_THREADS) s.nl[cur][i] = s.nl_true[i];
+            __syncthreads();
+            if (tid == 0) { acq_core(s.ph[cur], s.fr[cur], s.sw[cur], s.sp[cur], s.nl[cur], mism, m, kacq); restarts++; }
+            r = mism;
+            __syncthreads();
+            continue;
+        }
+        // block consistent: commit it; the speculative core of the next block used the right start state and flag
+        for (int i = tid; i < m; i += ACQ_THREADS) ph_out[i0 + i] = s.ph[cur][i];
+        if (tid == 0) { s.avg[0] = s.avg[m]; s.lks[0] = s.lks[m]; }
+        if (!has_next && tid == 0) {
+            res->locked = 0; res->lock_sample = 0; res->track_begin = n;
+            res->phase = s.ph[cur][m]; res->freq = s.fr[cur][m]; res->sweep = s.sw[cur][m];
+            res->avg_phase = s.avg[m]; res->locksig = s.lks[m];
+            res->lock_freq_hz = 0; res->alpha = kacq.alpha; res->beta = kacq.beta;
+            if (restarts) atomicAdd(&a.counters[2], restarts);
+        }
+        i0 += ACQ_B; r = 0; next_loaded = false;
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// carrier guess per tile: warp per (capture, tile >= 1)
+// ---------------------------------------------------------------------------------------------------
+constexpr int EST_WARPS = 4;
+
+__global__ void __launch_bounds__(EST_WARPS * 32) k_estimate(const TiledArgs a)
+{
+    __shared__ float2 zs[EST_WARPS][EST_FFT];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const unsigned per_cap = a.pll.max_tiles - 1;
+    const u64 wid = (u64)blockIdx.x * EST_WARPS + wib;
+    if (per_cap == 0 || wid >= (u64)a.n_captures * per_cap) return;
+    const uint32_t cap = (uint32_t)(wid / per_cap);
+    const unsigned k = 1 + (unsigned)(wid % per_cap);
+    const AcqResult &acq = a.acq[cap];
+    const u64 n = cap_len(a, cap), first = (u64)cap * a.stride;
+    u64 warm, begin, end;
+    if (!acq.locked || !tile_range(acq.track_begin, n, a.pll, k, warm, begin, end)) return;
+    float2 *z = zs[wib];
+    const int D = a.est_decim;
+    const long long w0 = (long long)warm - (long long)EST_FFT * D;
+    // decimate by block sums, store bit-reversed
+    for (int j = lane; j < EST_FFT; j += 32) {
+        float sr = 0.f, si = 0.f;
+        const long long b0 = w0 + (long long)j * D;
+        for (int d = 0; d < D; d++) {
+            const long long i = b0 + d;
+            if (i >= 0) { float p, q; load_iq1(a.iq, a.pcm16, first + (u64)i, p, q); sr += p; si += q; }
+        }
+        z[__brev((unsigned)j) >> 22] = make_float2(sr, si);
+    }
+    __syncwarp();
+    for (int len = 2; len <= EST_FFT; len <<= 1) {
+        const int half = len >> 1;
+        for (int b = lane; b < EST_FFT / 2; b += 32) {
+            const int grp = b / half, pos = b - grp * half;
+            const int i0 = grp * len + pos, i1 = i0 + half;
+            float sn, cs;
+            est_sincos_turns(-(float)pos / (float)len, sn, cs);
+            const float2 u = z[i0], v = z[i1];
+            const float tr = v.x * cs - v.y * sn, ti = v.x * sn + v.y * cs;
+            z[i0] = make_float2(u.x + tr, u.y + ti);
+            z[i1] = make_float2(u.x - tr, u.y - ti);
+        }
+        __syncwarp();
+    }
+    const float fs_d = a.cc.pll.Fs / (float)D, bin_hz = fs_d / (float)EST_FFT;
+    int kmax = (int)(a.est_fmax / bin_hz) + 1;
+    if (kmax > EST_FFT / 2 - 2) kmax = EST_FFT / 2 - 2;
+    float best = -1.f; int best_k = 0;
+    for (int kk = -kmax + lane; kk <= kmax; kk += 32) {
+        const float2 v = z[kk & (EST_FFT - 1)];
+        const float m2 = v.x * v.x + v.y * v.y;
+        if (m2 > best) { best = m2; best_k = kk; }
+    }
+    for (int o = 16; o; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int ok = __shfl_xor_sync(0xffffffffu, best_k, o);
+        if (ob > best || (ob == best && ok < best_k)) { best = ob; best_k = ok; }
+    }
+    const float delta = est_peak_offset(z[(best_k - 1) & (EST_FFT - 1)], z[best_k & (EST_FFT - 1)], z[(best_k + 1) & (EST_FFT - 1)]);
+    const float f_hz = ((float)best_k + delta) * bin_hz;
+    const float cyc = f_hz / a.cc.pll.Fs;                  // cycles per sample
+    // phase of the carrier at `warm`: coherent sum over the last 1024 samples, derotated by the estimate
+    float ar = 0.f, ai = 0.f;
+    for (int j = lane; j < 1024; j += 32) {
+        const long long i = (long long)warm - 1024 + j;
+        if (i >= 0) {
+            float p, q, sn, cs;
+            load_iq1(a.iq, a.pcm16, first + (u64)i, p, q);
+            est_sincos_turns(-cyc * (float)(j - 1024), sn, cs);
+            ar += p * cs - q * sn; ai += p * sn + q * cs;
+        }
+    }
+    for (int o = 16; o; o >>= 1) { ar += __shfl_xor_sync(0xffffffffu, ar, o); ai += __shfl_xor_sync(0xffffffffu, ai, o); }
+    if (lane == 0) {
+        LoopState2 g;
+        g.a = atan2f(ai, ar);
+        g.b = 6.283185307179586f * cyc;
+        a.guess[(size_t)cap * a.pll.max_tiles + k] = g;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// PLL track core: lane per (capture, tile)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_pll_core(const TiledArgs a)
+{
+    const u64 gid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (u64)a.n_captures * a.pll.max_tiles) return;
+    // consecutive lanes take consecutive captures (same tile index): equal work per lane inside a warp
+    const uint32_t cap = (uint32_t)(gid % a.n_captures);
+    const unsigned k = (unsigned)(gid / a.n_captures);
+    const AcqResult &acq = a.acq[cap];
+    const u64 n = cap_len(a, cap), first = (u64)cap * a.stride;
+    u64 warm, begin, end;
+    if (!acq.locked || !tile_range(acq.track_begin, n, a.pll, k, warm, begin, end)) return;
+    const TrackConst kc = track_const(a, acq);
+    const float *sp = a.sp + (u64)cap * a.ws_stride;
+    float *ph = a.ph + (u64)cap * a.ws_stride;
+    const size_t slot = (size_t)cap * a.pll.max_tiles + k;
+    float phase, freq;
+    if (k == 0) { phase = acq.phase; freq = acq.freq; }
+    else {
+        const LoopState2 g = a.guess[slot];
+        phase = g.a; freq = g.b;
+        if (freq > kc.max_freq) freq = kc.max_freq; else if (freq < kc.min_freq) freq = kc.min_freq;
+        pll_track_run<false>(sp, ph, warm, begin, phase, freq, kc);
+    }
+    a.pll_start[slot] = LoopState2{phase, freq};
+    pll_track_run<true>(sp, ph, begin, end, phase, freq, kc);
+    a.pll_end[slot] = LoopState2{phase, freq};
+}
+
+PDT_DEV bool same_bits(const LoopState2 &x, const LoopState2 &y) { return pdt_f2u(x.a) == pdt_f2u(y.a) && pdt_f2u(x.b) == pdt_f2u(y.b); }
+
+PDT_DEV LoopState2 ld_state(const LoopState2 *p)
+{
+    // one 8-byte access: a concurrent writer (parallel repair pass) is seen either entirely or not at all
+    const unsigned long long v = *reinterpret_cast<const volatile unsigned long long *>(p);
+    LoopState2 r; r.a = pdt_u2f((uint32_t)v); r.b = pdt_u2f((uint32_t)(v >> 32));
+    return r;
+}
+PDT_DEV void st_state(LoopState2 *p, const LoopState2 &v)
+{
+    *reinterpret_cast<volatile unsigned long long *>(p) = (unsigned long long)pdt_f2u(v.a) | ((unsigned long long)pdt_f2u(v.b) << 32);
+}
+
+// Parallel repair pass: every tile whose warm-up state differs from the end state of its predecessor is re-run
+// from that end state, all such tiles at once.  A predecessor that is itself being repaired in the same pass may
+// still change; the state actually used is recorded in pll_start, so the next pass (or the final serial sweep in
+// k_pll_fix) sees the difference.  Tiles converge long before their end, so one pass almost always suffices.
+__global__ void __launch_bounds__(128) k_pll_fix_par(const TiledArgs a)
+{
+    const u64 gid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (u64)a.n_captures * a.pll.max_tiles) return;
+    const uint32_t cap = (uint32_t)(gid % a.n_captures);
+    const unsigned k = (unsigned)(gid / a.n_captures);
+    if (k == 0) return;
+    const AcqResult &acq = a.acq[cap];
+    const u64 n = cap_len(a, cap);
+    u64 warm, begin, end;
+    if (!acq.locked || !tile_range(acq.track_begin, n, a.pll, k, warm, begin, end)) return;
+    const size_t slot = (size_t)cap * a.pll.max_tiles + k;
+    const LoopState2 truth = ld_state(&a.pll_end[slot - 1]);
+    if (same_bits(ld_state(&a.pll_start[slot]), truth)) return;
+    const TrackConst kc = track_const(a, acq);
+    float phase = truth.a, freq = truth.b;
+    pll_track_run<true>(a.sp + (u64)cap * a.ws_stride, a.ph + (u64)cap * a.ws_stride, begin, end, phase, freq, kc);
+    st_state(&a.pll_start[slot], truth);
+    st_state(&a.pll_end[slot], LoopState2{phase, freq});
+    atomicAdd(&a.counters[0], 1u);
+}
+
+__global__ void __launch_bounds__(128) k_pll_fix(const TiledArgs a)
+{
+    const uint32_t cap = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cap >= a.n_captures) return;
+    const AcqResult &acq = a.acq[cap];
+    if (!acq.locked) return;
+    const u64 n = cap_len(a, cap), first = (u64)cap * a.stride;
+    const TrackConst kc = track_const(a, acq);
+    uint32_t fixed = 0;
+    for (unsigned k = 1; k < a.pll.max_tiles; k++) {
+        u64 warm, begin, end;
+        if (!tile_range(acq.track_begin, n, a.pll, k, warm, begin, end)) break;
+        const size_t slot = (size_t)cap * a.pll.max_tiles + k;
+        const LoopState2 truth = a.pll_end[slot - 1];
+        if (same_bits(a.pll_start[slot], truth)) continue;
+        float phase = truth.a, freq = truth.b;                        // speculation failed: re-run from the true state
+        pll_track_run<true>(a.sp + (u64)cap * a.ws_stride, a.ph + (u64)cap * a.ws_stride, begin, end, phase, freq, kc);
+        a.pll_start[slot] = truth;
+        a.pll_end[slot] = LoopState2{phase, freq};
+        fixed++;
+    }
+    if (fixed) atomicAdd(&a.counters[0], fixed);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// front: out = Im(x·e^{-jφ}) (CarrierTrackingPLL.c:106-113) then the ×L zero-stuff FIR (LowPassFilter.c:43-70)
+// ---------------------------------------------------------------------------------------------------
+constexpr int FRONT_THREADS = 128;
+constexpr int FRONT_SPAN = FRONT_THREADS * FIR_K;      // 3328 input samples per CTA
+
+template <int L>
+__global__ void __launch_bounds__(FRONT_THREADS) k_front(const TiledArgs a, const __grid_constant__ TapsRev taps)
+{
+    extern __shared__ __align__(16) float fsm[];
+    float *outs = fsm;                                  // [FRONT_SPAN + FIR_K]  (one block of history in front)
+    float *ys = fsm + FRONT_SPAN + FIR_K + 2;           // [FRONT_SPAN·L]
+    const uint32_t cap = blockIdx.y;
+    const int tid = threadIdx.x;
+    const u64 n = cap_len(a, cap), first = (u64)cap * a.stride;
+    const u64 base = (u64)blockIdx.x * FRONT_SPAN;
+    if (base >= n) return;
+    const float *ph = a.ph + (u64)cap * a.ws_stride;
+    const pdt_traces *tr = a.traces ? &a.traces[cap] : nullptr;
+    for (int idx = tid; idx < FRONT_SPAN + FIR_K; idx += FRONT_THREADS) {
+        const long long i = (long long)base - FIR_K + idx;
+        float o = 0.0f;
+        if (i >= 0 && (u64)i < n) {
+            float p, q, ti, tr_;
+            load_iq1(a.iq, a.pcm16, first + (u64)i, p, q);
+            sincos_exact(ph[i], ti, tr_);
+            const float nti = -ti;
+            o = p * nti + q * tr_;                                                  // :110,:113
+            if (tr && tr->pll_out && idx >= FIR_K) reinterpret_cast<float *>(tr->pll_out)[i] = o;
+        }
+        outs[idx] = o;
+    }
+    __syncthreads();
+    {
+        const u64 j0 = base + (u64)tid * FIR_K;
+        if (j0 < n) {
+            float prev[FIR_K], cur[FIR_K];
+#pragma unroll
+            for (int s = 0; s < FIR_K; s++) { prev[s] = outs[tid * FIR_K + s]; cur[s] = outs[(tid + 1) * FIR_K + s]; }
+            float *dst = ys + (size_t)tid * FIR_K * L;
+            fir_block26<L>(prev, cur, taps, [&](int o, float v) { dst[o] = v; });
+        }
+    }
+    __syncthreads();
+    const u64 span = (n - base < FRONT_SPAN) ? (n - base) : FRONT_SPAN;
+    float *y = a.y + (u64)cap * a.ws_stride * L + base * L;
+    for (u64 o = tid; o < span * L; o += FRONT_THREADS) y[o] = ys[o];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// AGC core: lane per (capture, tile)
+// ---------------------------------------------------------------------------------------------------
+PDT_DEV float agc_guess(const float *y, u64 at)
+{
+    // equilibrium of AGC.c:98-131 is E|y·g| = 1  ->  g ≈ 1 / mean|y| over the samples in front of the warm-up
+    const u64 cnt = at < 1024 ? at : 1024;
+    float sum = 0.0f;
+    for (u64 i = at - cnt; i < at; i++) sum += fabsf(y[i]);
+    if (!(sum > 0.0f)) return 1.0f;
+    return (float)cnt / sum;
+}
+
+__global__ void __launch_bounds__(128) k_agc_core(const TiledArgs a)
+{
+    const u64 gid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (u64)a.n_captures * a.agc_max_tiles) return;
+    const uint32_t cap = (uint32_t)(gid % a.n_captures);
+    const unsigned k = (unsigned)(gid / a.n_captures);
+    const AcqResult &acq = a.acq[cap];
+    const int L = a.cc.L;
+    const u64 nL = cap_len(a, cap) * L, first = (u64)cap * a.ws_stride * L;
+    const TilePlan plan = agc_plan(a, acq);
+    u64 warm, begin, end;
+    if (!tile_range(0, nL, plan, k, warm, begin, end)) return;
+    const float *y = a.y + first;
+    float *z = a.z + first;
+    const size_t slot = (size_t)cap * a.agc_max_tiles + k;
+    AgcState st;
+    st.init = 1;
+    if (k == 0) st.gain = acq.norm;                                      // AGC.c:92-96: first call seeds gain with `initial`
+    else {
+        st.gain = agc_guess(y, warm);
+        agc_run<false>(y, z, warm, begin, st, a.cc.agc_attack, a.cc.agc_decay);
+    }
+    a.agc_start[slot] = LoopState2{st.gain, 0.0f};
+    agc_run<true>(y, z, begin, end, st, a.cc.agc_attack, a.cc.agc_decay);
+    a.agc_end[slot] = LoopState2{st.gain, 0.0f};
+}
+
+__global__ void __launch_bounds__(128) k_agc_fix_par(const TiledArgs a)
+{
+    const u64 gid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (u64)a.n_captures * a.agc_max_tiles) return;
+    const uint32_t cap = (uint32_t)(gid % a.n_captures);
+    const unsigned k = (unsigned)(gid / a.n_captures);
+    if (k == 0) return;
+    const AcqResult &acq = a.acq[cap];
+    const int L = a.cc.L;
+    const u64 nL = cap_len(a, cap) * L, first = (u64)cap * a.ws_stride * L;
+    const TilePlan plan = agc_plan(a, acq);
+    u64 warm, begin, end;
+    if (!tile_range(0, nL, plan, k, warm, begin, end)) return;
+    const size_t slot = (size_t)cap * a.agc_max_tiles + k;
+    const LoopState2 truth = ld_state(&a.agc_end[slot - 1]);
+    if (same_bits(ld_state(&a.agc_start[slot]), truth)) return;
+    AgcState st; st.init = 1; st.gain = truth.a;
+    agc_run<true>(a.y + first, a.z + first, begin, end, st, a.cc.agc_attack, a.cc.agc_decay);
+    st_state(&a.agc_start[slot], truth);
+    st_state(&a.agc_end[slot], LoopState2{st.gain, 0.0f});
+    atomicAdd(&a.counters[1], 1u);
+}
+
+__global__ void __launch_bounds__(128) k_agc_fix(const TiledArgs a)
+{
+    const uint32_t cap = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cap >= a.n_captures) return;
+    const AcqResult &acq = a.acq[cap];
+    const int L = a.cc.L;
+    const u64 nL = cap_len(a, cap) * L, first = (u64)cap * a.ws_stride * L;
+    const TilePlan plan = agc_plan(a, acq);
+    uint32_t fixed = 0;
+    for (unsigned k = 1; k < a.agc_max_tiles; k++) {
+        u64 warm, begin, end;
+        if (!tile_range(0, nL, plan, k, warm, begin, end)) break;
+        const size_t slot = (size_t)cap * a.agc_max_tiles + k;
+        const LoopState2 truth = a.agc_end[slot - 1];
+        if (same_bits(a.agc_start[slot], truth)) continue;
+        AgcState st; st.init = 1; st.gain = truth.a;
+        agc_run<true>(a.y + first, a.z + first, begin, end, st, a.cc.agc_attack, a.cc.agc_decay);
+        a.agc_start[slot] = truth;
+        a.agc_end[slot] = LoopState2{st.gain, 0.0f};
+        fixed++;
+    }
+    if (fixed) atomicAdd(&a.counters[1], fixed);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// back: Gardner -> Manchester -> ByteSync, warp per capture, chunk by chunk (the chunk length is part of the
+// reference's numerics: Gardner's position is a float in chunk-relative samples).
+// The AGC output streams through a per-warp shared-memory window; lane 0 runs the recurrences.
+// ---------------------------------------------------------------------------------------------------
+constexpr int BACK_WIN = 4096;
+constexpr int BACK_WARPS = 2;
+
+__global__ void __launch_bounds__(BACK_WARPS * 32) k_back(const TiledArgs a)
+{
+    __shared__ float wins[BACK_WARPS][BACK_WIN];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t cap = blockIdx.x * BACK_WARPS + wib;
+    if (cap >= a.n_captures) return;
+    const ChainConst &cc = a.cc;
+    const int L = cc.L;
+    const u64 n = cap_len(a, cap);
+    const float *z = a.z + (u64)cap * a.ws_stride * L;
+    float *win = wins[wib];
+    pdt_frame *frames = a.frames + (size_t)cap * cc.max_frames;
+    const pdt_traces *tr = a.traces ? &a.traces[cap] : nullptr;
+    const unsigned full_out = cc.chunk * (unsigned)L;
+
+    BackState st;
+    back_reset(st);
+    gardner_begin(st.gar, cc.gardner_fs, cc.baud);
+
+    for (u64 base = 0; base < n; base += cc.chunk) {
+        const unsigned m = (unsigned)((n - base < cc.chunk) ? (n - base) : cc.chunk);
+        const unsigned n_out = m * (unsigned)L;
+        const u64 ibase = base * (u64)L;
+        const bool has_prev = base > 0;
+        bool first_symbol = true;
+        unsigned w0 = 0;
+        for (;;) {
+            // resident window: chunk-relative [w0, w0 + BACK_WIN)
+            if (((ibase + w0) & 3) == 0) {
+#pragma unroll 8
+                for (unsigned i = lane * 4; i < BACK_WIN; i += 128) {
+                    const unsigned idx = w0 + i;
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (idx + 4 <= n_out) v = ld4(z + ibase + idx);
+                    else {
+                        if (idx < n_out) v.x = z[ibase + idx];
+                        if (idx + 1 < n_out) v.y = z[ibase + idx + 1];
+                        if (idx + 2 < n_out) v.z = z[ibase + idx + 2];
+                    }
+                    st4(win + i, v);
+                }
+            } else {
+#pragma unroll 8
+                for (unsigned i = lane; i < BACK_WIN; i += 32) {
+                    const unsigned idx = w0 + i;
+                    win[i] = (idx < n_out) ? z[ibase + idx] : 0.0f;
+                }
+            }
+            __syncwarp();
+            int finished = 0;
+            if (lane == 0) {
+                for (;;) {
+                    const float nr = rintf(st.gar.next);
+                    if (!(nr < (float)n_out)) { finished = 1; break; }                 // GardenerClockRecovery.c:24
+                    const unsigned at = (unsigned)nr;
+                    if (at >= w0 + BACK_WIN) break;                                    // refill
+                    const float cur = win[at - w0];
+                    float half;
+                    const unsigned hi = (unsigned)rintf(st.gar.half);                  // :28 index-then-value reuse
+                    if (first_symbol) half = stale_lookup(z, ibase, hi, n_out, full_out, has_prev);
+                    else              half = (hi >= w0 && hi < w0 + BACK_WIN) ? win[hi - w0] : stale_lookup(z, ibase, hi, n_out, full_out, has_prev);
+                    first_symbol = false;
+                    float e = cc.g_kp * (cur - st.gar.prev) * half;                    // :43
+                    if (e > cc.g_range) e = cc.g_range; else if (e < -cc.g_range) e = -cc.g_range;
+                    st.gar.next = st.gar.next - e;
+                    st.gar.half = st.gar.next + st.gar.step / 2.0;                     // :59
+                    st.gar.next = st.gar.next + st.gar.step;
+                    st.gar.prev = cur;
+                    if (tr && st.n_sym < tr->cap) {
+                        if (tr->sym)         reinterpret_cast<float *>(tr->sym)[st.n_sym] = cur;
+                        if (tr->gardner_err) reinterpret_cast<float *>(tr->gardner_err)[st.n_sym] = e;
+                        if (tr->gardner_idx) tr->gardner_idx[st.n_sym] = ibase + at;
+                    }
+                    st.n_sym++;
+                    back_consume(st, cc, cur, ibase + at, frames, tr);
+                }
+            }
+            finished = __shfl_sync(0xffffffffu, finished, 0);
+            if (finished) break;
+            const float nr = __shfl_sync(0xffffffffu, rintf(st.gar.next), 0);
+            // next window starts a little before the pick so that the mid-sample (behind the pick) stays resident
+            const unsigned at = (unsigned)nr;
+            const unsigned back = (unsigned)(st.gar.step) + 8;
+            unsigned nw0 = at > back ? at - back : 0;
+            nw0 = __shfl_sync(0xffffffffu, nw0, 0);
+            w0 = nw0 & ~3u;
+            __syncwarp();
+        }
+        if (lane == 0) st.gar.next = st.gar.next - n_out;                              // :111
+        __syncwarp();
+    }
+    if (lane == 0) {
+        back_finish(st, frames);
+        const AcqResult &acq = a.acq[cap];
+        pdt_capture_stats s;
+        s.n_samples = n; s.n_symbols = st.n_sym; s.n_bits = st.n_bits; s.n_frames = st.n_frames;
+        s.locked = acq.locked; s.lock_sample = acq.lock_sample; s.lock_freq_hz = acq.lock_freq_hz;
+        s.norm_factor = acq.norm; s.avg_phase = acq.avg_phase;
+        s.final_phase = acq.phase; s.final_freq = acq.freq;
+        if (acq.locked) {
+            u64 warm, begin, end;
+            for (unsigned k = 0; k < a.pll.max_tiles; k++) {
+                if (!tile_range(acq.track_begin, n, a.pll, k, warm, begin, end)) break;
+                const LoopState2 e = a.pll_end[(size_t)cap * a.pll.max_tiles + k];
+                s.final_phase = e.a; s.final_freq = e.b;
+            }
+        }
+        s.final_gain = acq.norm;
+        {
+            const TilePlan plan = agc_plan(a, acq);
+            u64 warm, begin, end;
+            for (unsigned k = 0; k < a.agc_max_tiles; k++) {
+                if (!tile_range(0, n * L, plan, k, warm, begin, end)) break;
+                s.final_gain = a.agc_end[(size_t)cap * a.agc_max_tiles + k].a;
+            }
+        }
+        s.final_next = st.gar.next;
+        a.stats[cap] = s;
+    }
+}
+
+} // namespace tiled
+} // namespace pdt

@@ -54,9 +54,11 @@ class DevTraces:
                       gardner_err=z(cap), gardner_idx=z(cap, torch.int64), bits=z(cap, torch.uint8))
         self.cap = cap
 
-    def struct(self):
+    def struct(self, skip=()):
         s = pdt.Traces()
         for k, v in self.t.items():
+            if k in skip:
+                continue
             setattr(s, k, v.data_ptr())
         s.cap = self.cap
         return s
@@ -66,11 +68,17 @@ class DevTraces:
         return a if n is None else a[:n]
 
 
-def _run_batch_with_traces(torch, prec, mode, fs, iq, chunk=None, force_l1=False):
+ENGINES = {"exact": pdt.PDT_ENGINE_EXACT, "tiled": pdt.PDT_ENGINE_TILED}
+
+
+def _run_batch_with_traces(torch, prec, mode, fs, iq, chunk=None, force_l1=False, engine="exact", **overrides):
     p = pdt.default_params(prec, mode, fs)
     if chunk:
         p.chunk = chunk
     p.force_min_interp1 = int(force_l1)
+    p.engine = ENGINES[engine]
+    for k, v in overrides.items():
+        setattr(p, k, v)
     dt = np.float32 if prec == "f32" else np.float64
     iq = np.ascontiguousarray(iq, dt)
     n = iq.size // 2
@@ -79,7 +87,9 @@ def _run_batch_with_traces(torch, prec, mode, fs, iq, chunk=None, force_l1=False
     cap = n * L // 4 + 64
     tr = DevTraces(torch, dt, n, L, cap)
     d_iq = torch.from_numpy(iq).cuda()
-    d.demod_device(d_iq.data_ptr(), 1, n, traces=[tr.struct()])
+    assert d.engine == ENGINES[engine]
+    # the per-sample frequency and lock-detector taps exist only in the exact engine (asking for them selects it)
+    d.demod_device(d_iq.data_ptr(), 1, n, traces=[tr.struct(skip=("pll_freq", "lock") if engine == "tiled" else ())])
     stats, frames = d.fetch(1)
     return d, stats[0], frames[0], tr
 
@@ -87,17 +97,20 @@ def _run_batch_with_traces(torch, prec, mode, fs, iq, chunk=None, force_l1=False
 # ------------------------------------------------------------------------------------------------------
 # whole chain, batch API, with every intermediate stream compared against the oracle
 # ------------------------------------------------------------------------------------------------------
-def test_poes_5sec_clip_bit_exact_all_stages(torch_cuda, oracle32, golden_dir):
+@pytest.mark.parametrize("engine", ["exact", "tiled"])
+def test_poes_5sec_clip_bit_exact_all_stages(torch_cuda, oracle32, golden_dir, engine):
     rate, pcm = po.read_wav_pcm16(_golden(golden_dir, "5sec_clip.wav"))
     iq = oracle32.pcm16_to_complex(pcm)
     want = oracle32.chain(iq, rate, trace=True)
-    d, st, fr, tr = _run_batch_with_traces(torch_cuda, "f32", pdt.PDT_MODE_POES, rate, iq)
+    d, st, fr, tr = _run_batch_with_traces(torch_cuda, "f32", pdt.PDT_MODE_POES, rate, iq, engine=engine)
     assert (st["n_symbols"], st["n_bits"], st["n_frames"]) == (want["total_symbols"], want["total_bits"], want["total_frames"])
     assert st["locked"] == 1 and st["lock_sample"] == want["lock_sample"]
     assert np.float32(st["norm_factor"]) == np.float32(want["norm_factor"])
     ns, nb = int(st["n_symbols"]), int(st["n_bits"])
     for k_dev, k_or in (("pll_phase", "tr_phase"), ("pll_freq", "tr_freq"), ("pll_out", "tr_pll_out"), ("lpf", "tr_lpf"),
                         ("agc", "tr_agc")):
+        if engine == "tiled" and k_dev == "pll_freq":
+            continue
         assert np.array_equal(tr.host(k_dev), want[k_or]), k_dev
     assert np.array_equal(tr.host("sym", ns), want["tr_sym"])
     assert np.array_equal(tr.host("gardner_err", ns), want["tr_gerr"])
@@ -142,14 +155,16 @@ def test_argos_wav_packets(torch_cuda, oracle64, golden_dir):
     assert np.array_equal(tr.host("bits", nb), want["tr_bits"])
 
 
-@pytest.mark.parametrize("fs,chunk,seed", [(250000, 10000, 7), (250000, 4096, 8), (50000, 10000, 9), (18750, 10000, 10)])
-def test_poes_synthetic_vs_oracle(torch_cuda, oracle32, fs, chunk, seed):
-    """L = 1 / 3 / 8 (the historical 8x interpolator), ragged last chunk, non-default chunk length."""
+@pytest.mark.parametrize("fs,chunk,seed,engine", [(250000, 10000, 7, "exact"), (250000, 4096, 8, "exact"), (50000, 10000, 9, "exact"),
+                                                  (18750, 10000, 10, "exact"), (250000, 10000, 7, "tiled"), (250000, 4096, 8, "tiled"),
+                                                  (50000, 10000, 9, "tiled"), (75000, 10000, 11, "tiled"), (37500, 7000, 12, "tiled")])
+def test_poes_synthetic_vs_oracle(torch_cuda, oracle32, fs, chunk, seed, engine):
+    """L = 1 / 2 / 3 / 4 / 8 (the historical 8x interpolator), ragged last chunk, non-default chunk length, both engines."""
     pcm, info = make_poes_capture(int(1.3 * fs) + 123, fs, seed, esn0_db=11.0, doppler_hz=-2000.0 + 300 * seed)
     iq = oracle32.pcm16_to_complex(pcm)
     want = oracle32.chain(iq, fs, chunk=chunk, trace=True)
-    d, st, fr, tr = _run_batch_with_traces(torch_cuda, "f32", pdt.PDT_MODE_POES, fs, iq, chunk=chunk)
-    assert d.params.interp == {250000: 1, 50000: 3, 18750: 8}[fs]
+    d, st, fr, tr = _run_batch_with_traces(torch_cuda, "f32", pdt.PDT_MODE_POES, fs, iq, chunk=chunk, engine=engine)
+    assert d.params.interp == {250000: 1, 75000: 2, 50000: 3, 37500: 4, 18750: 8}[fs]
     assert want["total_frames"] >= 8
     ns, nb = int(st["n_symbols"]), int(st["n_bits"])
     assert (ns, nb, st["n_frames"]) == (want["total_symbols"], want["total_bits"], want["total_frames"])
@@ -164,6 +179,88 @@ def test_poes_synthetic_vs_oracle(torch_cuda, oracle32, fs, chunk, seed):
     if fs >= 50000:        # at 18.75 ksps (1.13 samples per chip before the 8x interpolator) the link itself makes bit errors
         assert all((b - a) % 320 == 1 for a, b in zip(cnt, cnt[1:]))
         assert sum(check_parity(f[2]) for f in full) >= len(full) - 1
+
+
+def test_tiled_long_capture_many_tiles_bit_exact(torch_cuda, oracle32):
+    """4 s @ 250 ksps: ~30 PLL tiles and several AGC tiles; every stream bit-identical to the serial oracle, and the
+    speculation is almost always accepted (re-runs are allowed, wrong results are not)."""
+    fs = 250000
+    pcm, info = make_poes_capture(1_000_000, fs, 21, esn0_db=14.0, doppler_hz=700.0, drift_hz_s=45.0, amplitude=0.2)
+    iq = oracle32.pcm16_to_complex(pcm)
+    want = oracle32.chain(iq, fs, trace=True)
+    d, st, fr, tr = _run_batch_with_traces(torch_cuda, "f32", pdt.PDT_MODE_POES, fs, iq, engine="tiled")
+    ns, nb = int(st["n_symbols"]), int(st["n_bits"])
+    assert st["locked"] == 1 and st["lock_sample"] == want["lock_sample"]
+    for k_dev, k_or in (("pll_phase", "tr_phase"), ("pll_out", "tr_pll_out"), ("lpf", "tr_lpf"), ("agc", "tr_agc")):
+        bad = np.nonzero(tr.host(k_dev) != want[k_or])[0]
+        assert bad.size == 0, (k_dev, bad[:5], bad.size)
+    assert (ns, nb, st["n_frames"]) == (want["total_symbols"], want["total_bits"], want["total_frames"])
+    assert np.array_equal(tr.host("gardner_idx", ns).astype(np.uint64), want["tr_gidx"])
+    assert np.array_equal(tr.host("gardner_err", ns), want["tr_gerr"])
+    assert np.array_equal(tr.host("bits", nb), want["tr_bits"])
+    _frames_text_equal_bytes(d.format_frames(fr, int(st["n_frames"])), want["text"])
+    pll_rerun, agc_rerun, acq_restarts, tiles = d.tiled_counters()
+    print("tiled counters", pll_rerun, agc_rerun, acq_restarts, tiles)
+    assert tiles >= 20 and pll_rerun <= 3 and agc_rerun <= 3
+
+
+def test_tiled_failed_speculation_is_repaired(torch_cuda, oracle32):
+    """Warm-up windows far too short to converge: the verification must reject them and the re-run must restore the
+    exact serial result (this is what makes the tiled engine exact by construction, not by luck)."""
+    fs = 250000
+    pcm, info = make_poes_capture(400_000, fs, 22, esn0_db=14.0, doppler_hz=-900.0, amplitude=0.3)
+    iq = oracle32.pcm16_to_complex(pcm)
+    want = oracle32.chain(iq, fs, trace=True)
+    d, st, fr, tr = _run_batch_with_traces(torch_cuda, "f32", pdt.PDT_MODE_POES, fs, iq, engine="tiled",
+                                           pll_warm=1024, pll_tile=20000, agc_min_tile=4096)
+    ns, nb = int(st["n_symbols"]), int(st["n_bits"])
+    for k_dev, k_or in (("pll_phase", "tr_phase"), ("pll_out", "tr_pll_out"), ("agc", "tr_agc")):
+        assert np.array_equal(tr.host(k_dev), want[k_or]), k_dev
+    assert (ns, nb, st["n_frames"]) == (want["total_symbols"], want["total_bits"], want["total_frames"])
+    assert np.array_equal(tr.host("bits", nb), want["tr_bits"])
+    pll_rerun, agc_rerun, _, _ = d.tiled_counters()
+    assert pll_rerun >= 5          # the speculation really did fail
+
+
+def test_tiled_unlocked_and_tiny_captures(torch_cuda, oracle32):
+    """Noise only (the PLL never latches: everything stays in the acquisition kernel), and captures shorter than one chunk."""
+    fs = 250000
+    rng = np.random.default_rng(5)
+    noise = (rng.standard_normal(2 * 150_000) * 900).astype(np.int16)
+    short, _ = make_poes_capture(5000, fs, 23)
+    for pcm in (noise, short, short[:2 * 3]):
+        iq = oracle32.pcm16_to_complex(pcm)
+        want = oracle32.chain(iq, fs, trace=True)
+        d, st, fr, tr = _run_batch_with_traces(torch_cuda, "f32", pdt.PDT_MODE_POES, fs, iq, engine="tiled")
+        ns, nb = int(st["n_symbols"]), int(st["n_bits"])
+        assert st["locked"] == int(want["locked"])
+        assert (ns, nb, st["n_frames"]) == (want["total_symbols"], want["total_bits"], want["total_frames"])
+        assert np.array_equal(tr.host("pll_out"), want["tr_pll_out"])
+        assert np.array_equal(tr.host("agc"), want["tr_agc"])
+        assert np.array_equal(tr.host("bits", nb), want["tr_bits"])
+
+
+def test_tiled_stream_groups_equal_exact_engine(torch_cuda):
+    """A batch large enough to be cut into capture groups on internal streams (fork/join inside pdt_demod_device):
+    stats and frames of every capture must equal the exact engine's, whatever the grouping."""
+    torch = torch_cuda
+    fs, n, caps = 250000, 120_000, 200
+    L = pdt.load("f32")
+    d_iq = torch.empty(caps * n * 2, dtype=torch.int16, device="cuda")
+    assert L.pdt_synth_poes_device(d_iq.data_ptr(), 1, caps, n, n, float(fs), 77, 0) == 0
+    res = {}
+    for eng in ("exact", "tiled"):
+        p = pdt.default_params("f32", pdt.PDT_MODE_POES, fs)
+        p.engine = ENGINES[eng]
+        d = pdt.Demod("f32", p, caps, n, 16)
+        d.demod_device(d_iq.data_ptr(), caps, n, pcm16=True)
+        res[eng] = d.fetch(caps)
+    (se, fe), (st, ft) = res["exact"], res["tiled"]
+    assert se["locked"].sum() >= caps // 2 and se["n_frames"].sum() > caps
+    for k in ("n_samples", "n_symbols", "n_bits", "n_frames", "locked", "lock_sample", "lock_freq_hz", "norm_factor",
+              "final_phase", "final_freq", "final_gain", "final_next"):
+        assert np.array_equal(se[k], st[k]), k
+    assert np.array_equal(fe, ft)
 
 
 def test_poes_golden_synth_c2(torch_cuda, golden_dir):
