@@ -301,7 +301,7 @@ def main():
     Lf = max(d.params.interp, 1)
     # algorithmic bytes per input sample of each kernel: what it must read + write once
     alg = {"k_chain_exact": bytes_per_sample, "k_sp": bytes_per_sample + 4, "k_front": bytes_per_sample + 4 + 4 * Lf,
-           "k_pll_core": 8, "k_agc_core": 8 * Lf, "k_back": 4 * Lf, "k_acquire": bytes_per_sample + 8}
+           "k_pll_core": 8, "k_agc_core": 8 * Lf, "k_gardner": 4 * Lf, "k_bits": 0.8 * Lf, "k_acquire": bytes_per_sample + 8}
     dom_name, k_ms = kernels[0]
     alg_bytes = C_ * n * alg.get(dom_name, bytes_per_sample)
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9

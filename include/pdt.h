@@ -72,6 +72,8 @@ typedef struct pdt_params {
     int      engine;             /* PDT_ENGINE_AUTO | PDT_ENGINE_EXACT | PDT_ENGINE_TILED */
     uint32_t pll_warm, pll_tile; /* tiled engine: PLL warm-up / tile length in samples (0 = derived from the loop bandwidth) */
     uint32_t agc_min_tile;       /* tiled engine: smallest AGC tile in interpolated samples (0 = default) */
+    uint32_t acq_first;          /* tiled engine: samples covered by the first acquisition pass; captures that have not
+                                    latched by then continue on a second stream (0 = default 131072) */
 } pdt_params;
 
 /* One decoded minor frame (POES, 104 bytes incl. the literal ED E2) or packet (ARGOS, 7 bytes). */

@@ -40,7 +40,8 @@ class Params(C.Structure):
                 ("lpf_fc", C.c_double), ("baud", C.c_double), ("gardner_err_lim", C.c_double),
                 ("gardner_gain", C.c_double), ("manchester_resync", C.c_double), ("squelch_thresh", C.c_double),
                 ("norm_factor", C.c_double), ("sync_word", C.c_char * 32), ("sync_len", C.c_int),
-                ("engine", C.c_int), ("pll_warm", C.c_uint32), ("pll_tile", C.c_uint32), ("agc_min_tile", C.c_uint32)]
+                ("engine", C.c_int), ("pll_warm", C.c_uint32), ("pll_tile", C.c_uint32), ("agc_min_tile", C.c_uint32),
+                ("acq_first", C.c_uint32)]
 
 
 class Frame(C.Structure):

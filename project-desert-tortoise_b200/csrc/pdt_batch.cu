@@ -140,12 +140,13 @@ struct pdt_ctx {
     tiled::TiledArgs ta;                 // workspace pointers + plans of the tiled engine (engine == PDT_ENGINE_TILED)
     tiled::TapsRev   taps_rev;
     size_t      front_smem = 0;
-    static constexpr int MAX_GROUPS = 8;
-    cudaStream_t gstream[MAX_GROUPS] = {};
-    cudaEvent_t  ev_fork = nullptr, ev_join[MAX_GROUPS] = {};
+    static constexpr int MAX_GROUPS = 6;      // + the slow-capture stream + the caller's = the 8 hardware queues
+    static constexpr int MAX_MARKS = 48;
+    cudaStream_t gstream[MAX_GROUPS] = {}, sstream = nullptr;
+    cudaEvent_t  ev_fork = nullptr, ev_join[MAX_GROUPS] = {}, ev_acq[MAX_GROUPS] = {}, ev_sjoin = nullptr;
     int         profiling = 0, n_marks = 0;
-    cudaEvent_t marks[24] = {};
-    const char *mark_names[24] = {};
+    cudaEvent_t marks[MAX_MARKS] = {};
+    const char *mark_names[MAX_MARKS] = {};
 #endif
 };
 
@@ -160,6 +161,8 @@ static bool tiled_applicable(const pdt_params &p, const ChainConst &cc, uint32_t
     PllState ps; pll_reset(ps); pll_begin(ps, cc.pll);
     if (!((double)ps.max_freq + 10.0 * ((double)ps.alpha + (double)ps.beta) < 6.0)) return false;
     if (!(cc.pll.bw_track > 0) || !(cc.agc_decay > 0)) return false;
+    const double S = (double)cc.gardner_fs / (double)cc.baud;            // k_gardner: the window must hold several symbols
+    if (!(S > 2.0) || S > tiled::GAR_WIN / 8) return false;
     return true;
 }
 
@@ -195,6 +198,14 @@ static int tiled_setup(pdt_ctx *c)
     TA(t.guess, np * sizeof(LoopState2)); TA(t.pll_start, np * sizeof(LoopState2)); TA(t.pll_end, np * sizeof(LoopState2));
     TA(t.agc_start, na * sizeof(LoopState2)); TA(t.agc_end, na * sizeof(LoopState2));
     TA(t.counters, 4 * sizeof(uint32_t));
+    {
+        const double S = (double)cc.gardner_fs / (double)cc.baud;        // samples per symbol
+        t.sym_cap = (u64)((double)stride * cc.L / (S - 0.2)) + stride / cc.chunk + 64;
+        t.sym_cap = (t.sym_cap + 3) & ~3ull;
+        TA(t.sym, (size_t)c->max_captures * t.sym_cap * sizeof(float));
+        TA(t.gidx, (size_t)c->max_captures * t.sym_cap * sizeof(u64));
+        TA(t.gar, sizeof(GarRecord) * c->max_captures);
+    }
 #undef TA
     for (int u = 0; u < cc.N; u++) c->taps_rev.hr[u] = c->taps_h[cc.N - 1 - u];
     c->front_smem = sizeof(float) * ((size_t)FRONT_SPAN + FIR_K + 2 + (size_t)FRONT_SPAN * cc.L);
@@ -209,13 +220,89 @@ static void tiled_free(pdt_ctx *c)
     tiled::TiledArgs &t = c->ta;
     cudaFree(t.sp); cudaFree(t.ph); cudaFree(t.y); cudaFree(t.z); cudaFree(t.acq); cudaFree(t.guess);
     cudaFree(t.pll_start); cudaFree(t.pll_end); cudaFree(t.agc_start); cudaFree(t.agc_end); cudaFree(t.counters);
+    cudaFree(t.sym); cudaFree(t.gidx); cudaFree(t.gar);
 }
 
-// the kernel sequence for captures [c0, c0+cnt) of the batch on stream s
-static int tiled_run_group(pdt_ctx *c, const tiled::TiledArgs &base, uint32_t c0, uint32_t cnt, tiled::u64 n_max, cudaStream_t s, bool marks)
+// Kernel sequences for captures [c0, c0+cnt) of the batch.  `head` = StaticGain, sample phases and the first
+// acquisition pass; `pipeline` = everything behind the lock latch, for the captures the pass owns (slow_pass 0: those
+// that latched within the first acquisition pass, 1: the rest, after their second acquisition pass).
+struct GroupLaunch {
+    pdt_ctx *c; tiled::TiledArgs t; uint32_t cnt; tiled::u64 n_max; bool marks;
+    static unsigned blocks(tiled::u64 items, unsigned per) { return (unsigned)((items + per - 1) / per); }
+    void mark(cudaStream_t s, const char *name)
+    {
+        if (!marks || c->n_marks >= pdt_ctx::MAX_MARKS) return;
+        if (!c->marks[c->n_marks]) cudaEventCreate(&c->marks[c->n_marks]);
+        cudaEventRecord(c->marks[c->n_marks], s);
+        c->mark_names[c->n_marks++] = name;
+    }
+    void head(cudaStream_t s)
+    {
+        using namespace tiled;
+        mark(s, "begin");
+        k_norm<<<blocks((u64)cnt * 32, 128), 128, 0, s>>>(t);
+        mark(s, "k_norm");
+        dim3 g(std::min<unsigned>(blocks(n_max, 1024), 4096), cnt);
+        k_sp<<<g, 256, 0, s>>>(t);
+        mark(s, "k_sp");
+        k_acquire<<<cnt, ACQ_THREADS, 0, s>>>(t, 0);
+        mark(s, "k_acquire");
+        count_launch(3);
+    }
+    void acquire_rest(cudaStream_t s)
+    {
+        using namespace tiled;
+        k_acquire<<<cnt, ACQ_THREADS, 0, s>>>(t, 1);
+        mark(s, "k_acquire");
+        count_launch(1);
+    }
+    void pipeline(cudaStream_t s, int slow_pass)
+    {
+        using namespace tiled;
+        TiledArgs q = t;
+        q.slow_pass = slow_pass;
+        const int L = c->cc.L;
+        if (q.pll.max_tiles > 1)
+            k_estimate<<<blocks((u64)cnt * (q.pll.max_tiles - 1), EST_WARPS), EST_WARPS * 32, 0, s>>>(q);
+        mark(s, "k_estimate");
+        k_pll_core<<<blocks((u64)cnt * q.pll.max_tiles, 128), 128, 0, s>>>(q);
+        mark(s, "k_pll_core");
+        k_pll_fix_par<<<blocks((u64)cnt * q.pll.max_tiles, 128), 128, 0, s>>>(q);
+        k_pll_fix_par<<<blocks((u64)cnt * q.pll.max_tiles, 128), 128, 0, s>>>(q);
+        mark(s, "k_pll_fix_par");
+        k_pll_fix<<<blocks(cnt, 128), 128, 0, s>>>(q);
+        mark(s, "k_pll_fix");
+        {
+            dim3 g(blocks(n_max, FRONT_SPAN), cnt);
+            switch (L) {
+            case 1: k_front<1><<<g, FRONT_THREADS, c->front_smem, s>>>(q, c->taps_rev); break;
+            case 2: k_front<2><<<g, FRONT_THREADS, c->front_smem, s>>>(q, c->taps_rev); break;
+            case 3: k_front<3><<<g, FRONT_THREADS, c->front_smem, s>>>(q, c->taps_rev); break;
+            default: k_front<4><<<g, FRONT_THREADS, c->front_smem, s>>>(q, c->taps_rev); break;
+            }
+        }
+        mark(s, "k_front");
+        k_agc_plan<<<blocks((u64)cnt * 32, 128), 128, 0, s>>>(q);
+        mark(s, "k_agc_plan");
+        k_agc_core<<<blocks((u64)cnt * q.agc_max_tiles, 128), 128, 0, s>>>(q);
+        mark(s, "k_agc_core");
+        k_agc_fix_par<<<blocks((u64)cnt * q.agc_max_tiles, 128), 128, 0, s>>>(q);
+        mark(s, "k_agc_fix_par");
+        k_agc_fix<<<blocks(cnt, 128), 128, 0, s>>>(q);
+        mark(s, "k_agc_fix");
+        k_gardner<<<blocks(cnt, GAR_WARPS), GAR_WARPS * 32, 0, s>>>(q);
+        mark(s, "k_gardner");
+        k_bits<<<blocks(cnt, 32), 32, 0, s>>>(q);
+        mark(s, "k_bits");
+        count_launch(q.pll.max_tiles > 1 ? 12 : 11);
+    }
+};
+
+static GroupLaunch make_group(pdt_ctx *c, const tiled::TiledArgs &base, uint32_t c0, uint32_t cnt, tiled::u64 n_max, bool marks)
 {
     using namespace tiled;
-    TiledArgs t = base;
+    GroupLaunch g{c, base, cnt, n_max, marks};
+    TiledArgs &t = g.t;
     const int L = c->cc.L;
     const size_t elem = t.pcm16 ? 2 * sizeof(int16_t) : 2 * sizeof(float);
     t.iq = (const char *)base.iq + (size_t)c0 * t.stride * elem;
@@ -226,65 +313,18 @@ static int tiled_run_group(pdt_ctx *c, const tiled::TiledArgs &base, uint32_t c0
     t.acq += c0;
     t.guess += (size_t)c0 * t.pll.max_tiles; t.pll_start += (size_t)c0 * t.pll.max_tiles; t.pll_end += (size_t)c0 * t.pll.max_tiles;
     t.agc_start += (size_t)c0 * t.agc_max_tiles; t.agc_end += (size_t)c0 * t.agc_max_tiles;
+    t.sym += (size_t)c0 * t.sym_cap; t.gidx += (size_t)c0 * t.sym_cap; t.gar += c0;
     t.stats += c0; t.frames += (size_t)c0 * c->max_frames;
     if (t.traces) t.traces += c0;
-    auto blocks = [](u64 items, unsigned per) { return (unsigned)((items + per - 1) / per); };
-    auto mark = [&](const char *name) {
-        if (!marks || c->n_marks >= 24) return;
-        if (!c->marks[c->n_marks]) cudaEventCreate(&c->marks[c->n_marks]);
-        cudaEventRecord(c->marks[c->n_marks], s);
-        c->mark_names[c->n_marks++] = name;
-    };
-    mark("begin");
-    k_norm<<<blocks((u64)cnt * 32, 128), 128, 0, s>>>(t);
-    mark("k_norm");
-    {
-        dim3 g(std::min<unsigned>(blocks(n_max, 1024), 4096), cnt);
-        k_sp<<<g, 256, 0, s>>>(t);
-    }
-    mark("k_sp");
-    k_acquire<<<cnt, ACQ_THREADS, 0, s>>>(t);
-    mark("k_acquire");
-    if (t.pll.max_tiles > 1)
-        k_estimate<<<blocks((u64)cnt * (t.pll.max_tiles - 1), EST_WARPS), EST_WARPS * 32, 0, s>>>(t);
-    mark("k_estimate");
-    k_pll_core<<<blocks((u64)cnt * t.pll.max_tiles, 128), 128, 0, s>>>(t);
-    mark("k_pll_core");
-    k_pll_fix_par<<<blocks((u64)cnt * t.pll.max_tiles, 128), 128, 0, s>>>(t);
-    k_pll_fix_par<<<blocks((u64)cnt * t.pll.max_tiles, 128), 128, 0, s>>>(t);
-    mark("k_pll_fix_par");
-    k_pll_fix<<<blocks(cnt, 128), 128, 0, s>>>(t);
-    mark("k_pll_fix");
-    {
-        dim3 g(blocks(n_max, FRONT_SPAN), cnt);
-        switch (L) {
-        case 1: k_front<1><<<g, FRONT_THREADS, c->front_smem, s>>>(t, c->taps_rev); break;
-        case 2: k_front<2><<<g, FRONT_THREADS, c->front_smem, s>>>(t, c->taps_rev); break;
-        case 3: k_front<3><<<g, FRONT_THREADS, c->front_smem, s>>>(t, c->taps_rev); break;
-        default: k_front<4><<<g, FRONT_THREADS, c->front_smem, s>>>(t, c->taps_rev); break;
-        }
-    }
-    mark("k_front");
-    k_agc_plan<<<blocks((u64)cnt * 32, 128), 128, 0, s>>>(t);
-    mark("k_agc_plan");
-    k_agc_core<<<blocks((u64)cnt * t.agc_max_tiles, 128), 128, 0, s>>>(t);
-    mark("k_agc_core");
-    k_agc_fix_par<<<blocks((u64)cnt * t.agc_max_tiles, 128), 128, 0, s>>>(t);
-    mark("k_agc_fix_par");
-    k_agc_fix<<<blocks(cnt, 128), 128, 0, s>>>(t);
-    mark("k_agc_fix");
-    k_back<<<blocks(cnt, BACK_WARPS), BACK_WARPS * 32, 0, s>>>(t);
-    mark("k_back");
-    count_launch(t.pll.max_tiles > 1 ? 14 : 13);
-    PDT_CUDA(cudaGetLastError());
-    return PDT_OK;
+    return g;
 }
 
 // Captures are independent, and the kernels that carry the serial recurrences (k_acquire, k_pll_core, k_agc_core,
 // k_back) are latency-bound with few warps, while k_sp / k_front are throughput-bound.  The batch is therefore cut
 // into groups that run the same kernel sequence on internal streams, forked from and joined to the caller's
-// stream: one group's serial kernels overlap another group's bulk kernels, and a capture that takes long to
-// acquire lock only delays its own group.
+// stream: one group's serial kernels overlap another group's bulk kernels.  Inside a group the captures that have
+// not latched after the first acquisition pass (`acq_first` samples) move to a second stream, where their serial
+// acquisition continues while the majority is already running the rest of the chain.
 static int tiled_run(pdt_ctx *c, const void *d_iq, int pcm16, uint32_t n_captures, uint64_t stride, const uint64_t *n_samples,
                      const pdt_traces *traces, cudaStream_t s)
 {
@@ -297,29 +337,58 @@ static int tiled_run(pdt_ctx *c, const void *d_iq, int pcm16, uint32_t n_capture
     if (n_samples) { n_max = 0; for (uint32_t i = 0; i < n_captures; i++) n_max = std::max<u64>(n_max, n_samples[i]); }
     if (n_max == 0) return PDT_OK;
     const int L = c->cc.L;
+    const u64 acq_first = c->params.acq_first ? c->params.acq_first : 131072;
+    t.acq_first = (n_max > 2 * acq_first) ? ((acq_first + ACQ_B - 1) / ACQ_B) * ACQ_B : 0;
+    const bool two_pass = t.acq_first != 0;
     PDT_CUDA(cudaMemsetAsync(t.counters, 0, 4 * sizeof(uint32_t), s));
     c->n_marks = 0;
     int groups = (int)std::min<uint32_t>(pdt_ctx::MAX_GROUPS, (n_captures + 63) / 64);
     if (c->profiling || traces || groups < 2) {
-        const int rc = tiled_run_group(c, t, 0, n_captures, n_max, s, c->profiling != 0);
-        if (rc != PDT_OK) return rc;
+        GroupLaunch g = make_group(c, t, 0, n_captures, n_max, c->profiling != 0);
+        g.head(s);
+        g.pipeline(s, 0);
+        if (two_pass) { g.acquire_rest(s); g.pipeline(s, 1); }
     } else {
         if (!c->ev_fork) PDT_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
         PDT_CUDA(cudaEventRecord(c->ev_fork, s));
         const uint32_t per = (n_captures + groups - 1) / groups;
-        for (int g = 0; g < groups; g++) {
-            const uint32_t c0 = (uint32_t)g * per;
+        int used = 0;
+        for (int gi = 0; gi < groups; gi++) {
+            const uint32_t c0 = (uint32_t)gi * per;
             if (c0 >= n_captures) break;
             const uint32_t cnt = std::min<uint32_t>(per, n_captures - c0);
-            if (!c->gstream[g]) PDT_CUDA(cudaStreamCreateWithFlags(&c->gstream[g], cudaStreamNonBlocking));
-            if (!c->ev_join[g]) PDT_CUDA(cudaEventCreateWithFlags(&c->ev_join[g], cudaEventDisableTiming));
-            PDT_CUDA(cudaStreamWaitEvent(c->gstream[g], c->ev_fork, 0));
-            const int rc = tiled_run_group(c, t, c0, cnt, n_max, c->gstream[g], false);
-            if (rc != PDT_OK) return rc;
-            PDT_CUDA(cudaEventRecord(c->ev_join[g], c->gstream[g]));
-            PDT_CUDA(cudaStreamWaitEvent(s, c->ev_join[g], 0));
+            if (!c->gstream[gi]) PDT_CUDA(cudaStreamCreateWithFlags(&c->gstream[gi], cudaStreamNonBlocking));
+            if (!c->ev_join[gi]) PDT_CUDA(cudaEventCreateWithFlags(&c->ev_join[gi], cudaEventDisableTiming));
+            PDT_CUDA(cudaStreamWaitEvent(c->gstream[gi], c->ev_fork, 0));
+            GroupLaunch g = make_group(c, t, c0, cnt, n_max, false);
+            g.head(c->gstream[gi]);
+            if (two_pass) {
+                if (!c->ev_acq[gi]) PDT_CUDA(cudaEventCreateWithFlags(&c->ev_acq[gi], cudaEventDisableTiming));
+                PDT_CUDA(cudaEventRecord(c->ev_acq[gi], c->gstream[gi]));
+            }
+            g.pipeline(c->gstream[gi], 0);
+            PDT_CUDA(cudaEventRecord(c->ev_join[gi], c->gstream[gi]));
+            PDT_CUDA(cudaStreamWaitEvent(s, c->ev_join[gi], 0));
+            used = gi + 1;
+        }
+        if (two_pass) {
+            // ONE slow-capture stream for the whole batch (streams beyond the device's 8 hardware queues alias, and a
+            // launch waiting behind the long second acquisition pass would block every stream sharing its queue)
+            if (!c->sstream) {
+                int lo = 0, hi = 0;
+                cudaDeviceGetStreamPriorityRange(&lo, &hi);
+                PDT_CUDA(cudaStreamCreateWithPriority(&c->sstream, cudaStreamNonBlocking, hi));
+            }
+            if (!c->ev_sjoin) PDT_CUDA(cudaEventCreateWithFlags(&c->ev_sjoin, cudaEventDisableTiming));
+            for (int gi = 0; gi < used; gi++) PDT_CUDA(cudaStreamWaitEvent(c->sstream, c->ev_acq[gi], 0));
+            GroupLaunch whole = make_group(c, t, 0, n_captures, n_max, false);
+            whole.acquire_rest(c->sstream);
+            whole.pipeline(c->sstream, 1);
+            PDT_CUDA(cudaEventRecord(c->ev_sjoin, c->sstream));
+            PDT_CUDA(cudaStreamWaitEvent(s, c->ev_sjoin, 0));
         }
     }
+    PDT_CUDA(cudaGetLastError());
     if (traces) {      // trace taps that are whole workspaces: copy them out (test/debug path)
         for (uint32_t i = 0; i < n_captures; i++) {
             const u64 n = n_samples ? n_samples[i] : stride;
@@ -473,7 +542,10 @@ void pdt_destroy(pdt_ctx *c)
     if (c->engine == PDT_ENGINE_TILED) tiled_free(c);
     for (cudaEvent_t e : c->marks) if (e) cudaEventDestroy(e);
     for (cudaStream_t gs : c->gstream) if (gs) cudaStreamDestroy(gs);
+    if (c->sstream) cudaStreamDestroy(c->sstream);
     for (cudaEvent_t e : c->ev_join) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->ev_acq) if (e) cudaEventDestroy(e);
+    if (c->ev_sjoin) cudaEventDestroy(c->ev_sjoin);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
 #endif
     delete c;

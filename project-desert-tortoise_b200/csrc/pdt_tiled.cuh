@@ -80,7 +80,8 @@ PDT_DEV void pll_track_step(float &phase, float &freq, float sp, const TrackCons
 // ---------------------------------------------------------------------------------------------------
 struct AcqResult {
     int   locked;               // latch fired inside the capture
-    int   pad;
+    int   slow;                 // not latched within the first acquisition pass: handled by the slow-capture pipeline
+    u64   resume_at;            // where the second acquisition pass continues (loop state below is the state before it)
     u64   lock_sample;          // ℓ : absolute index of the latch sample
     u64   track_begin;          // first sample handled by the tiled track core (ℓ+1, or n when never locked)
     float phase, freq;          // PLL state BEFORE sample track_begin
@@ -273,6 +274,34 @@ PDT_DEV void back_consume(BackState &st, const ChainConst &cc, float sym, u64 ab
             st.cur_frame = (int)st.n_frames;
             pdt_frame &f = frames[st.cur_frame];
             f.sample_index = abs_interp_idx; f.bit_index = (uint32_t)st.n_bits;
+            f.inverse = (ev == EV_SYNC_INV); f.complete = 0; f.pad = 0;
+            f.n_bytes = (uint8_t)cc.prefix_bytes; st.cur_n = cc.prefix_bytes;
+            if (cc.prefix_bytes) { f.bytes[0] = 0xED; f.bytes[1] = 0xE2; }
+        } else st.cur_frame = -1;
+        st.n_frames++;
+    }
+    st.n_bits++;
+}
+
+// same, for the two-kernel back end: the pick index of a symbol is only needed when its bit completes a sync word
+PDT_DEV void back_consume_lazy(BackState &st, const ChainConst &cc, float sym, const u64 *gidx, u64 sym_index, pdt_frame *frames,
+                               const pdt_traces *tr)
+{
+    unsigned char bit;
+    if (!manchester_step(st.man, sym, cc.man_thresh, bit)) return;
+    if (tr && tr->bits && st.n_bits < tr->cap) tr->bits[st.n_bits] = bit;
+    int emit, eol; unsigned char byte;
+    const int ev = sync_step(st.sync, cc.sync, bit, emit, byte, eol);
+    if (emit && st.cur_frame >= 0) {
+        pdt_frame &f = frames[st.cur_frame];
+        if (st.cur_n < PDT_FRAME_MAX_BYTES) f.bytes[st.cur_n++] = byte;
+        if (eol) { f.n_bytes = (uint8_t)st.cur_n; f.complete = 1; st.cur_frame = -1; }
+    } else if (eol) st.cur_frame = -1;
+    if (ev != EV_NONE) {
+        if (st.n_frames < cc.max_frames) {
+            st.cur_frame = (int)st.n_frames;
+            pdt_frame &f = frames[st.cur_frame];
+            f.sample_index = gidx[sym_index]; f.bit_index = (uint32_t)st.n_bits;
             f.inverse = (ev == EV_SYNC_INV); f.complete = 0; f.pad = 0;
             f.n_bytes = (uint8_t)cc.prefix_bytes; st.cur_n = cc.prefix_bytes;
             if (cc.prefix_bytes) { f.bytes[0] = 0xED; f.bytes[1] = 0xE2; }

@@ -10,13 +10,16 @@
 //   k_front<L>  NCO sincos + derotation + ×L interpolating FIR (exact order)    CTA per 3328-sample span
 //   k_agc_core  AGC gain recurrence, warm-up + main                             lane per tile
 //   k_agc_fix   same verification for the AGC                                   thread per capture
-//   k_back      Gardner -> Manchester -> ByteSync -> frame table                warp per capture
+//   k_gardner   Gardner timing recovery -> symbol stream                        warp per capture
+//   k_bits      Manchester -> ByteSync -> frame table                           lane per capture
 #pragma once
 
 #include "pdt_tiled.cuh"
 
 namespace pdt {
 namespace tiled {
+
+struct GarRecord { u64 n_sym; float final_next; float pad; };
 
 struct TiledArgs {
     ChainConst  cc;
@@ -35,11 +38,18 @@ struct TiledArgs {
     u64         agc_min_tile; unsigned agc_max_tiles;   // in interpolated samples
     int         est_decim;   // D
     float       est_fmax;    // peak search limit (Hz)
-    TrackConst  acq_gains;   // unused (acquisition gains come from pll_begin) — kept for alignment of the struct
+    u64         acq_first;   // samples covered by the first acquisition pass (0 = whole capture in one pass)
+    int         slow_pass;   // 0: kernels process the captures that latched in the first pass, 1: the slow ones
+    float      *sym;         // [captures][sym_cap]     Gardner symbol stream
+    u64        *gidx;        // [captures][sym_cap]     absolute interpolated-sample index of every pick
+    GarRecord  *gar;         // [captures]
+    u64         sym_cap;
     pdt_capture_stats *stats; pdt_frame *frames; const pdt_traces *traces;
 };
 
 PDT_DEV u64 cap_len(const TiledArgs &a, uint32_t c) { return a.n_samples ? a.n_samples[c] : a.n_uniform; }
+// does this launch (fast pipeline / slow-capture pipeline) own capture c?
+PDT_DEV bool cap_selected(const TiledArgs &a, uint32_t c) { return (a.acq[c].slow != 0) == (a.slow_pass != 0); }
 
 PDT_DEV TrackConst track_const(const TiledArgs &a, const AcqResult &acq)
 {
@@ -70,7 +80,7 @@ __global__ void __launch_bounds__(128) k_agc_plan(const TiledArgs a)
 {
     const uint32_t cap = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (cap >= a.n_captures) return;
+    if (cap >= a.n_captures || !cap_selected(a, cap)) return;
     const u64 nL = cap_len(a, cap) * a.cc.L;
     const float *y = a.y + (u64)cap * a.ws_stride * a.cc.L;
     // 32 evenly spread segments of 256 samples (lane = segment); the largest segment mean bounds the smallest gain,
@@ -182,7 +192,15 @@ PDT_DEV void acq_core(float *ph, float *fr, float *sw, const float *sp, const un
     ph[m] = phase; fr[m] = freq; sw[m] = sweep;
 }
 
-__global__ void __launch_bounds__(ACQ_THREADS) k_acquire(const TiledArgs a)
+// CarrierTrackingPLL.c:232 — |π/2 - averagePhase| < 0.05 (float fabs of a double difference, compared in double)
+PDT_DEV unsigned char acq_noise_like(float avg) { return (double)fabsf((float)(PDT_PI / 2.0 - (double)avg)) < 0.05; }
+
+// pass 0: samples [0, min(n, acq_first)) of every capture.  A capture whose loop has not latched by then is marked
+//         `slow` and its loop state is saved;
+// pass 1: the slow captures only, from where pass 0 stopped to the end of the capture.
+// (The two passes let the host run the rest of the chain for the quickly-locking majority while the few captures
+// that lock late, or never, are still in their serial acquisition.)
+__global__ void __launch_bounds__(ACQ_THREADS) k_acquire(const TiledArgs a, const int pass)
 {
     __shared__ AcqSmem s;
     const uint32_t cap = blockIdx.x;
@@ -200,8 +218,17 @@ __global__ void __launch_bounds__(ACQ_THREADS) k_acquire(const TiledArgs a)
     const float avg_alpha = 0.00005f;
     uint32_t restarts = 0;
 
+    u64 i_begin = 0, i_stop = n;
+    if (pass == 0) {
+        if (a.acq_first && a.acq_first < n) i_stop = a.acq_first;
+    } else {
+        if (!res->slow || res->resume_at >= n) return;
+        i_begin = res->resume_at;
+        ps.phase = res->phase; ps.freq = res->freq; ps.sweep = res->sweep; ps.avg_phase = res->avg_phase; ps.locksig = res->locksig;
+    }
+
     auto load_inputs = [&](int buf, u64 i0) {
-        const int m = (int)((n - i0 < ACQ_B) ? (n - i0) : ACQ_B);
+        const int m = (int)((i_stop - i0 < ACQ_B) ? (i_stop - i0) : ACQ_B);
         for (int i = tid; i < m; i += ACQ_THREADS) {
             float p, q;
             load_iq1(a.iq, a.pcm16, first + i0 + i, p, q);
@@ -211,32 +238,34 @@ __global__ void __launch_bounds__(ACQ_THREADS) k_acquire(const TiledArgs a)
 
     if (n == 0) {
         if (tid == 0) {
-            res->locked = 0; res->lock_sample = 0; res->track_begin = 0; res->phase = ps.phase; res->freq = ps.freq;
+            res->locked = 0; res->slow = 0; res->resume_at = 0; res->lock_sample = 0; res->track_begin = 0;
+            res->phase = ps.phase; res->freq = ps.freq;
             res->sweep = ps.sweep; res->avg_phase = ps.avg_phase; res->locksig = ps.locksig; res->lock_freq_hz = 0;
             res->alpha = kacq.alpha; res->beta = kacq.beta;
         }
         return;
     }
-    load_inputs(0, 0);
+    load_inputs(0, i_begin);
     {
-        const int m0 = (int)(n < ACQ_B ? n : ACQ_B);
-        for (int i = tid; i < m0; i += ACQ_THREADS) s.nl[0][i] = 1;      // |π/2 - avg_phase| < 0.05 holds for the initial avg_phase = π/2
+        const int m0 = (int)(i_stop - i_begin < ACQ_B ? i_stop - i_begin : ACQ_B);
+        const unsigned char f0 = acq_noise_like(ps.avg_phase);              // true for the initial avg_phase = π/2
+        for (int i = tid; i < m0; i += ACQ_THREADS) s.nl[0][i] = f0;
+        if (tid == 0) {
+            s.ph[0][0] = ps.phase; s.fr[0][0] = ps.freq; s.sw[0][0] = ps.sweep; s.avg[0] = ps.avg_phase; s.lks[0] = ps.locksig;
+        }
+        __syncthreads();
+        if (tid == 0) acq_core(s.ph[0], s.fr[0], s.sw[0], s.sp[0], s.nl[0], 0, m0, kacq);
+        __syncthreads();
     }
-    if (tid == 0) {
-        s.ph[0][0] = ps.phase; s.fr[0][0] = ps.freq; s.sw[0][0] = ps.sweep; s.avg[0] = ps.avg_phase; s.lks[0] = ps.locksig;
-    }
-    __syncthreads();
-    if (tid == 0) acq_core(s.ph[0], s.fr[0], s.sw[0], s.sp[0], s.nl[0], 0, (int)(n < ACQ_B ? n : ACQ_B), kacq);
-    __syncthreads();
 
     int r = 0;
     bool next_loaded = false;
-    for (u64 i0 = 0; i0 < n;) {
-        const int cur = (int)((i0 / ACQ_B) & 1), nxt = cur ^ 1;
-        const int m = (int)((n - i0 < ACQ_B) ? (n - i0) : ACQ_B);
-        const bool has_next = i0 + ACQ_B < n;
-        const int m_next = has_next ? (int)((n - i0 - ACQ_B < ACQ_B) ? (n - i0 - ACQ_B) : ACQ_B) : 0;
-        // ---- [A],[D] feed-forward parts of block `cur` from r; stage the next block's inputs -------------
+    for (u64 i0 = i_begin; i0 < i_stop;) {
+        const int cur = (int)(((i0 - i_begin) / ACQ_B) & 1), nxt = cur ^ 1;
+        const int m = (int)((i_stop - i0 < ACQ_B) ? (i_stop - i0) : ACQ_B);
+        const bool has_next = i0 + ACQ_B < i_stop;
+        const int m_next = has_next ? (int)((i_stop - i0 - ACQ_B < ACQ_B) ? (i_stop - i0 - ACQ_B) : ACQ_B) : 0;
+        // ---- P1: [A],[D] feed-forward parts of block `cur` from r; stage the next block's inputs and flag guess ----
         for (int i = r + tid; i < m; i += ACQ_THREADS) {
             float ti, tr;
             sincos_exact(s.ph[cur][i], ti, tr);                                     // :106-107
@@ -248,37 +277,42 @@ __global__ void __launch_bounds__(ACQ_THREADS) k_acquire(const TiledArgs a)
             const float nre = p * inv, nim = q * inv;
             s.lterm[i] = pp.lock_alpha * (nre * tr + nim * ti);
         }
-        if (has_next && !next_loaded) load_inputs(nxt, i0 + ACQ_B);
+        if (has_next) {
+            if (!next_loaded) load_inputs(nxt, i0 + ACQ_B);
+            const unsigned char f = s.nl[cur][m - 1];
+            for (int i = tid; i < m_next; i += ACQ_THREADS) s.nl[nxt][i] = f;
+        }
         next_loaded = true;
+        if (tid == 0) { s.mism = m; s.latch = m; }
         __syncthreads();
-        // ---- serial phase: the two EMAs of block `cur`, and SPECULATIVELY the core of the next block -------
+        // ---- S: the two EMAs of block `cur` (pure dependent chains), and SPECULATIVELY the core of the next block ----
         if (tid == 0) {
             if (has_next) {
-                const unsigned char f = s.nl[cur][m - 1];
-                for (int i = 0; i < m_next; i++) s.nl[nxt][i] = f;
                 s.ph[nxt][0] = s.ph[cur][m]; s.fr[nxt][0] = s.fr[cur][m]; s.sw[nxt][0] = s.sw[cur][m];
                 acq_core(s.ph[nxt], s.fr[nxt], s.sw[nxt], s.sp[nxt], s.nl[nxt], 0, m_next, kacq);
             }
         } else if (tid == 32) {
             float avg = s.avg[r];
-            int mism = m;
+#pragma unroll 4
             for (int i = r; i < m; i++) {
                 avg = (float)((double)avg * (1.0 - avg_alpha) + (double)s.aterm[i]);               // :124
                 s.avg[i + 1] = avg;
-                const unsigned char t = (double)fabsf((float)(PDT_PI / 2.0 - (double)avg)) < 0.05;   // :232
-                s.nl_true[i] = t;
-                if (t != s.nl[cur][i] && mism == m) mism = i;
             }
-            s.mism = mism;
         } else if (tid == 64) {
             float lk = s.lks[r];
-            int latch = m;
+#pragma unroll 4
             for (int i = r; i < m; i++) {
                 lk = (float)((double)lk * (1.0 - pp.lock_alpha) + (double)s.lterm[i]);             // :220
                 s.lks[i + 1] = lk;
-                if (lk > pp.lock_thresh && latch == m) latch = i;                                  // :266
             }
-            s.latch = latch;
+        }
+        __syncthreads();
+        // ---- P2: the decisions taken from the EMAs, all samples at once ---------------------------------------------
+        for (int i = r + tid; i < m; i += ACQ_THREADS) {
+            const unsigned char t = acq_noise_like(s.avg[i + 1]);                                  // :232
+            s.nl_true[i] = t;
+            if (t != s.nl[cur][i]) atomicMin(&s.mism, i);
+            if (s.lks[i + 1] > pp.lock_thresh) atomicMin(&s.latch, i);                             // :266
         }
         __syncthreads();
         const int mism = s.mism, latch = s.latch;
@@ -288,7 +322,8 @@ __global__ void __launch_bounds__(ACQ_THREADS) k_acquire(const TiledArgs a)
             for (int i = tid; i < cnt; i += ACQ_THREADS) ph_out[i0 + i] = s.ph[cur][i];
             if (tid == 0) {
                 const float freq = s.fr[cur][cnt];
-                res->locked = 1; res->lock_sample = i0 + latch; res->track_begin = i0 + cnt;
+                res->locked = 1; res->lock_sample = i0 + latch; res->track_begin = i0 + cnt; res->resume_at = n;
+                if (pass == 0) res->slow = 0;
                 res->phase = s.ph[cur][cnt]; res->freq = freq; res->sweep = s.sw[cur][cnt];
                 res->avg_phase = s.avg[cnt]; res->locksig = s.lks[cnt];
                 res->lock_freq_hz = freq * pp.Fs / (2.0 * PDT_PI);                                  // :269
@@ -315,7 +350,10 @@ __global__ void __launch_bounds__(ACQ_THREADS) k_acquire(const TiledArgs a)
         for (int i = tid; i < m; i += ACQ_THREADS) ph_out[i0 + i] = s.ph[cur][i];
         if (tid == 0) { s.avg[0] = s.avg[m]; s.lks[0] = s.lks[m]; }
         if (!has_next && tid == 0) {
+            const bool done = (i_stop == n);
             res->locked = 0; res->lock_sample = 0; res->track_begin = n;
+            res->resume_at = i_stop;
+            if (pass == 0) res->slow = done ? 0 : 1;
             res->phase = s.ph[cur][m]; res->freq = s.fr[cur][m]; res->sweep = s.sw[cur][m];
             res->avg_phase = s.avg[m]; res->locksig = s.lks[m];
             res->lock_freq_hz = 0; res->alpha = kacq.alpha; res->beta = kacq.beta;
@@ -343,7 +381,7 @@ __global__ void __launch_bounds__(EST_WARPS * 32) k_estimate(const TiledArgs a)
     const AcqResult &acq = a.acq[cap];
     const u64 n = cap_len(a, cap), first = (u64)cap * a.stride;
     u64 warm, begin, end;
-    if (!acq.locked || !tile_range(acq.track_begin, n, a.pll, k, warm, begin, end)) return;
+    if (!cap_selected(a, cap) || !acq.locked || !tile_range(acq.track_begin, n, a.pll, k, warm, begin, end)) return;
     float2 *z = zs[wib];
     const int D = a.est_decim;
     const long long w0 = (long long)warm - (long long)EST_FFT * D;
@@ -422,7 +460,7 @@ __global__ void __launch_bounds__(128) k_pll_core(const TiledArgs a)
     const AcqResult &acq = a.acq[cap];
     const u64 n = cap_len(a, cap), first = (u64)cap * a.stride;
     u64 warm, begin, end;
-    if (!acq.locked || !tile_range(acq.track_begin, n, a.pll, k, warm, begin, end)) return;
+    if (!cap_selected(a, cap) || !acq.locked || !tile_range(acq.track_begin, n, a.pll, k, warm, begin, end)) return;
     const TrackConst kc = track_const(a, acq);
     const float *sp = a.sp + (u64)cap * a.ws_stride;
     float *ph = a.ph + (u64)cap * a.ws_stride;
@@ -468,7 +506,7 @@ __global__ void __launch_bounds__(128) k_pll_fix_par(const TiledArgs a)
     const AcqResult &acq = a.acq[cap];
     const u64 n = cap_len(a, cap);
     u64 warm, begin, end;
-    if (!acq.locked || !tile_range(acq.track_begin, n, a.pll, k, warm, begin, end)) return;
+    if (!cap_selected(a, cap) || !acq.locked || !tile_range(acq.track_begin, n, a.pll, k, warm, begin, end)) return;
     const size_t slot = (size_t)cap * a.pll.max_tiles + k;
     const LoopState2 truth = ld_state(&a.pll_end[slot - 1]);
     if (same_bits(ld_state(&a.pll_start[slot]), truth)) return;
@@ -485,7 +523,7 @@ __global__ void __launch_bounds__(128) k_pll_fix(const TiledArgs a)
     const uint32_t cap = blockIdx.x * blockDim.x + threadIdx.x;
     if (cap >= a.n_captures) return;
     const AcqResult &acq = a.acq[cap];
-    if (!acq.locked) return;
+    if (!cap_selected(a, cap) || !acq.locked) return;
     const u64 n = cap_len(a, cap), first = (u64)cap * a.stride;
     const TrackConst kc = track_const(a, acq);
     uint32_t fixed = 0;
@@ -520,7 +558,7 @@ __global__ void __launch_bounds__(FRONT_THREADS) k_front(const TiledArgs a, cons
     const int tid = threadIdx.x;
     const u64 n = cap_len(a, cap), first = (u64)cap * a.stride;
     const u64 base = (u64)blockIdx.x * FRONT_SPAN;
-    if (base >= n) return;
+    if (base >= n || !cap_selected(a, cap)) return;
     const float *ph = a.ph + (u64)cap * a.ws_stride;
     const pdt_traces *tr = a.traces ? &a.traces[cap] : nullptr;
     for (int idx = tid; idx < FRONT_SPAN + FIR_K; idx += FRONT_THREADS) {
@@ -577,7 +615,7 @@ __global__ void __launch_bounds__(128) k_agc_core(const TiledArgs a)
     const u64 nL = cap_len(a, cap) * L, first = (u64)cap * a.ws_stride * L;
     const TilePlan plan = agc_plan(a, acq);
     u64 warm, begin, end;
-    if (!tile_range(0, nL, plan, k, warm, begin, end)) return;
+    if (!cap_selected(a, cap) || !tile_range(0, nL, plan, k, warm, begin, end)) return;
     const float *y = a.y + first;
     float *z = a.z + first;
     const size_t slot = (size_t)cap * a.agc_max_tiles + k;
@@ -605,7 +643,7 @@ __global__ void __launch_bounds__(128) k_agc_fix_par(const TiledArgs a)
     const u64 nL = cap_len(a, cap) * L, first = (u64)cap * a.ws_stride * L;
     const TilePlan plan = agc_plan(a, acq);
     u64 warm, begin, end;
-    if (!tile_range(0, nL, plan, k, warm, begin, end)) return;
+    if (!cap_selected(a, cap) || !tile_range(0, nL, plan, k, warm, begin, end)) return;
     const size_t slot = (size_t)cap * a.agc_max_tiles + k;
     const LoopState2 truth = ld_state(&a.agc_end[slot - 1]);
     if (same_bits(ld_state(&a.agc_start[slot]), truth)) return;
@@ -619,7 +657,7 @@ __global__ void __launch_bounds__(128) k_agc_fix_par(const TiledArgs a)
 __global__ void __launch_bounds__(128) k_agc_fix(const TiledArgs a)
 {
     const uint32_t cap = blockIdx.x * blockDim.x + threadIdx.x;
-    if (cap >= a.n_captures) return;
+    if (cap >= a.n_captures || !cap_selected(a, cap)) return;
     const AcqResult &acq = a.acq[cap];
     const int L = a.cc.L;
     const u64 nL = cap_len(a, cap) * L, first = (u64)cap * a.ws_stride * L;
@@ -641,44 +679,65 @@ __global__ void __launch_bounds__(128) k_agc_fix(const TiledArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------------
-// back: Gardner -> Manchester -> ByteSync, warp per capture, chunk by chunk (the chunk length is part of the
-// reference's numerics: Gardner's position is a float in chunk-relative samples).
-// The AGC output streams through a per-warp shared-memory window; lane 0 runs the recurrences.
+// back end, two kernels:
+//   k_gardner  GardenerClockRecovery.c:24-111 — warp per capture, chunk by chunk (the chunk length is part of the
+//              reference's numerics: the sampling position is a float in chunk-relative samples).  The AGC
+//              output streams through a per-warp shared-memory window; lane 0 runs the timing recurrence and nothing
+//              else (its dependent chain — round, window read, error, clamp, advance — is what bounds this kernel);
+//              symbols and pick indices are staged in shared memory and flushed coalesced by the whole warp.
+//   k_bits     ManchesterDecode.c:27-97 + ByteSync.c:42-148 over the symbol stream, lane per capture.
 // ---------------------------------------------------------------------------------------------------
-constexpr int BACK_WIN = 4096;
-constexpr int BACK_WARPS = 2;
+constexpr int GAR_WIN = 4096;
+constexpr int GAR_WARPS = 2;
+constexpr int GAR_STAGE = 512;          // symbols staged per flush (a window yields window/step of them; a full stage just flushes early)
 
-__global__ void __launch_bounds__(BACK_WARPS * 32) k_back(const TiledArgs a)
+
+// rintf(x) as an integer.  FAST: x + 1.5·2^23 rounds to nearest-even at unit granularity for |x| < 2^22, and the integer is
+// the low mantissa — two dependent ALU ops instead of FRND + F2I (25 cycles, tools/microbench.cu).
+template <bool FAST>
+PDT_DEV int rint_index(float x)
 {
-    __shared__ float wins[BACK_WARPS][BACK_WIN];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const uint32_t cap = blockIdx.x * BACK_WARPS + wib;
-    if (cap >= a.n_captures) return;
+    if (FAST) return (int)pdt_f2u(x + 12582912.0f) - 0x4B400000;
+    const float r = rintf(x);
+    return (r < 0.0f) ? -1 : (int)(unsigned)r;
+}
+
+template <bool FAST>
+__device__ __forceinline__ void gardner_capture(const TiledArgs &a, const uint32_t cap, float *win, float *ssym, float *serr, unsigned *sidx,
+                                                const int lane)
+{
     const ChainConst &cc = a.cc;
     const int L = cc.L;
     const u64 n = cap_len(a, cap);
     const float *z = a.z + (u64)cap * a.ws_stride * L;
-    float *win = wins[wib];
-    pdt_frame *frames = a.frames + (size_t)cap * cc.max_frames;
+    float *sym_out = a.sym + (u64)cap * a.sym_cap;
+    u64 *gidx_out = a.gidx + (u64)cap * a.sym_cap;
     const pdt_traces *tr = a.traces ? &a.traces[cap] : nullptr;
     const unsigned full_out = cc.chunk * (unsigned)L;
+    const float kp = cc.g_kp, range = cc.g_range;
 
-    BackState st;
-    back_reset(st);
-    gardner_begin(st.gar, cc.gardner_fs, cc.baud);
+    GardnerState gs = GardnerState();
+    gardner_begin(gs, cc.gardner_fs, cc.baud);
+    const float step = gs.step;
+    // half = next + step/2.0 is a double sum narrowed to float (GardenerClockRecovery.c:59); the double sum of two floats
+    // is exact when their exponents are < 29 apart, and then the float sum is the same correctly rounded value
+    const float half_step = (float)((double)step / 2.0);
+    const bool half_exact = ((double)half_step == (double)step / 2.0);
+    u64 n_sym = 0;
 
     for (u64 base = 0; base < n; base += cc.chunk) {
         const unsigned m = (unsigned)((n - base < cc.chunk) ? (n - base) : cc.chunk);
         const unsigned n_out = m * (unsigned)L;
         const u64 ibase = base * (u64)L;
         const bool has_prev = base > 0;
-        bool first_symbol = true;
+        bool first_symbol = true, reload = true;
         unsigned w0 = 0;
         for (;;) {
-            // resident window: chunk-relative [w0, w0 + BACK_WIN)
-            if (((ibase + w0) & 3) == 0) {
+            // resident window: chunk-relative [w0, w0 + GAR_WIN)
+            if (!reload) {
+            } else if (((ibase + w0) & 3) == 0) {
 #pragma unroll 8
-                for (unsigned i = lane * 4; i < BACK_WIN; i += 128) {
+                for (unsigned i = lane * 4; i < GAR_WIN; i += 128) {
                     const unsigned idx = w0 + i;
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (idx + 4 <= n_out) v = ld4(z + ibase + idx);
@@ -691,82 +750,135 @@ __global__ void __launch_bounds__(BACK_WARPS * 32) k_back(const TiledArgs a)
                 }
             } else {
 #pragma unroll 8
-                for (unsigned i = lane; i < BACK_WIN; i += 32) {
+                for (unsigned i = lane; i < GAR_WIN; i += 32) {
                     const unsigned idx = w0 + i;
                     win[i] = (idx < n_out) ? z[ibase + idx] : 0.0f;
                 }
             }
             __syncwarp();
-            int finished = 0;
+            int finished = 0, cnt = 0;
             if (lane == 0) {
+                float next = gs.next, prev = gs.prev, half = gs.half;
+                const int w_lo = (int)w0, w_hi = (int)(w0 + GAR_WIN);
                 for (;;) {
-                    const float nr = rintf(st.gar.next);
-                    if (!(nr < (float)n_out)) { finished = 1; break; }                 // GardenerClockRecovery.c:24
-                    const unsigned at = (unsigned)nr;
-                    if (at >= w0 + BACK_WIN) break;                                    // refill
-                    const float cur = win[at - w0];
-                    float half;
-                    const unsigned hi = (unsigned)rintf(st.gar.half);                  // :28 index-then-value reuse
-                    if (first_symbol) half = stale_lookup(z, ibase, hi, n_out, full_out, has_prev);
-                    else              half = (hi >= w0 && hi < w0 + BACK_WIN) ? win[hi - w0] : stale_lookup(z, ibase, hi, n_out, full_out, has_prev);
+                    const int at = rint_index<FAST>(next);
+                    if (at >= (int)n_out) { finished = 1; break; }                     // GardenerClockRecovery.c:24
+                    if (at >= w_hi || cnt >= GAR_STAGE) break;                         // refill / flush
+                    const float cur = win[(at < w_lo ? w_lo : at) - w_lo];
+                    const int hi = rint_index<FAST>(half);                             // :28 index-then-value reuse
+                    float hv;
+                    if (!first_symbol && hi >= w_lo && hi < w_hi) hv = win[hi - w_lo];
+                    else hv = stale_lookup(z, ibase, (unsigned)hi, n_out, full_out, has_prev);
                     first_symbol = false;
-                    float e = cc.g_kp * (cur - st.gar.prev) * half;                    // :43
-                    if (e > cc.g_range) e = cc.g_range; else if (e < -cc.g_range) e = -cc.g_range;
-                    st.gar.next = st.gar.next - e;
-                    st.gar.half = st.gar.next + st.gar.step / 2.0;                     // :59
-                    st.gar.next = st.gar.next + st.gar.step;
-                    st.gar.prev = cur;
-                    if (tr && st.n_sym < tr->cap) {
-                        if (tr->sym)         reinterpret_cast<float *>(tr->sym)[st.n_sym] = cur;
-                        if (tr->gardner_err) reinterpret_cast<float *>(tr->gardner_err)[st.n_sym] = e;
-                        if (tr->gardner_idx) tr->gardner_idx[st.n_sym] = ibase + at;
-                    }
-                    st.n_sym++;
-                    back_consume(st, cc, cur, ibase + at, frames, tr);
+                    float e = kp * (cur - prev) * hv;                                  // :43
+                    e = (e > range) ? range : ((e < -range) ? -range : e);
+                    next = next - e;
+                    if (half_exact && (fabsf(next) >= 9.5367431640625e-07f || next == 0.0f)) half = next + half_step;
+                    else half = next + step / 2.0;                                     // :59
+                    next = next + step;
+                    prev = cur;
+                    ssym[cnt] = cur; sidx[cnt] = (unsigned)at; if (serr) serr[cnt] = e;
+                    cnt++;
                 }
+                gs.next = next; gs.prev = prev; gs.half = half;
             }
             finished = __shfl_sync(0xffffffffu, finished, 0);
+            cnt = __shfl_sync(0xffffffffu, cnt, 0);
+            __syncwarp();
+            for (int j = lane; j < cnt; j += 32) {
+                const u64 k = n_sym + (u64)j;
+                if (k < a.sym_cap) { sym_out[k] = ssym[j]; gidx_out[k] = ibase + sidx[j]; }
+                if (tr && k < tr->cap) {
+                    if (tr->sym)         reinterpret_cast<float *>(tr->sym)[k] = ssym[j];
+                    if (tr->gardner_err) reinterpret_cast<float *>(tr->gardner_err)[k] = serr[j];
+                    if (tr->gardner_idx) tr->gardner_idx[k] = ibase + sidx[j];
+                }
+            }
+            n_sym += (u64)cnt;
             if (finished) break;
-            const float nr = __shfl_sync(0xffffffffu, rintf(st.gar.next), 0);
             // next window starts a little before the pick so that the mid-sample (behind the pick) stays resident
-            const unsigned at = (unsigned)nr;
-            const unsigned back = (unsigned)(st.gar.step) + 8;
-            unsigned nw0 = at > back ? at - back : 0;
-            nw0 = __shfl_sync(0xffffffffu, nw0, 0);
-            w0 = nw0 & ~3u;
+            int at = 0;
+            if (lane == 0) at = rint_index<FAST>(gs.next);
+            at = __shfl_sync(0xffffffffu, at, 0);
+            const unsigned back = (unsigned)step + 8;
+            const unsigned nw0 = (unsigned)at > back ? (unsigned)at - back : 0;
+            reload = (unsigned)at >= w0 + GAR_WIN;                             // a pure stage flush keeps the window
+            if (reload) w0 = nw0 & ~3u;
             __syncwarp();
         }
-        if (lane == 0) st.gar.next = st.gar.next - n_out;                              // :111
+        if (lane == 0) gs.next = gs.next - n_out;                                      // :111
         __syncwarp();
     }
-    if (lane == 0) {
-        back_finish(st, frames);
-        const AcqResult &acq = a.acq[cap];
-        pdt_capture_stats s;
-        s.n_samples = n; s.n_symbols = st.n_sym; s.n_bits = st.n_bits; s.n_frames = st.n_frames;
-        s.locked = acq.locked; s.lock_sample = acq.lock_sample; s.lock_freq_hz = acq.lock_freq_hz;
-        s.norm_factor = acq.norm; s.avg_phase = acq.avg_phase;
-        s.final_phase = acq.phase; s.final_freq = acq.freq;
-        if (acq.locked) {
-            u64 warm, begin, end;
-            for (unsigned k = 0; k < a.pll.max_tiles; k++) {
-                if (!tile_range(acq.track_begin, n, a.pll, k, warm, begin, end)) break;
-                const LoopState2 e = a.pll_end[(size_t)cap * a.pll.max_tiles + k];
-                s.final_phase = e.a; s.final_freq = e.b;
-            }
-        }
-        s.final_gain = acq.norm;
-        {
-            const TilePlan plan = agc_plan(a, acq);
-            u64 warm, begin, end;
-            for (unsigned k = 0; k < a.agc_max_tiles; k++) {
-                if (!tile_range(0, n * L, plan, k, warm, begin, end)) break;
-                s.final_gain = a.agc_end[(size_t)cap * a.agc_max_tiles + k].a;
-            }
-        }
-        s.final_next = st.gar.next;
-        a.stats[cap] = s;
+    if (lane == 0) { GarRecord r; r.n_sym = n_sym; r.final_next = gs.next; r.pad = 0.f; a.gar[cap] = r; }
+}
+
+__global__ void __launch_bounds__(GAR_WARPS * 32) k_gardner(const TiledArgs a)
+{
+    __shared__ __align__(16) float wins[GAR_WARPS][GAR_WIN];
+    __shared__ float ssym[GAR_WARPS][GAR_STAGE], serr[GAR_WARPS][GAR_STAGE];
+    __shared__ unsigned sidx[GAR_WARPS][GAR_STAGE];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t cap = blockIdx.x * GAR_WARPS + wib;
+    if (cap >= a.n_captures || !cap_selected(a, cap)) return;
+    const bool fast = (double)a.cc.chunk * a.cc.L + 64.0 < 4.0e6;
+    float *e = (a.traces && a.traces[cap].gardner_err) ? serr[wib] : nullptr;
+    if (fast) gardner_capture<true>(a, cap, wins[wib], ssym[wib], e, sidx[wib], lane);
+    else      gardner_capture<false>(a, cap, wins[wib], ssym[wib], e, sidx[wib], lane);
+}
+
+// Manchester + ByteSync + frame table: lane per capture over its symbol stream (both are cheap integer state machines;
+// the symbol stream is 1/15 of the sample stream).
+__global__ void __launch_bounds__(32) k_bits(const TiledArgs a)
+{
+    const uint32_t cap = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cap >= a.n_captures || !cap_selected(a, cap)) return;
+    const ChainConst &cc = a.cc;
+    const u64 n = cap_len(a, cap);
+    const int L = cc.L;
+    const GarRecord gr = a.gar[cap];
+    const float *sym = a.sym + (u64)cap * a.sym_cap;
+    const u64 *gidx = a.gidx + (u64)cap * a.sym_cap;
+    pdt_frame *frames = a.frames + (size_t)cap * cc.max_frames;
+    const pdt_traces *tr = a.traces ? &a.traces[cap] : nullptr;
+    BackState st;
+    back_reset(st);
+    const u64 ns = gr.n_sym < a.sym_cap ? gr.n_sym : a.sym_cap;
+    u64 i = 0;
+    for (; i + 4 <= ns; i += 4) {
+        const float4 v = ld4(sym + i);
+        back_consume_lazy(st, cc, v.x, gidx, i, frames, tr);
+        back_consume_lazy(st, cc, v.y, gidx, i + 1, frames, tr);
+        back_consume_lazy(st, cc, v.z, gidx, i + 2, frames, tr);
+        back_consume_lazy(st, cc, v.w, gidx, i + 3, frames, tr);
     }
+    for (; i < ns; i++) back_consume_lazy(st, cc, sym[i], gidx, i, frames, tr);
+    st.n_sym = gr.n_sym;
+    back_finish(st, frames);
+    const AcqResult &acq = a.acq[cap];
+    pdt_capture_stats s;
+    s.n_samples = n; s.n_symbols = st.n_sym; s.n_bits = st.n_bits; s.n_frames = st.n_frames;
+    s.locked = acq.locked; s.lock_sample = acq.lock_sample; s.lock_freq_hz = acq.lock_freq_hz;
+    s.norm_factor = acq.norm; s.avg_phase = acq.avg_phase;
+    s.final_phase = acq.phase; s.final_freq = acq.freq;
+    if (acq.locked) {
+        u64 warm, begin, end;
+        for (unsigned k = 0; k < a.pll.max_tiles; k++) {
+            if (!tile_range(acq.track_begin, n, a.pll, k, warm, begin, end)) break;
+            const LoopState2 e = a.pll_end[(size_t)cap * a.pll.max_tiles + k];
+            s.final_phase = e.a; s.final_freq = e.b;
+        }
+    }
+    s.final_gain = acq.norm;
+    {
+        const TilePlan plan = agc_plan(a, acq);
+        u64 warm, begin, end;
+        for (unsigned k = 0; k < a.agc_max_tiles; k++) {
+            if (!tile_range(0, n * L, plan, k, warm, begin, end)) break;
+            s.final_gain = a.agc_end[(size_t)cap * a.agc_max_tiles + k].a;
+        }
+    }
+    s.final_next = gr.final_next;
+    a.stats[cap] = s;
 }
 
 } // namespace tiled

@@ -222,6 +222,42 @@ def test_tiled_failed_speculation_is_repaired(torch_cuda, oracle32):
     assert pll_rerun >= 5          # the speculation really did fail
 
 
+@pytest.mark.parametrize("kind", ["early", "late", "never"])
+def test_tiled_two_pass_acquisition_bit_exact(torch_cuda, oracle32, kind):
+    """First acquisition pass of 40960 samples only: a capture that latches inside it, one that latches in the second
+    pass (its carrier appears late) and one that never latches; every stream must equal the serial oracle."""
+    fs, n = 250000, 300_000
+    if kind == "never":
+        rng = np.random.default_rng(11)
+        pcm = (rng.standard_normal(2 * n) * 700).astype(np.int16)
+    else:
+        # the sweep runs to the positive frequency limit and stays there (CarrierTrackingPLL.c:232-246): a carrier that
+        # appears late is only captured near +4.5 kHz
+        pcm, _ = make_poes_capture(n, fs, 31, esn0_db=15.0, doppler_hz=1200.0 if kind == "early" else 4400.0, amplitude=0.25)
+        if kind == "late":
+            rng = np.random.default_rng(12)
+            quiet = 150_000
+            pcm = pcm.copy()
+            pcm[: 2 * quiet] = (rng.standard_normal(2 * quiet) * 300).astype(np.int16)
+    iq = oracle32.pcm16_to_complex(pcm)
+    want = oracle32.chain(iq, fs, trace=True)
+    d, st, fr, tr = _run_batch_with_traces(torch_cuda, "f32", pdt.PDT_MODE_POES, fs, iq, engine="tiled", acq_first=40960)
+    ns, nb = int(st["n_symbols"]), int(st["n_bits"])
+    assert st["locked"] == int(want["locked"])
+    if kind == "early":
+        assert st["lock_sample"] < 40960
+    if kind == "late":
+        assert st["locked"] == 1 and st["lock_sample"] > 40960
+    if want["locked"]:
+        assert st["lock_sample"] == want["lock_sample"]
+    for k_dev, k_or in (("pll_phase", "tr_phase"), ("pll_out", "tr_pll_out"), ("lpf", "tr_lpf"), ("agc", "tr_agc")):
+        assert np.array_equal(tr.host(k_dev), want[k_or]), k_dev
+    assert (ns, nb, st["n_frames"]) == (want["total_symbols"], want["total_bits"], want["total_frames"])
+    assert np.array_equal(tr.host("gardner_idx", ns).astype(np.uint64), want["tr_gidx"])
+    assert np.array_equal(tr.host("bits", nb), want["tr_bits"])
+    _frames_text_equal_bytes(d.format_frames(fr, int(st["n_frames"])), want["text"])
+
+
 def test_tiled_unlocked_and_tiny_captures(torch_cuda, oracle32):
     """Noise only (the PLL never latches: everything stays in the acquisition kernel), and captures shorter than one chunk."""
     fs = 250000
@@ -240,9 +276,11 @@ def test_tiled_unlocked_and_tiny_captures(torch_cuda, oracle32):
         assert np.array_equal(tr.host("bits", nb), want["tr_bits"])
 
 
-def test_tiled_stream_groups_equal_exact_engine(torch_cuda):
+@pytest.mark.parametrize("acq_first", [0, 28160])
+def test_tiled_stream_groups_equal_exact_engine(torch_cuda, acq_first):
     """A batch large enough to be cut into capture groups on internal streams (fork/join inside pdt_demod_device):
-    stats and frames of every capture must equal the exact engine's, whatever the grouping."""
+    stats and frames of every capture must equal the exact engine's, whatever the grouping.  With a short first
+    acquisition pass the late-locking captures of every group additionally move to the slow-capture streams."""
     torch = torch_cuda
     fs, n, caps = 250000, 120_000, 200
     L = pdt.load("f32")
@@ -252,11 +290,15 @@ def test_tiled_stream_groups_equal_exact_engine(torch_cuda):
     for eng in ("exact", "tiled"):
         p = pdt.default_params("f32", pdt.PDT_MODE_POES, fs)
         p.engine = ENGINES[eng]
+        p.acq_first = acq_first
         d = pdt.Demod("f32", p, caps, n, 16)
         d.demod_device(d_iq.data_ptr(), caps, n, pcm16=True)
         res[eng] = d.fetch(caps)
     (se, fe), (st, ft) = res["exact"], res["tiled"]
     assert se["locked"].sum() >= caps // 2 and se["n_frames"].sum() > caps
+    if acq_first:      # the two-pass path must really have been exercised by both kinds of capture
+        late = (se["locked"] == 0) | (se["lock_sample"] >= acq_first)
+        assert late.sum() >= 3 and (~late).sum() >= 3
     for k in ("n_samples", "n_symbols", "n_bits", "n_frames", "locked", "lock_sample", "lock_freq_hz", "norm_factor",
               "final_phase", "final_freq", "final_gain", "final_next"):
         assert np.array_equal(se[k], st[k]), k
