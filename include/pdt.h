@@ -163,6 +163,10 @@ int         pdt_tiled_counters(pdt_ctx *ctx, uint32_t out[4], void *stream);
  * their names (static strings) and durations in milliseconds. */
 int         pdt_set_profiling(pdt_ctx *ctx, int enable);
 int         pdt_kernel_times(pdt_ctx *ctx, const char **names, float *ms, int cap);
+/* pdt_set_profiling(ctx, 2): timeline mode — the batch runs exactly as in production (capture groups on internal
+ * streams) with a timing event after every kernel of every stream; pdt_timeline() returns for each of them its name,
+ * its stream (capture group 0…, 99 = the slow-capture stream) and its END time in ms since the batch was forked. */
+int         pdt_timeline(pdt_ctx *ctx, const char **names, int *groups, float *end_ms, int cap);
 
 /* Number of kernels launched by this library since load (bench.py reports it as gpu_launches). */
 uint64_t    pdt_launch_count(void);

@@ -116,6 +116,7 @@ def load(prec: str = "f32"):
     L.pdt_launch_count.restype = u64
     L.pdt_set_profiling.argtypes = [vp, C.c_int]
     L.pdt_kernel_times.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]
+    L.pdt_timeline.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_int), C.POINTER(C.c_float), C.c_int]
     L.pdt_engine.argtypes = [vp]
     L.pdt_tiled_counters.argtypes = [vp, C.POINTER(C.c_uint32 * 4), vp]
     L.pdt_synth_poes_device.argtypes = [vp, C.c_int, u32, u64, u64, C.c_double, u64, vp]
@@ -159,7 +160,7 @@ EXPORTED_SYMBOLS = [
     "pdt_version", "pdt_last_error", "pdt_real_size", "pdt_device_count", "pdt_set_device", "pdt_params_default",
     "pdt_create", "pdt_destroy", "pdt_get_params", "pdt_get_taps", "pdt_demod_device", "pdt_demod_host", "pdt_fetch",
     "pdt_result_tables", "pdt_format_frames", "pdt_launch_count", "pdt_synth_poes_device", "pdt_engine",
-    "pdt_tiled_counters", "pdt_set_profiling", "pdt_kernel_times",
+    "pdt_tiled_counters", "pdt_set_profiling", "pdt_kernel_times", "pdt_timeline",
     # include/pdt_legacy.h
     "FindSignalAmplitude", "Squelch", "StaticGain", "NormalizingAGC", "NormalizingAGCC", "CarrierTrackPLL", "arctan2",
     "Q_rsqrt", "LowPassFilter", "LowPassFilterInterp", "MakeLPFIR", "GardenerClockRecovery", "MMClockRecovery", "sign",
@@ -248,12 +249,23 @@ class Demod:
 
     def kernel_times(self):
         """[(kernel name, ms)] of the last batch (tiled engine with profiling enabled), in launch order."""
-        names = (C.c_char_p * 24)()
-        ms = (C.c_float * 24)()
-        k = self.L.pdt_kernel_times(self.ctx, names, ms, 24)
+        names = (C.c_char_p * 64)()
+        ms = (C.c_float * 64)()
+        k = self.L.pdt_kernel_times(self.ctx, names, ms, 64)
         if k < 0:
             raise PdtError(self.L.pdt_last_error().decode())
         return [(names[i].decode(), float(ms[i])) for i in range(k)]
+
+    def timeline(self):
+        """[(kernel name, stream group, end ms)] of the last batch run with set_profiling(2)."""
+        cap = 512
+        names = (C.c_char_p * cap)()
+        groups = (C.c_int * cap)()
+        ms = (C.c_float * cap)()
+        k = self.L.pdt_timeline(self.ctx, names, groups, ms, cap)
+        if k < 0:
+            raise PdtError(self.L.pdt_last_error().decode())
+        return [(names[i].decode(), int(groups[i]), float(ms[i])) for i in range(k)]
 
     def result_tables(self):
         ds, df, mf = C.c_void_p(), C.c_void_p(), C.c_uint32()

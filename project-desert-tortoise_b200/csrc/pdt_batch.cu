@@ -141,7 +141,8 @@ struct pdt_ctx {
     tiled::TapsRev   taps_rev;
     size_t      front_smem = 0;
     static constexpr int MAX_GROUPS = 6;      // + the slow-capture stream + the caller's = the 8 hardware queues
-    static constexpr int MAX_MARKS = 48;
+    static constexpr int MAX_MARKS = 512;
+    int         mark_group[MAX_MARKS] = {};
     cudaStream_t gstream[MAX_GROUPS] = {}, sstream = nullptr;
     cudaEvent_t  ev_fork = nullptr, ev_join[MAX_GROUPS] = {}, ev_acq[MAX_GROUPS] = {}, ev_sjoin = nullptr;
     int         profiling = 0, n_marks = 0;
@@ -227,13 +228,14 @@ static void tiled_free(pdt_ctx *c)
 // acquisition pass; `pipeline` = everything behind the lock latch, for the captures the pass owns (slow_pass 0: those
 // that latched within the first acquisition pass, 1: the rest, after their second acquisition pass).
 struct GroupLaunch {
-    pdt_ctx *c; tiled::TiledArgs t; uint32_t cnt; tiled::u64 n_max; bool marks;
+    pdt_ctx *c; tiled::TiledArgs t; uint32_t cnt; tiled::u64 n_max; bool marks; int gid = 0;
     static unsigned blocks(tiled::u64 items, unsigned per) { return (unsigned)((items + per - 1) / per); }
     void mark(cudaStream_t s, const char *name)
     {
         if (!marks || c->n_marks >= pdt_ctx::MAX_MARKS) return;
         if (!c->marks[c->n_marks]) cudaEventCreate(&c->marks[c->n_marks]);
         cudaEventRecord(c->marks[c->n_marks], s);
+        c->mark_group[c->n_marks] = gid;
         c->mark_names[c->n_marks++] = name;
     }
     void head(cudaStream_t s)
@@ -292,7 +294,7 @@ struct GroupLaunch {
         mark(s, "k_agc_fix");
         k_gardner<<<blocks(cnt, GAR_WARPS), GAR_WARPS * 32, 0, s>>>(q);
         mark(s, "k_gardner");
-        k_bits<<<blocks(cnt, 32), 32, 0, s>>>(q);
+        k_bits<<<blocks(cnt, BITS_WARPS), BITS_WARPS * 32, 0, s>>>(q);
         mark(s, "k_bits");
         count_launch(q.pll.max_tiles > 1 ? 12 : 11);
     }
@@ -343,13 +345,15 @@ static int tiled_run(pdt_ctx *c, const void *d_iq, int pcm16, uint32_t n_capture
     PDT_CUDA(cudaMemsetAsync(t.counters, 0, 4 * sizeof(uint32_t), s));
     c->n_marks = 0;
     int groups = (int)std::min<uint32_t>(pdt_ctx::MAX_GROUPS, (n_captures + 63) / 64);
-    if (c->profiling || traces || groups < 2) {
+    if (c->profiling == 1 || traces || groups < 2) {
         GroupLaunch g = make_group(c, t, 0, n_captures, n_max, c->profiling != 0);
         g.head(s);
         g.pipeline(s, 0);
         if (two_pass) { g.acquire_rest(s); g.pipeline(s, 1); }
     } else {
+        const bool tl = c->profiling == 2;        // timeline mode: timing events on every group stream
         if (!c->ev_fork) PDT_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        if (tl) { GroupLaunch g0 = make_group(c, t, 0, n_captures, n_max, true); g0.gid = -1; g0.mark(s, "fork"); }
         PDT_CUDA(cudaEventRecord(c->ev_fork, s));
         const uint32_t per = (n_captures + groups - 1) / groups;
         int used = 0;
@@ -360,7 +364,8 @@ static int tiled_run(pdt_ctx *c, const void *d_iq, int pcm16, uint32_t n_capture
             if (!c->gstream[gi]) PDT_CUDA(cudaStreamCreateWithFlags(&c->gstream[gi], cudaStreamNonBlocking));
             if (!c->ev_join[gi]) PDT_CUDA(cudaEventCreateWithFlags(&c->ev_join[gi], cudaEventDisableTiming));
             PDT_CUDA(cudaStreamWaitEvent(c->gstream[gi], c->ev_fork, 0));
-            GroupLaunch g = make_group(c, t, c0, cnt, n_max, false);
+            GroupLaunch g = make_group(c, t, c0, cnt, n_max, tl);
+            g.gid = gi;
             g.head(c->gstream[gi]);
             if (two_pass) {
                 if (!c->ev_acq[gi]) PDT_CUDA(cudaEventCreateWithFlags(&c->ev_acq[gi], cudaEventDisableTiming));
@@ -381,7 +386,9 @@ static int tiled_run(pdt_ctx *c, const void *d_iq, int pcm16, uint32_t n_capture
             }
             if (!c->ev_sjoin) PDT_CUDA(cudaEventCreateWithFlags(&c->ev_sjoin, cudaEventDisableTiming));
             for (int gi = 0; gi < used; gi++) PDT_CUDA(cudaStreamWaitEvent(c->sstream, c->ev_acq[gi], 0));
-            GroupLaunch whole = make_group(c, t, 0, n_captures, n_max, false);
+            GroupLaunch whole = make_group(c, t, 0, n_captures, n_max, tl);
+            whole.gid = 99;
+            whole.mark(c->sstream, "begin");
             whole.acquire_rest(c->sstream);
             whole.pipeline(c->sstream, 1);
             PDT_CUDA(cudaEventRecord(c->ev_sjoin, c->sstream));
@@ -642,11 +649,29 @@ int pdt_kernel_times(pdt_ctx *c, const char **names, float *ms, int cap)
     if (!c || !names || !ms) return fail(PDT_EINVAL, "bad arguments");
 #if PDT_USE_FLOATS
     if (c->engine != PDT_ENGINE_TILED || c->n_marks < 2) return 0;
+    if (c->profiling == 2) return 0;
     PDT_CUDA(cudaEventSynchronize(c->marks[c->n_marks - 1]));
     int k = 0;
     for (int i = 1; i < c->n_marks && k < cap; i++, k++) {
         names[k] = c->mark_names[i];
         PDT_CUDA(cudaEventElapsedTime(&ms[k], c->marks[i - 1], c->marks[i]));
+    }
+    return k;
+#else
+    return 0;
+#endif
+}
+
+int pdt_timeline(pdt_ctx *c, const char **names, int *groups, float *end_ms, int cap)
+{
+    if (!c || !names || !groups || !end_ms) return fail(PDT_EINVAL, "bad arguments");
+#if PDT_USE_FLOATS
+    if (c->engine != PDT_ENGINE_TILED || c->profiling != 2 || c->n_marks < 2) return 0;
+    PDT_CUDA(cudaDeviceSynchronize());
+    int k = 0;
+    for (int i = 1; i < c->n_marks && k < cap; i++, k++) {
+        names[k] = c->mark_names[i]; groups[k] = c->mark_group[i];
+        PDT_CUDA(cudaEventElapsedTime(&end_ms[k], c->marks[0], c->marks[i]));
     }
     return k;
 #else

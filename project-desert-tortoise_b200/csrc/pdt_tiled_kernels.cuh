@@ -164,32 +164,73 @@ __global__ void __launch_bounds__(256) k_sp(const TiledArgs a)
 constexpr int ACQ_B = 512;
 constexpr int ACQ_THREADS = 256;
 
-struct AcqSmem {
+struct __align__(16) AcqSmem {
     float sp[2][ACQ_B], a[2][ACQ_B], b[2][ACQ_B];               // inputs of the current and the next block
-    float ph[2][ACQ_B + 1], fr[2][ACQ_B + 1], sw[2][ACQ_B + 1]; // state BEFORE each sample (and after the last)
+    float ph[2][ACQ_B + 4], fr[2][ACQ_B + 4], sw[2][ACQ_B + 4]; // state BEFORE each sample (and after the last)
     float aterm[ACQ_B], lterm[ACQ_B];
-    float avg[ACQ_B + 1], lks[ACQ_B + 1];
+    float avg[ACQ_B + 4], lks[ACQ_B + 4];
     unsigned char nl[2][ACQ_B], nl_true[ACQ_B];
     int mism, latch;
 };
 
-// [B]+[C]: serial core over samples [r, m) of one block with the flags nl[]
-PDT_DEV void acq_core(float *ph, float *fr, float *sw, const float *sp, const unsigned char *nl, int r, int m, const TrackConst &k)
+// [B]+[C]: serial core over samples [r, m) of one block with the flags nl[].  Inputs are fetched a quad ahead and the
+// three state streams leave as float4: the loop is one dependent chain and must never wait on shared memory.
+PDT_DEV void acq_step(float &phase, float &freq, float &sweep, float sp, bool on, const TrackConst &k)
+{
+    pll_track_step(phase, freq, sp, k);
+    const float f2 = freq + sweep;                                              // CarrierTrackingPLL.c:232-246
+    float s2 = (f2 >= 0) ? fabsf(sweep) : -fabsf(sweep);
+    s2 = (f2 <= k.min_freq) ? -sweep : s2;
+    s2 = (f2 >= k.max_freq) ? -sweep : s2;
+    freq = on ? f2 : freq;
+    sweep = on ? s2 : sweep;
+}
+
+PDT_DEV void acq_core(float *__restrict__ ph, float *__restrict__ fr, float *__restrict__ sw, const float *__restrict__ sp,
+                      const unsigned char *__restrict__ nl, int r, int m, const TrackConst &k)
 {
     float phase = ph[r], freq = fr[r], sweep = sw[r];
-#pragma unroll 4
-    for (int i = r; i < m; i++) {
-        ph[i] = phase; fr[i] = freq; sw[i] = sweep;
-        pll_track_step(phase, freq, sp[i], k);
-        const float f2 = freq + sweep;                                          // CarrierTrackingPLL.c:232-246
-        float s2 = (f2 >= 0) ? fabsf(sweep) : -fabsf(sweep);
-        s2 = (f2 <= k.min_freq) ? -sweep : s2;
-        s2 = (f2 >= k.max_freq) ? -sweep : s2;
-        const bool on = nl[i] != 0;
-        freq = on ? f2 : freq;
-        sweep = on ? s2 : sweep;
+    int i = r;
+    for (; i < m && (i & 3); i++) { ph[i] = phase; fr[i] = freq; sw[i] = sweep; acq_step(phase, freq, sweep, sp[i], nl[i] != 0, k); }
+    if (i + 4 <= m) {
+        float4 c = ld4(sp + i);
+        uchar4 f = *reinterpret_cast<const uchar4 *>(nl + i);
+        for (; i + 4 <= m; i += 4) {
+            float4 cn = c; uchar4 fn = f;
+            if (i + 8 <= m) { cn = ld4(sp + i + 4); fn = *reinterpret_cast<const uchar4 *>(nl + i + 4); }
+            float4 p, q, w;
+            p.x = phase; q.x = freq; w.x = sweep; acq_step(phase, freq, sweep, c.x, f.x != 0, k);
+            p.y = phase; q.y = freq; w.y = sweep; acq_step(phase, freq, sweep, c.y, f.y != 0, k);
+            p.z = phase; q.z = freq; w.z = sweep; acq_step(phase, freq, sweep, c.z, f.z != 0, k);
+            p.w = phase; q.w = freq; w.w = sweep; acq_step(phase, freq, sweep, c.w, f.w != 0, k);
+            st4(ph + i, p); st4(fr + i, q); st4(sw + i, w);
+            c = cn; f = fn;
+        }
     }
+    for (; i < m; i++) { ph[i] = phase; fr[i] = freq; sw[i] = sweep; acq_step(phase, freq, sweep, sp[i], nl[i] != 0, k); }
     ph[m] = phase; fr[m] = freq; sw[m] = sweep;
+}
+
+// x <- (float)((double)x·c + (double)t[i]) over [r, m): the EMA of CarrierTrackingPLL.c:124 / :220 as one dependent chain
+PDT_DEV void acq_ema(float *__restrict__ out, const float *__restrict__ term, int r, int m, double c)
+{
+    float x = out[r];
+    int i = r;
+    for (; i < m && (i & 3); i++) { x = (float)((double)x * c + (double)term[i]); out[i + 1] = x; }
+    if (i + 4 <= m) {
+        float4 t = ld4(term + i);
+        for (; i + 4 <= m; i += 4) {
+            float4 tn = t;
+            if (i + 8 <= m) tn = ld4(term + i + 4);
+            const double t0 = (double)t.x, t1 = (double)t.y, t2 = (double)t.z, t3 = (double)t.w;
+            x = (float)((double)x * c + t0); out[i + 1] = x;
+            x = (float)((double)x * c + t1); out[i + 2] = x;
+            x = (float)((double)x * c + t2); out[i + 3] = x;
+            x = (float)((double)x * c + t3); out[i + 4] = x;
+            t = tn;
+        }
+    }
+    for (; i < m; i++) { x = (float)((double)x * c + (double)term[i]); out[i + 1] = x; }
 }
 
 // CarrierTrackingPLL.c:232 — |π/2 - averagePhase| < 0.05 (float fabs of a double difference, compared in double)
@@ -292,19 +333,9 @@ __global__ void __launch_bounds__(ACQ_THREADS) k_acquire(const TiledArgs a, cons
                 acq_core(s.ph[nxt], s.fr[nxt], s.sw[nxt], s.sp[nxt], s.nl[nxt], 0, m_next, kacq);
             }
         } else if (tid == 32) {
-            float avg = s.avg[r];
-#pragma unroll 4
-            for (int i = r; i < m; i++) {
-                avg = (float)((double)avg * (1.0 - avg_alpha) + (double)s.aterm[i]);               // :124
-                s.avg[i + 1] = avg;
-            }
+            acq_ema(s.avg, s.aterm, r, m, 1.0 - avg_alpha);                                        // :124
         } else if (tid == 64) {
-            float lk = s.lks[r];
-#pragma unroll 4
-            for (int i = r; i < m; i++) {
-                lk = (float)((double)lk * (1.0 - pp.lock_alpha) + (double)s.lterm[i]);             // :220
-                s.lks[i + 1] = lk;
-            }
+            acq_ema(s.lks, s.lterm, r, m, 1.0 - pp.lock_alpha);                                    // :220
         }
         __syncthreads();
         // ---- P2: the decisions taken from the EMAs, all samples at once ---------------------------------------------
@@ -702,16 +733,36 @@ PDT_DEV int rint_index(float x)
     return (r < 0.0f) ? -1 : (int)(unsigned)r;
 }
 
+// one symbol with every check of the reference loop (used for the first symbol of a chunk and near the window / chunk end)
 template <bool FAST>
-__device__ __forceinline__ void gardner_capture(const TiledArgs &a, const uint32_t cap, float *win, float *ssym, float *serr, unsigned *sidx,
-                                                const int lane)
+__device__ __forceinline__ void gardner_careful(float &next, float &prev, float &half, bool &first_symbol, int at, const float *__restrict__ win,
+                                                int w_lo, int w_hi, const float *__restrict__ z, u64 ibase, unsigned n_out, unsigned full_out,
+                                                bool has_prev, float kp, float range, float step, float &sym, float &err)
+{
+    const float cur = win[min((unsigned)(at - w_lo), (unsigned)(GAR_WIN - 1))];
+    const int hi = rint_index<FAST>(half);                                             // :28 index-then-value reuse
+    float hv;
+    if (!first_symbol && hi >= w_lo && hi < w_hi) hv = win[hi - w_lo];
+    else hv = stale_lookup(z, ibase, (unsigned)hi, n_out, full_out, has_prev);
+    first_symbol = false;
+    const float e = clamp_like_ifs(kp * (cur - prev) * hv, -range, range);             // :43-57
+    next = next - e;
+    half = next + step / 2.0;                                                          // :59
+    next = next + step;
+    prev = cur;
+    sym = cur; err = e;
+}
+
+template <bool FAST>
+__device__ __forceinline__ void gardner_capture(const TiledArgs &a, const uint32_t cap, float *__restrict__ win, float *__restrict__ ssym,
+                                                float *__restrict__ serr, unsigned *__restrict__ sidx, const int lane)
 {
     const ChainConst &cc = a.cc;
     const int L = cc.L;
     const u64 n = cap_len(a, cap);
-    const float *z = a.z + (u64)cap * a.ws_stride * L;
-    float *sym_out = a.sym + (u64)cap * a.sym_cap;
-    u64 *gidx_out = a.gidx + (u64)cap * a.sym_cap;
+    const float *__restrict__ z = a.z + (u64)cap * a.ws_stride * L;
+    float *__restrict__ sym_out = a.sym + (u64)cap * a.sym_cap;
+    u64 *__restrict__ gidx_out = a.gidx + (u64)cap * a.sym_cap;
     const pdt_traces *tr = a.traces ? &a.traces[cap] : nullptr;
     const unsigned full_out = cc.chunk * (unsigned)L;
     const float kp = cc.g_kp, range = cc.g_range;
@@ -719,10 +770,12 @@ __device__ __forceinline__ void gardner_capture(const TiledArgs &a, const uint32
     GardnerState gs = GardnerState();
     gardner_begin(gs, cc.gardner_fs, cc.baud);
     const float step = gs.step;
-    // half = next + step/2.0 is a double sum narrowed to float (GardenerClockRecovery.c:59); the double sum of two floats
-    // is exact when their exponents are < 29 apart, and then the float sum is the same correctly rounded value
+    // half = next + step/2.0 is a double sum narrowed to float (GardenerClockRecovery.c:59).  The double sum of two floats
+    // is exact when their exponents are < 29 apart, and then the float sum is the same correctly rounded value: the batch
+    // loop below uses the float sum and re-runs the batch with the double expression if `next` ever was tiny but non-zero.
     const float half_step = (float)((double)step / 2.0);
-    const bool half_exact = ((double)half_step == (double)step / 2.0);
+    const bool half_float_ok = ((double)half_step == (double)step / 2.0) && step > 1.0f && step < 1.0e6f;
+    const float inv_adv = 1.0f / (step + fabsf(range) + 0.01f);
     u64 n_sym = 0;
 
     for (u64 base = 0; base < n; base += cc.chunk) {
@@ -760,25 +813,53 @@ __device__ __forceinline__ void gardner_capture(const TiledArgs &a, const uint32
             if (lane == 0) {
                 float next = gs.next, prev = gs.prev, half = gs.half;
                 const int w_lo = (int)w0, w_hi = (int)(w0 + GAR_WIN);
+                const int limit = ((int)n_out < w_hi) ? (int)n_out : w_hi;
                 for (;;) {
                     const int at = rint_index<FAST>(next);
                     if (at >= (int)n_out) { finished = 1; break; }                     // GardenerClockRecovery.c:24
                     if (at >= w_hi || cnt >= GAR_STAGE) break;                         // refill / flush
-                    const float cur = win[(at < w_lo ? w_lo : at) - w_lo];
-                    const int hi = rint_index<FAST>(half);                             // :28 index-then-value reuse
-                    float hv;
-                    if (!first_symbol && hi >= w_lo && hi < w_hi) hv = win[hi - w_lo];
-                    else hv = stale_lookup(z, ibase, (unsigned)hi, n_out, full_out, has_prev);
-                    first_symbol = false;
-                    float e = kp * (cur - prev) * hv;                                  // :43
-                    e = (e > range) ? range : ((e < -range) ? -range : e);
-                    next = next - e;
-                    if (half_exact && (fabsf(next) >= 9.5367431640625e-07f || next == 0.0f)) half = next + half_step;
-                    else half = next + step / 2.0;                                     // :59
-                    next = next + step;
-                    prev = cur;
-                    ssym[cnt] = cur; sidx[cnt] = (unsigned)at; if (serr) serr[cnt] = e;
-                    cnt++;
+                    // symbols that certainly stay below `limit`: the position advances by at most step + |range| per symbol
+                    int k = 0;
+                    if (!first_symbol && half_float_ok) {
+                        const float room = (float)limit - 4.0f - next;
+                        k = (room > 0.0f) ? 1 + (int)(room * inv_adv) : 0;
+                        if (k > GAR_STAGE - cnt) k = GAR_STAGE - cnt;
+                    }
+                    if (k < 2) {
+                        float sv, ev;
+                        gardner_careful<FAST>(next, prev, half, first_symbol, at, win, w_lo, w_hi, z, ibase, n_out, full_out, has_prev,
+                                              kp, range, step, sv, ev);
+                        ssym[cnt] = sv; sidx[cnt] = (unsigned)at; if (serr) serr[cnt] = ev;
+                        cnt++;
+                        continue;
+                    }
+                    // ---- the hot loop: k symbols, no exit test, no window test (both proven above), float mid-point sum ----
+                    const float next0 = next, prev0 = prev, half0 = half;
+                    bool tiny = false;
+                    for (int j = 0; j < k; j++) {
+                        const int aj = rint_index<FAST>(next);
+                        const float cur = win[min((unsigned)(aj - w_lo), (unsigned)(GAR_WIN - 1))];
+                        const int hj = rint_index<FAST>(half);
+                        const float hv = win[min((unsigned)(hj - w_lo), (unsigned)(GAR_WIN - 1))];
+                        const float e = clamp_like_ifs(kp * (cur - prev) * hv, -range, range);
+                        next = next - e;
+                        tiny |= !(fabsf(next) >= 9.5367431640625e-07f || next == 0.0f);
+                        half = next + half_step;
+                        next = next + step;
+                        prev = cur;
+                        ssym[cnt + j] = cur; sidx[cnt + j] = (unsigned)aj; if (serr) serr[cnt + j] = e;
+                    }
+                    if (tiny) {                 // never observed; keeps the result exact by construction
+                        next = next0; prev = prev0; half = half0;
+                        for (int j = 0; j < k; j++) {
+                            const int aj = rint_index<FAST>(next);
+                            float sv, ev;
+                            gardner_careful<FAST>(next, prev, half, first_symbol, aj, win, w_lo, w_hi, z, ibase, n_out, full_out, has_prev,
+                                                  kp, range, step, sv, ev);
+                            ssym[cnt + j] = sv; sidx[cnt + j] = (unsigned)aj; if (serr) serr[cnt + j] = ev;
+                        }
+                    }
+                    cnt += k;
                 }
                 gs.next = next; gs.prev = prev; gs.half = half;
             }
@@ -826,59 +907,149 @@ __global__ void __launch_bounds__(GAR_WARPS * 32) k_gardner(const TiledArgs a)
     else      gardner_capture<false>(a, cap, wins[wib], ssym[wib], e, sidx[wib], lane);
 }
 
-// Manchester + ByteSync + frame table: lane per capture over its symbol stream (both are cheap integer state machines;
-// the symbol stream is 1/15 of the sample stream).
-__global__ void __launch_bounds__(32) k_bits(const TiledArgs a)
+// ---------------------------------------------------------------------------------------------------
+// k_bits: ManchesterDecode.c:27-97 + ByteSync.c:42-148 over the symbol stream, warp per capture, 32 symbols per step.
+//  * Manchester: the only state carried from symbol to symbol is the pair phase `clockmod`, and a symbol either sets it
+//    to its own parity (two strong equal-sign symbols in front of it, :42-50) or leaves it alone, so the phase seen
+//    by lane l is the parity of the last such symbol at or before l (one ballot), else the carried one.
+//  * ByteSync: every new bit gets the 32-bit history ending at it (a funnel shift of the carried history and this step's
+//    bits), all sync comparisons of the step happen at once, and the frame shifter only walks the few events.
+// ---------------------------------------------------------------------------------------------------
+constexpr int BITS_WARPS = 4;
+constexpr int BITS_FRAME_WORDS = (PDT_FRAME_MAX_BYTES + 3) / 4;
+
+__global__ void __launch_bounds__(BITS_WARPS * 32) k_bits(const TiledArgs a)
 {
-    const uint32_t cap = blockIdx.x * blockDim.x + threadIdx.x;
+    __shared__ unsigned fbuf_all[BITS_WARPS][BITS_FRAME_WORDS];
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t cap = blockIdx.x * BITS_WARPS + wib;
     if (cap >= a.n_captures || !cap_selected(a, cap)) return;
     const ChainConst &cc = a.cc;
+    const SyncParams sp = cc.sync;
     const u64 n = cap_len(a, cap);
     const int L = cc.L;
     const GarRecord gr = a.gar[cap];
-    const float *sym = a.sym + (u64)cap * a.sym_cap;
-    const u64 *gidx = a.gidx + (u64)cap * a.sym_cap;
+    const float *__restrict__ sym = a.sym + (u64)cap * a.sym_cap;
+    const u64 *__restrict__ gidx = a.gidx + (u64)cap * a.sym_cap;
     pdt_frame *frames = a.frames + (size_t)cap * cc.max_frames;
     const pdt_traces *tr = a.traces ? &a.traces[cap] : nullptr;
-    BackState st;
-    back_reset(st);
+    unsigned *fbuf = fbuf_all[wib];
+    const float thr = cc.man_thresh;
     const u64 ns = gr.n_sym < a.sym_cap ? gr.n_sym : a.sym_cap;
-    u64 i = 0;
-    for (; i + 4 <= ns; i += 4) {
-        const float4 v = ld4(sym + i);
-        back_consume_lazy(st, cc, v.x, gidx, i, frames, tr);
-        back_consume_lazy(st, cc, v.y, gidx, i + 1, frames, tr);
-        back_consume_lazy(st, cc, v.z, gidx, i + 2, frames, tr);
-        back_consume_lazy(st, cc, v.w, gidx, i + 3, frames, tr);
-    }
-    for (; i < ns; i++) back_consume_lazy(st, cc, sym[i], gidx, i, frames, tr);
-    st.n_sym = gr.n_sym;
-    back_finish(st, frames);
-    const AcqResult &acq = a.acq[cap];
-    pdt_capture_stats s;
-    s.n_samples = n; s.n_symbols = st.n_sym; s.n_bits = st.n_bits; s.n_frames = st.n_frames;
-    s.locked = acq.locked; s.lock_sample = acq.lock_sample; s.lock_freq_hz = acq.lock_freq_hz;
-    s.norm_factor = acq.norm; s.avg_phase = acq.avg_phase;
-    s.final_phase = acq.phase; s.final_freq = acq.freq;
-    if (acq.locked) {
-        u64 warm, begin, end;
-        for (unsigned k = 0; k < a.pll.max_tiles; k++) {
-            if (!tile_range(acq.track_begin, n, a.pll, k, warm, begin, end)) break;
-            const LoopState2 e = a.pll_end[(size_t)cap * a.pll.max_tiles + k];
-            s.final_phase = e.a; s.final_freq = e.b;
+    const unsigned lt_mask = (1u << lane) - 1u, le_mask = lt_mask | (1u << lane);
+    // frame geometry: bits a frame takes after the sync bit, and where its first bit lands in the stored byte string
+    const int frame_bits = 8 * (sp.last_idx - 1) - sp.carry_bits;              // 813 (POES) / 56 (ARGOS)
+    const int q_base = 8 * cc.prefix_bytes + sp.carry_bits;
+    const int full_bytes = cc.prefix_bytes + (sp.last_idx - 1);
+
+    unsigned cm = 0, hist = 0;                 // Manchester pair phase; ByteSync history (newest bit = LSB)
+    float carry1 = 0.0f, carry2 = 0.0f;        // sym[base-1], sym[base-2]
+    int in_frame = 0, fb = 0, inv = 0, cur_frame = -1;
+    u64 n_bits = 0; uint32_t n_frames = 0;
+
+    auto flush_frame = [&](int n_bytes, int complete) {        // whole warp; cur_frame >= 0
+        __syncwarp();
+        pdt_frame &f = frames[cur_frame];
+        for (int t = lane; t < PDT_FRAME_MAX_BYTES; t += 32) {
+            const unsigned w = fbuf[t >> 2];
+            f.bytes[t] = (t < n_bytes) ? (uint8_t)(w >> (24 - 8 * (t & 3))) : (uint8_t)0;
         }
-    }
-    s.final_gain = acq.norm;
-    {
-        const TilePlan plan = agc_plan(a, acq);
-        u64 warm, begin, end;
-        for (unsigned k = 0; k < a.agc_max_tiles; k++) {
-            if (!tile_range(0, n * L, plan, k, warm, begin, end)) break;
-            s.final_gain = a.agc_end[(size_t)cap * a.agc_max_tiles + k].a;
+        if (lane == 0) { f.n_bytes = (uint8_t)n_bytes; f.complete = (uint8_t)complete; }
+        __syncwarp();
+    };
+
+    for (u64 base = 0; base < ns; base += 32) {
+        const u64 i = base + (u64)lane;
+        const bool valid = i < ns;
+        const float c = valid ? sym[i] : 0.0f;
+        float p = __shfl_up_sync(FULL, c, 1), pp = __shfl_up_sync(FULL, c, 2);
+        if (lane == 0) { p = carry1; pp = carry2; }
+        if (lane == 1) pp = carry1;
+        const bool cond = valid && sign_of(pp) == sign_of(p) && fabsf(pp) > thr && fabsf(p) > thr;      // ManchesterDecode.c:42-50
+        const unsigned below = __ballot_sync(FULL, cond) & le_mask;
+        const unsigned par = (unsigned)(i & 1);
+        const unsigned cm_l = below ? (((unsigned)base + (31u - (unsigned)__clz((int)below))) & 1u) : cm;
+        const bool emit = valid && par == cm_l;                                                        // :52
+        const unsigned bit = (fabsf(p) > fabsf(c)) ? (p > 0 ? 1u : 0u) : (c > 0 ? 0u : 1u);           // :60-82
+        const unsigned eb = __ballot_sync(FULL, emit);
+        const int k = __popc(eb), pos = __popc(eb & lt_mask);
+        cm = __shfl_sync(FULL, cm_l, 31);
+        carry2 = __shfl_sync(FULL, c, 30); carry1 = __shfl_sync(FULL, c, 31);
+        if (k == 0) continue;
+        const unsigned v = __reduce_or_sync(FULL, emit ? (bit << (k - 1 - pos)) : 0u);                 // this step's bits, oldest = MSB
+        if (tr && tr->bits && emit && n_bits + (u64)pos < tr->cap) tr->bits[n_bits + (u64)pos] = (uint8_t)('0' + bit);
+        const unsigned long long H = ((unsigned long long)hist << k) | (unsigned long long)v;
+        const unsigned hj = (lane < k) ? (unsigned)(H >> (k - 1 - lane)) : 0u;                         // history ending at new bit `lane`
+        const unsigned bn = __ballot_sync(FULL, lane < k && (hj & sp.mask) == sp.word);                // ByteSync.c:104-118
+        const unsigned bi = sp.inverse_enabled ? __ballot_sync(FULL, lane < k && (~hj & sp.mask) == sp.word) : 0u;   // :120-133
+        int j0 = 0, sf = 0;
+        for (;;) {
+            if (in_frame) {
+                int take = k - j0; if (take > frame_bits - fb) take = frame_bits - fb;
+                if (lane >= j0 && lane < j0 + take && cur_frame >= 0) {
+                    const unsigned b = ((v >> (k - 1 - lane)) & 1u) ^ (unsigned)inv;                   // :46-52 zero/one swap for an inverted stream
+                    const int q = q_base + fb + (lane - j0);
+                    if (b) atomicOr(&fbuf[q >> 5], 1u << (31 - (q & 31)));
+                }
+                fb += take; j0 += take;
+                if (fb < frame_bits) break;                       // all new bits went into the open frame
+                if (cur_frame >= 0) flush_frame(full_bytes, 1);   // :58-72 frame complete
+                in_frame = 0; cur_frame = -1;
+                sf = j0 - 1;                                      // the closing bit itself is examined for a sync word (emission precedes detection)
+            }
+            const unsigned m = (bn | bi) & ~((sf >= 32) ? FULL : ((1u << sf) - 1u));
+            if (m == 0) break;
+            const int jm = __ffs((int)m) - 1;
+            inv = ((bn >> jm) & 1u) ? 0 : 1;
+            cur_frame = (n_frames < cc.max_frames) ? (int)n_frames : -1;
+            n_frames++;
+            if (cur_frame >= 0) {
+                __syncwarp();
+                for (int t = lane; t < BITS_FRAME_WORDS; t += 32) fbuf[t] = (t == 0 && cc.prefix_bytes) ? 0xEDE20000u : 0u;
+                if (emit && pos == jm) {
+                    pdt_frame &f = frames[cur_frame];
+                    f.sample_index = gidx[i]; f.bit_index = (uint32_t)(n_bits + (u64)jm);
+                    f.inverse = (uint8_t)inv; f.complete = 0; f.pad = 0; f.n_bytes = (uint8_t)cc.prefix_bytes;
+                    if (cc.prefix_bytes) { f.bytes[0] = 0xED; f.bytes[1] = 0xE2; }
+                }
+                __syncwarp();
+            }
+            in_frame = 1; fb = 0; j0 = jm + 1;
+            if (j0 >= k) break;
         }
+        n_bits += (u64)k;
+        hist = (unsigned)H;
     }
-    s.final_next = gr.final_next;
-    a.stats[cap] = s;
+    // a capture may end inside a frame: the bytes completed so far are kept
+    if (in_frame && cur_frame >= 0) flush_frame(cc.prefix_bytes + (sp.carry_bits + fb) / 8, 0);
+    if (lane == 0) {
+        const AcqResult &acq = a.acq[cap];
+        pdt_capture_stats s;
+        s.n_samples = n; s.n_symbols = gr.n_sym; s.n_bits = n_bits; s.n_frames = n_frames;
+        s.locked = acq.locked; s.lock_sample = acq.lock_sample; s.lock_freq_hz = acq.lock_freq_hz;
+        s.norm_factor = acq.norm; s.avg_phase = acq.avg_phase;
+        s.final_phase = acq.phase; s.final_freq = acq.freq;
+        if (acq.locked) {
+            u64 warm, begin, end;
+            for (unsigned k = 0; k < a.pll.max_tiles; k++) {
+                if (!tile_range(acq.track_begin, n, a.pll, k, warm, begin, end)) break;
+                const LoopState2 e = a.pll_end[(size_t)cap * a.pll.max_tiles + k];
+                s.final_phase = e.a; s.final_freq = e.b;
+            }
+        }
+        s.final_gain = acq.norm;
+        {
+            const TilePlan plan = agc_plan(a, acq);
+            u64 warm, begin, end;
+            for (unsigned k = 0; k < a.agc_max_tiles; k++) {
+                if (!tile_range(0, n * L, plan, k, warm, begin, end)) break;
+                s.final_gain = a.agc_end[(size_t)cap * a.agc_max_tiles + k].a;
+            }
+        }
+        s.final_next = gr.final_next;
+        a.stats[cap] = s;
+    }
 }
 
 } // namespace tiled
