@@ -184,7 +184,10 @@ static int tiled_setup(pdt_ctx *c)
     t.pll.W = W; t.pll.T = T; t.pll.T0 = W + T;
     t.pll.max_tiles = 1 + (unsigned)((stride + T - 1) / T);
     t.agc_min_tile = c->params.agc_min_tile ? ((c->params.agc_min_tile + 3) & ~3u) : 4096u * (unsigned)cc.L;
-    t.agc_max_tiles = 1 + (unsigned)((stride * cc.L + t.agc_min_tile - 1) / t.agc_min_tile);
+    {
+        const u64 t_min = ((t.agc_min_tile / 2) + 3) & ~3ull;       // agc_plan: T = W/2 >= agc_min_tile/2
+        t.agc_max_tiles = 2 + (unsigned)((stride * cc.L + t_min - 1) / t_min);
+    }
     t.est_fmax = (float)c->params.max_carrier_dev + 600.0f;
     int D = (int)((double)cc.pll.Fs / (2.5 * (double)t.est_fmax));
     t.est_decim = D < 1 ? 1 : D;

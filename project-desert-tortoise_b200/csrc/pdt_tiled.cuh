@@ -114,6 +114,12 @@ PDT_DEV bool tile_range(u64 first, u64 n, const TilePlan &p, unsigned k, u64 &wa
 PDT_DEV float4 ld4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 PDT_DEV void   st4(float *p, float4 v) { *reinterpret_cast<float4 *>(p) = v; }
 
+// Lane-serial streaming loops.  Each lane walks its own tile, so its loads are 16-byte pieces of a private stream:
+// nothing hides their DRAM latency (~1000-1500 cycles under load, ncu: 50 % long-scoreboard stalls with one quad
+// group of look-ahead) except distance.  PF_Q quads are kept in flight: a quad is re-loaded for the NEXT 4·PF_Q-sample
+// round as soon as it has been consumed, i.e. 4·PF_Q samples (>= 2000 cycles of recurrence) ahead of its use.
+constexpr int PF_Q = 8;
+
 // run the track core over sp[i0, i1); STORE: write the phase used to derotate sample i to ph[i]
 template <bool STORE>
 PDT_DEV void pll_track_run(const float *__restrict__ sp, float *__restrict__ ph, u64 i0, u64 i1, float &phase, float &freq,
@@ -121,19 +127,21 @@ PDT_DEV void pll_track_run(const float *__restrict__ sp, float *__restrict__ ph,
 {
     u64 i = i0;
     for (; i < i1 && (i & 3); i++) { if (STORE) ph[i] = phase; pll_track_step(phase, freq, sp[i], k); }
-    if (i + 16 <= i1) {
-        float4 c0 = ld4(sp + i), c1 = ld4(sp + i + 4), c2 = ld4(sp + i + 8), c3 = ld4(sp + i + 12);
-        for (; i + 16 <= i1; i += 16) {
-            float4 n0 = c0, n1 = c1, n2 = c2, n3 = c3;
-            if (i + 32 <= i1) { n0 = ld4(sp + i + 16); n1 = ld4(sp + i + 20); n2 = ld4(sp + i + 24); n3 = ld4(sp + i + 28); }
-            float4 o;
-#define PDT_Q(c, off)                                                                                         \
-            o.x = phase; pll_track_step(phase, freq, c.x, k); o.y = phase; pll_track_step(phase, freq, c.y, k); \
-            o.z = phase; pll_track_step(phase, freq, c.z, k); o.w = phase; pll_track_step(phase, freq, c.w, k); \
-            if (STORE) st4(ph + i + off, o);
-            PDT_Q(c0, 0) PDT_Q(c1, 4) PDT_Q(c2, 8) PDT_Q(c3, 12)
-#undef PDT_Q
-            c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    if (i + 4 * PF_Q <= i1) {
+        float4 c[PF_Q];
+#pragma unroll
+        for (int q = 0; q < PF_Q; q++) c[q] = ld4(sp + i + 4 * q);
+        for (; i + 4 * PF_Q <= i1; i += 4 * PF_Q) {
+            const bool more = i + 8 * PF_Q <= i1;
+#pragma unroll
+            for (int q = 0; q < PF_Q; q++) {
+                const float4 v = c[q];
+                if (more) c[q] = ld4(sp + i + 4 * PF_Q + 4 * q);
+                float4 o;
+                o.x = phase; pll_track_step(phase, freq, v.x, k); o.y = phase; pll_track_step(phase, freq, v.y, k);
+                o.z = phase; pll_track_step(phase, freq, v.z, k); o.w = phase; pll_track_step(phase, freq, v.w, k);
+                if (STORE) st4(ph + i + 4 * q, o);
+            }
         }
     }
     for (; i < i1; i++) { if (STORE) ph[i] = phase; pll_track_step(phase, freq, sp[i], k); }
@@ -145,22 +153,108 @@ PDT_DEV void agc_run(const float *__restrict__ x, float *__restrict__ z, u64 i0,
 {
     u64 i = i0;
     for (; i < i1 && (i & 3); i++) { const float v = agc_step(st, x[i], attack, decay); if (STORE) z[i] = v; }
-    if (i + 16 <= i1) {
-        float4 c0 = ld4(x + i), c1 = ld4(x + i + 4), c2 = ld4(x + i + 8), c3 = ld4(x + i + 12);
-        for (; i + 16 <= i1; i += 16) {
-            float4 n0 = c0, n1 = c1, n2 = c2, n3 = c3;
-            if (i + 32 <= i1) { n0 = ld4(x + i + 16); n1 = ld4(x + i + 20); n2 = ld4(x + i + 24); n3 = ld4(x + i + 28); }
-            float4 o;
-#define PDT_Q(c, off)                                                                                     \
-            o.x = agc_step(st, c.x, attack, decay); o.y = agc_step(st, c.y, attack, decay);                 \
-            o.z = agc_step(st, c.z, attack, decay); o.w = agc_step(st, c.w, attack, decay);                 \
-            if (STORE) st4(z + i + off, o);
-            PDT_Q(c0, 0) PDT_Q(c1, 4) PDT_Q(c2, 8) PDT_Q(c3, 12)
-#undef PDT_Q
-            c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    if (i + 4 * PF_Q <= i1) {
+        float4 c[PF_Q];
+#pragma unroll
+        for (int q = 0; q < PF_Q; q++) c[q] = ld4(x + i + 4 * q);
+        for (; i + 4 * PF_Q <= i1; i += 4 * PF_Q) {
+            const bool more = i + 8 * PF_Q <= i1;
+#pragma unroll
+            for (int q = 0; q < PF_Q; q++) {
+                const float4 v = c[q];
+                if (more) c[q] = ld4(x + i + 4 * PF_Q + 4 * q);
+                float4 o;
+                o.x = agc_step(st, v.x, attack, decay); o.y = agc_step(st, v.y, attack, decay);
+                o.z = agc_step(st, v.z, attack, decay); o.w = agc_step(st, v.w, attack, decay);
+                if (STORE) st4(z + i + 4 * q, o);
+            }
         }
     }
     for (; i < i1; i++) { const float v = agc_step(st, x[i], attack, decay); if (STORE) z[i] = v; }
+}
+
+// The AGC loop almost always sits in one regime: |error| <= gain, so the DECAY rate applies (AGC.c:108-118 picks the
+// attack rate only while the gain is below the error, i.e. for gains < ~1), and neither clamp (:124-131) fires.  There
+// the recurrence is four dependent float ops:  z = x·g;  e = |z| - 1;  g = g - e·decay   (16 cycles against 45 for the
+// general step with its predicated selects, tools/microbench.cu).  agc_run_fast assumes that regime and PROVES it on the
+// side: `lo` = min over the run of (gain - |error|) and of the new gain, `hi` = max of the new gain, NaN-propagating.  The
+// caller accepts the result only if lo >= 0 and hi <= 5000 and otherwise re-runs the range with the general step, so
+// the output is the reference's in every case.
+struct AgcProof { float lo, hi; };
+
+PDT_DEV float min_nan(float a, float b)
+{
+#ifdef __CUDA_ARCH__
+    float r; asm("min.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r;
+#else
+    return (a != a || b != b) ? NAN : (a < b ? a : b);
+#endif
+}
+PDT_DEV float max_nan(float a, float b)
+{
+#ifdef __CUDA_ARCH__
+    float r; asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r;
+#else
+    return (a != a || b != b) ? NAN : (a > b ? a : b);
+#endif
+}
+
+PDT_DEV float agc_step_fast(float &gain, float x, float decay, AgcProof &pr)
+{
+    const float zv = x * gain;
+    const float err = fabsf(zv) - 1.0f;
+    const float g = gain - err * decay;
+    pr.lo = min_nan(pr.lo, min_nan(gain - fabsf(err), g));
+    pr.hi = max_nan(pr.hi, g);
+    gain = g;
+    return zv;
+}
+
+PDT_DEV bool agc_proof_ok(const AgcProof &pr) { return pr.lo >= 0.0f && pr.hi <= 5000.0f; }
+
+template <bool STORE>
+PDT_DEV void agc_run_fast(const float *__restrict__ x, float *__restrict__ z, u64 i0, u64 i1, float &gain, float decay, AgcProof &pr)
+{
+    u64 i = i0;
+    for (; i < i1 && (i & 3); i++) { const float v = agc_step_fast(gain, x[i], decay, pr); if (STORE) z[i] = v; }
+    if (i + 4 * PF_Q <= i1) {
+        float4 c[PF_Q];
+#pragma unroll
+        for (int q = 0; q < PF_Q; q++) c[q] = ld4(x + i + 4 * q);
+        for (; i + 4 * PF_Q <= i1; i += 4 * PF_Q) {
+            const bool more = i + 8 * PF_Q <= i1;
+#pragma unroll
+            for (int q = 0; q < PF_Q; q++) {
+                const float4 v = c[q];
+                if (more) c[q] = ld4(x + i + 4 * PF_Q + 4 * q);
+                float4 o;
+                o.x = agc_step_fast(gain, v.x, decay, pr); o.y = agc_step_fast(gain, v.y, decay, pr);
+                o.z = agc_step_fast(gain, v.z, decay, pr); o.w = agc_step_fast(gain, v.w, decay, pr);
+                if (STORE) st4(z + i + 4 * q, o);
+            }
+        }
+    }
+    for (; i < i1; i++) { const float v = agc_step_fast(gain, x[i], decay, pr); if (STORE) z[i] = v; }
+}
+
+// a whole [warm-up +] tile: the proven fast regime first, the general recurrence if the proof fails
+PDT_DEV void agc_tile(const float *__restrict__ x, float *__restrict__ z, u64 warm, u64 begin, u64 end, float &gain, float &start_gain,
+                      float attack, float decay)
+{
+    const float g0 = gain;
+    AgcProof pr; pr.lo = 0.0f; pr.hi = 0.0f;
+    float g = g0;
+    if (warm < begin) agc_run_fast<false>(x, z, warm, begin, g, decay, pr);
+    float gs = g;
+    agc_run_fast<true>(x, z, begin, end, g, decay, pr);
+    if (!agc_proof_ok(pr)) {
+        AgcState st; st.init = 1; st.gain = g0;
+        if (warm < begin) agc_run<false>(x, z, warm, begin, st, attack, decay);
+        gs = st.gain;
+        agc_run<true>(x, z, begin, end, st, attack, decay);
+        g = st.gain;
+    }
+    start_gain = gs; gain = g;
 }
 
 // ---------------------------------------------------------------------------------------------------

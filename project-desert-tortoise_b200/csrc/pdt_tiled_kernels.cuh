@@ -72,7 +72,7 @@ PDT_DEV TilePlan agc_plan(const TiledArgs &a, const AcqResult &acq)
     if (w < (double)a.agc_min_tile) w = (double)a.agc_min_tile;
     if (w > 1e15) w = 1e15;
     p.W = ((u64)w + 3) & ~3ull;
-    p.T = p.W; p.T0 = 2 * p.W; p.max_tiles = a.agc_max_tiles;
+    p.T = (p.W / 2 + 3) & ~3ull; p.T0 = p.W; p.max_tiles = a.agc_max_tiles;
     return p;
 }
 
@@ -486,8 +486,8 @@ __global__ void __launch_bounds__(128) k_pll_core(const TiledArgs a)
     const u64 gid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (u64)a.n_captures * a.pll.max_tiles) return;
     // consecutive lanes take consecutive captures (same tile index): equal work per lane inside a warp
-    const uint32_t cap = (uint32_t)(gid % a.n_captures);
-    const unsigned k = (unsigned)(gid / a.n_captures);
+    const uint32_t cap = (uint32_t)(gid / a.pll.max_tiles);      // a warp = consecutive tiles of ONE capture: its 32 streams
+    const unsigned k = (unsigned)(gid % a.pll.max_tiles);         // share pages / TLB entries and have equal length
     const AcqResult &acq = a.acq[cap];
     const u64 n = cap_len(a, cap), first = (u64)cap * a.stride;
     u64 warm, begin, end;
@@ -531,8 +531,8 @@ __global__ void __launch_bounds__(128) k_pll_fix_par(const TiledArgs a)
 {
     const u64 gid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (u64)a.n_captures * a.pll.max_tiles) return;
-    const uint32_t cap = (uint32_t)(gid % a.n_captures);
-    const unsigned k = (unsigned)(gid / a.n_captures);
+    const uint32_t cap = (uint32_t)(gid / a.pll.max_tiles);      // a warp = consecutive tiles of ONE capture: its 32 streams
+    const unsigned k = (unsigned)(gid % a.pll.max_tiles);         // share pages / TLB entries and have equal length
     if (k == 0) return;
     const AcqResult &acq = a.acq[cap];
     const u64 n = cap_len(a, cap);
@@ -639,8 +639,8 @@ __global__ void __launch_bounds__(128) k_agc_core(const TiledArgs a)
 {
     const u64 gid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (u64)a.n_captures * a.agc_max_tiles) return;
-    const uint32_t cap = (uint32_t)(gid % a.n_captures);
-    const unsigned k = (unsigned)(gid / a.n_captures);
+    const uint32_t cap = (uint32_t)(gid / a.agc_max_tiles);
+    const unsigned k = (unsigned)(gid % a.agc_max_tiles);
     const AcqResult &acq = a.acq[cap];
     const int L = a.cc.L;
     const u64 nL = cap_len(a, cap) * L, first = (u64)cap * a.ws_stride * L;
@@ -650,24 +650,20 @@ __global__ void __launch_bounds__(128) k_agc_core(const TiledArgs a)
     const float *y = a.y + first;
     float *z = a.z + first;
     const size_t slot = (size_t)cap * a.agc_max_tiles + k;
-    AgcState st;
-    st.init = 1;
-    if (k == 0) st.gain = acq.norm;                                      // AGC.c:92-96: first call seeds gain with `initial`
-    else {
-        st.gain = agc_guess(y, warm);
-        agc_run<false>(y, z, warm, begin, st, a.cc.agc_attack, a.cc.agc_decay);
-    }
-    a.agc_start[slot] = LoopState2{st.gain, 0.0f};
-    agc_run<true>(y, z, begin, end, st, a.cc.agc_attack, a.cc.agc_decay);
-    a.agc_end[slot] = LoopState2{st.gain, 0.0f};
+    float gain, start_gain;
+    if (k == 0) gain = acq.norm;                                         // AGC.c:92-96: first call seeds gain with `initial`
+    else        gain = agc_guess(y, warm);
+    agc_tile(y, z, warm, begin, end, gain, start_gain, a.cc.agc_attack, a.cc.agc_decay);
+    a.agc_start[slot] = LoopState2{start_gain, 0.0f};
+    a.agc_end[slot] = LoopState2{gain, 0.0f};
 }
 
 __global__ void __launch_bounds__(128) k_agc_fix_par(const TiledArgs a)
 {
     const u64 gid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (u64)a.n_captures * a.agc_max_tiles) return;
-    const uint32_t cap = (uint32_t)(gid % a.n_captures);
-    const unsigned k = (unsigned)(gid / a.n_captures);
+    const uint32_t cap = (uint32_t)(gid / a.agc_max_tiles);
+    const unsigned k = (unsigned)(gid % a.agc_max_tiles);
     if (k == 0) return;
     const AcqResult &acq = a.acq[cap];
     const int L = a.cc.L;
@@ -678,10 +674,10 @@ __global__ void __launch_bounds__(128) k_agc_fix_par(const TiledArgs a)
     const size_t slot = (size_t)cap * a.agc_max_tiles + k;
     const LoopState2 truth = ld_state(&a.agc_end[slot - 1]);
     if (same_bits(ld_state(&a.agc_start[slot]), truth)) return;
-    AgcState st; st.init = 1; st.gain = truth.a;
-    agc_run<true>(a.y + first, a.z + first, begin, end, st, a.cc.agc_attack, a.cc.agc_decay);
+    float gain = truth.a, sg;
+    agc_tile(a.y + first, a.z + first, begin, begin, end, gain, sg, a.cc.agc_attack, a.cc.agc_decay);
     st_state(&a.agc_start[slot], truth);
-    st_state(&a.agc_end[slot], LoopState2{st.gain, 0.0f});
+    st_state(&a.agc_end[slot], LoopState2{gain, 0.0f});
     atomicAdd(&a.counters[1], 1u);
 }
 
@@ -700,10 +696,10 @@ __global__ void __launch_bounds__(128) k_agc_fix(const TiledArgs a)
         const size_t slot = (size_t)cap * a.agc_max_tiles + k;
         const LoopState2 truth = a.agc_end[slot - 1];
         if (same_bits(a.agc_start[slot], truth)) continue;
-        AgcState st; st.init = 1; st.gain = truth.a;
-        agc_run<true>(a.y + first, a.z + first, begin, end, st, a.cc.agc_attack, a.cc.agc_decay);
+        float gain = truth.a, sg;
+        agc_tile(a.y + first, a.z + first, begin, begin, end, gain, sg, a.cc.agc_attack, a.cc.agc_decay);
         a.agc_start[slot] = truth;
-        a.agc_end[slot] = LoopState2{st.gain, 0.0f};
+        a.agc_end[slot] = LoopState2{gain, 0.0f};
         fixed++;
     }
     if (fixed) atomicAdd(&a.counters[1], fixed);
