@@ -216,6 +216,9 @@ static int tiled_setup(pdt_ctx *c)
     void (*kf)(const TiledArgs, const TapsRev) = cc.L == 1 ? k_front<1> : cc.L == 2 ? k_front<2> : cc.L == 3 ? k_front<3> : k_front<4>;
     if ((e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->front_smem)) != cudaSuccess)
         return fail(PDT_ECUDA, "cudaFuncSetAttribute(k_front): %s", cudaGetErrorString(e));
+    for (void (*kl)(const TiledArgs) : {k_pll_core, k_pll_fix_par, k_agc_core, k_agc_fix_par})
+        if ((e = cudaFuncSetAttribute(kl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LS_SMEM)) != cudaSuccess)
+            return fail(PDT_ECUDA, "cudaFuncSetAttribute(lane-stream kernel): %s", cudaGetErrorString(e));
     return PDT_OK;
 }
 
@@ -270,10 +273,10 @@ struct GroupLaunch {
         if (q.pll.max_tiles > 1)
             k_estimate<<<blocks((u64)cnt * (q.pll.max_tiles - 1), EST_WARPS), EST_WARPS * 32, 0, s>>>(q);
         mark(s, "k_estimate");
-        k_pll_core<<<blocks((u64)cnt * q.pll.max_tiles, 128), 128, 0, s>>>(q);
+        k_pll_core<<<blocks((u64)cnt * q.pll.max_tiles, LS_WARPS * 32), LS_WARPS * 32, LS_SMEM, s>>>(q);
         mark(s, "k_pll_core");
-        k_pll_fix_par<<<blocks((u64)cnt * q.pll.max_tiles, 128), 128, 0, s>>>(q);
-        k_pll_fix_par<<<blocks((u64)cnt * q.pll.max_tiles, 128), 128, 0, s>>>(q);
+        k_pll_fix_par<<<blocks((u64)cnt * q.pll.max_tiles, LS_WARPS * 32), LS_WARPS * 32, LS_SMEM, s>>>(q);
+        k_pll_fix_par<<<blocks((u64)cnt * q.pll.max_tiles, LS_WARPS * 32), LS_WARPS * 32, LS_SMEM, s>>>(q);
         mark(s, "k_pll_fix_par");
         k_pll_fix<<<blocks(cnt, 128), 128, 0, s>>>(q);
         mark(s, "k_pll_fix");
@@ -289,9 +292,9 @@ struct GroupLaunch {
         mark(s, "k_front");
         k_agc_plan<<<blocks((u64)cnt * 32, 128), 128, 0, s>>>(q);
         mark(s, "k_agc_plan");
-        k_agc_core<<<blocks((u64)cnt * q.agc_max_tiles, 128), 128, 0, s>>>(q);
+        k_agc_core<<<blocks((u64)cnt * q.agc_max_tiles, LS_WARPS * 32), LS_WARPS * 32, LS_SMEM, s>>>(q);
         mark(s, "k_agc_core");
-        k_agc_fix_par<<<blocks((u64)cnt * q.agc_max_tiles, 128), 128, 0, s>>>(q);
+        k_agc_fix_par<<<blocks((u64)cnt * q.agc_max_tiles, LS_WARPS * 32), LS_WARPS * 32, LS_SMEM, s>>>(q);
         mark(s, "k_agc_fix_par");
         k_agc_fix<<<blocks(cnt, 128), 128, 0, s>>>(q);
         mark(s, "k_agc_fix");

@@ -15,6 +15,7 @@
 #pragma once
 
 #include "pdt_tiled.cuh"
+#include "pdt_lanestream.cuh"
 
 namespace pdt {
 namespace tiled {
@@ -479,34 +480,60 @@ __global__ void __launch_bounds__(EST_WARPS * 32) k_estimate(const TiledArgs a)
 }
 
 // ---------------------------------------------------------------------------------------------------
-// PLL track core: lane per (capture, tile)
+// PLL track core: lane per (capture, tile), a warp = 32 consecutive tiles of one capture, streams moved by the TMA
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128) k_pll_core(const TiledArgs a)
-{
-    const u64 gid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (u64)a.n_captures * a.pll.max_tiles) return;
-    // consecutive lanes take consecutive captures (same tile index): equal work per lane inside a warp
-    const uint32_t cap = (uint32_t)(gid / a.pll.max_tiles);      // a warp = consecutive tiles of ONE capture: its 32 streams
-    const unsigned k = (unsigned)(gid % a.pll.max_tiles);         // share pages / TLB entries and have equal length
-    const AcqResult &acq = a.acq[cap];
-    const u64 n = cap_len(a, cap), first = (u64)cap * a.stride;
-    u64 warm, begin, end;
-    if (!cap_selected(a, cap) || !acq.locked || !tile_range(acq.track_begin, n, a.pll, k, warm, begin, end)) return;
-    const TrackConst kc = track_const(a, acq);
-    const float *sp = a.sp + (u64)cap * a.ws_stride;
-    float *ph = a.ph + (u64)cap * a.ws_stride;
-    const size_t slot = (size_t)cap * a.pll.max_tiles + k;
-    float phase, freq;
-    if (k == 0) { phase = acq.phase; freq = acq.freq; }
-    else {
-        const LoopState2 g = a.guess[slot];
-        phase = g.a; freq = g.b;
-        if (freq > kc.max_freq) freq = kc.max_freq; else if (freq < kc.min_freq) freq = kc.min_freq;
-        pll_track_run<false>(sp, ph, warm, begin, phase, freq, kc);
+constexpr int LS_WARPS = 2;                               // warps per CTA of the lane-stream kernels
+constexpr size_t LS_SMEM = LS_WARPS * sizeof(LaneStreamSmem);
+
+struct PllLaneStep {
+    float phase, freq; TrackConst k;
+    __device__ __forceinline__ void quad(const float4 &v, float4 &o)
+    {
+        o.x = phase; pll_track_step(phase, freq, v.x, k); o.y = phase; pll_track_step(phase, freq, v.y, k);
+        o.z = phase; pll_track_step(phase, freq, v.z, k); o.w = phase; pll_track_step(phase, freq, v.w, k);
     }
-    a.pll_start[slot] = LoopState2{phase, freq};
-    pll_track_run<true>(sp, ph, begin, end, phase, freq, kc);
-    a.pll_end[slot] = LoopState2{phase, freq};
+    __device__ __forceinline__ float one(float v) { const float p = phase; pll_track_step(phase, freq, v, k); return p; }
+};
+
+__global__ void __launch_bounds__(LS_WARPS * 32) k_pll_core(const TiledArgs a)
+{
+    extern __shared__ __align__(128) unsigned char ls_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    LaneStream sm = lane_stream_init(&reinterpret_cast<LaneStreamSmem *>(ls_raw)[wib], lane);
+    const u64 gid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t cap = (uint32_t)(gid / a.pll.max_tiles);      // a warp = consecutive tiles of ONE capture: equal length,
+    const unsigned k = (unsigned)(gid % a.pll.max_tiles);         // same pages
+    bool active = cap < a.n_captures && cap_selected(a, cap);
+    u64 warm = 0, begin = 0, end = 0;
+    PllLaneStep st; st.phase = 0.f; st.freq = 0.f; st.k = TrackConst{0.f, 0.f, 0.f, 0.f};
+    const float *sp = a.sp; float *ph = a.ph;
+    size_t slot = 0;
+    if (active) {
+        const AcqResult &acq = a.acq[cap];
+        active = acq.locked && tile_range(acq.track_begin, cap_len(a, cap), a.pll, k, warm, begin, end);
+        if (active) {
+            st.k = track_const(a, acq);
+            sp = a.sp + (u64)cap * a.ws_stride; ph = a.ph + (u64)cap * a.ws_stride;
+            slot = (size_t)cap * a.pll.max_tiles + k;
+            if (k == 0) {
+                st.phase = acq.phase; st.freq = acq.freq;
+                // tile 0 starts at the (arbitrary) sample behind the lock latch: walk to the first 16-byte boundary
+                u64 a0 = (begin + 3) & ~3ull; if (a0 > end) a0 = end;
+                for (u64 i = begin; i < a0; i++) { ph[i] = st.phase; pll_track_step(st.phase, st.freq, sp[i], st.k); }
+                a.pll_start[slot] = LoopState2{acq.phase, acq.freq};
+                warm = begin = a0;
+            } else {
+                const LoopState2 g = a.guess[slot];
+                st.phase = g.a; st.freq = g.b;
+                if (st.freq > st.k.max_freq) st.freq = st.k.max_freq; else if (st.freq < st.k.min_freq) st.freq = st.k.min_freq;
+            }
+        }
+    }
+    if (!active) warm = begin = end = 0;
+    lane_stream<false>(sm, lane, sp, ph, warm, begin, begin, st);   // warm-up: nothing is stored
+    if (active && k != 0) a.pll_start[slot] = LoopState2{st.phase, st.freq};
+    lane_stream<true>(sm, lane, sp, ph, begin, begin, end, st);
+    if (active) a.pll_end[slot] = LoopState2{st.phase, st.freq};
 }
 
 PDT_DEV bool same_bits(const LoopState2 &x, const LoopState2 &y) { return pdt_f2u(x.a) == pdt_f2u(y.a) && pdt_f2u(x.b) == pdt_f2u(y.b); }
@@ -527,26 +554,38 @@ PDT_DEV void st_state(LoopState2 *p, const LoopState2 &v)
 // from that end state, all such tiles at once.  A predecessor that is itself being repaired in the same pass may
 // still change; the state actually used is recorded in pll_start, so the next pass (or the final serial sweep in
 // k_pll_fix) sees the difference.  Tiles converge long before their end, so one pass almost always suffices.
-__global__ void __launch_bounds__(128) k_pll_fix_par(const TiledArgs a)
+__global__ void __launch_bounds__(LS_WARPS * 32) k_pll_fix_par(const TiledArgs a)
 {
+    extern __shared__ __align__(128) unsigned char ls_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    LaneStream sm = lane_stream_init(&reinterpret_cast<LaneStreamSmem *>(ls_raw)[wib], lane);
     const u64 gid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (u64)a.n_captures * a.pll.max_tiles) return;
-    const uint32_t cap = (uint32_t)(gid / a.pll.max_tiles);      // a warp = consecutive tiles of ONE capture: its 32 streams
-    const unsigned k = (unsigned)(gid % a.pll.max_tiles);         // share pages / TLB entries and have equal length
-    if (k == 0) return;
-    const AcqResult &acq = a.acq[cap];
-    const u64 n = cap_len(a, cap);
-    u64 warm, begin, end;
-    if (!cap_selected(a, cap) || !acq.locked || !tile_range(acq.track_begin, n, a.pll, k, warm, begin, end)) return;
-    const size_t slot = (size_t)cap * a.pll.max_tiles + k;
-    const LoopState2 truth = ld_state(&a.pll_end[slot - 1]);
-    if (same_bits(ld_state(&a.pll_start[slot]), truth)) return;
-    const TrackConst kc = track_const(a, acq);
-    float phase = truth.a, freq = truth.b;
-    pll_track_run<true>(a.sp + (u64)cap * a.ws_stride, a.ph + (u64)cap * a.ws_stride, begin, end, phase, freq, kc);
-    st_state(&a.pll_start[slot], truth);
-    st_state(&a.pll_end[slot], LoopState2{phase, freq});
-    atomicAdd(&a.counters[0], 1u);
+    const uint32_t cap = (uint32_t)(gid / a.pll.max_tiles);
+    const unsigned k = (unsigned)(gid % a.pll.max_tiles);
+    bool active = cap < a.n_captures && k != 0 && cap_selected(a, cap);
+    u64 warm = 0, begin = 0, end = 0;
+    PllLaneStep st; st.phase = 0.f; st.freq = 0.f; st.k = TrackConst{0.f, 0.f, 0.f, 0.f};
+    size_t slot = 0;
+    LoopState2 truth{0.f, 0.f};
+    if (active) {
+        const AcqResult &acq = a.acq[cap];
+        active = acq.locked && tile_range(acq.track_begin, cap_len(a, cap), a.pll, k, warm, begin, end);
+        if (active) {
+            slot = (size_t)cap * a.pll.max_tiles + k;
+            truth = ld_state(&a.pll_end[slot - 1]);
+            active = !same_bits(ld_state(&a.pll_start[slot]), truth);
+            st.k = track_const(a, acq); st.phase = truth.a; st.freq = truth.b;
+        }
+    }
+    if (!__any_sync(0xffffffffu, active)) return;
+    if (!active) begin = end = 0;
+    const u64 off = (u64)(active ? cap : 0) * a.ws_stride;
+    lane_stream<true>(sm, lane, a.sp + off, a.ph + off, begin, begin, end, st);
+    if (active) {
+        st_state(&a.pll_start[slot], truth);
+        st_state(&a.pll_end[slot], LoopState2{st.phase, st.freq});
+        atomicAdd(&a.counters[0], 1u);
+    }
 }
 
 __global__ void __launch_bounds__(128) k_pll_fix(const TiledArgs a)
@@ -635,50 +674,116 @@ PDT_DEV float agc_guess(const float *y, u64 at)
     return (float)cnt / sum;
 }
 
-__global__ void __launch_bounds__(128) k_agc_core(const TiledArgs a)
+struct AgcFastLaneStep {
+    float gain, decay; AgcProof pr;
+    __device__ __forceinline__ void quad(const float4 &v, float4 &o)
+    {
+        o.x = agc_step_fast(gain, v.x, decay, pr); o.y = agc_step_fast(gain, v.y, decay, pr);
+        o.z = agc_step_fast(gain, v.z, decay, pr); o.w = agc_step_fast(gain, v.w, decay, pr);
+    }
+    __device__ __forceinline__ float one(float v) { return agc_step_fast(gain, v, decay, pr); }
+};
+struct AgcLaneStep {
+    AgcState st; float attack, decay;
+    __device__ __forceinline__ void quad(const float4 &v, float4 &o)
+    {
+        o.x = agc_step(st, v.x, attack, decay); o.y = agc_step(st, v.y, attack, decay);
+        o.z = agc_step(st, v.z, attack, decay); o.w = agc_step(st, v.w, attack, decay);
+    }
+    __device__ __forceinline__ float one(float v) { return agc_step(st, v, attack, decay); }
+};
+
+// [warm-up +] tile of every lane of the warp: the proven fast regime first; lanes whose proof fails (and only they) repeat
+// their range with the general recurrence.  Returns the gain at `begin` in start_gain and the final gain in gain.
+__device__ __forceinline__ void agc_tile_warp(LaneStream &sm, const int lane, const float *x, float *z, u64 warm, u64 begin, u64 end,
+                                              float &gain, float &start_gain, float attack, float decay)
 {
-    const u64 gid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (u64)a.n_captures * a.agc_max_tiles) return;
-    const uint32_t cap = (uint32_t)(gid / a.agc_max_tiles);
-    const unsigned k = (unsigned)(gid % a.agc_max_tiles);
-    const AcqResult &acq = a.acq[cap];
-    const int L = a.cc.L;
-    const u64 nL = cap_len(a, cap) * L, first = (u64)cap * a.ws_stride * L;
-    const TilePlan plan = agc_plan(a, acq);
-    u64 warm, begin, end;
-    if (!cap_selected(a, cap) || !tile_range(0, nL, plan, k, warm, begin, end)) return;
-    const float *y = a.y + first;
-    float *z = a.z + first;
-    const size_t slot = (size_t)cap * a.agc_max_tiles + k;
-    float gain, start_gain;
-    if (k == 0) gain = acq.norm;                                         // AGC.c:92-96: first call seeds gain with `initial`
-    else        gain = agc_guess(y, warm);
-    agc_tile(y, z, warm, begin, end, gain, start_gain, a.cc.agc_attack, a.cc.agc_decay);
-    a.agc_start[slot] = LoopState2{start_gain, 0.0f};
-    a.agc_end[slot] = LoopState2{gain, 0.0f};
+    const float g0 = gain;
+    AgcFastLaneStep fs; fs.gain = g0; fs.decay = decay; fs.pr.lo = 0.0f; fs.pr.hi = 0.0f;
+    lane_stream<false>(sm, lane, x, z, warm, begin, begin, fs);
+    float gs = fs.gain;
+    lane_stream<true>(sm, lane, x, z, begin, begin, end, fs);
+    float g = fs.gain;
+    const bool redo = (end > warm) && !agc_proof_ok(fs.pr);
+    if (__any_sync(0xffffffffu, redo)) {
+        AgcLaneStep gsx; gsx.st.init = 1; gsx.st.gain = g0; gsx.attack = attack; gsx.decay = decay;
+        const u64 w2 = redo ? warm : 0, b2 = redo ? begin : 0, e2 = redo ? end : 0;
+        lane_stream<false>(sm, lane, x, z, w2, b2, b2, gsx);
+        if (redo) gs = gsx.st.gain;
+        lane_stream<true>(sm, lane, x, z, b2, b2, e2, gsx);
+        if (redo) g = gsx.st.gain;
+    }
+    start_gain = gs; gain = g;
 }
 
-__global__ void __launch_bounds__(128) k_agc_fix_par(const TiledArgs a)
+__global__ void __launch_bounds__(LS_WARPS * 32) k_agc_core(const TiledArgs a)
 {
+    extern __shared__ __align__(128) unsigned char ls_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    LaneStream sm = lane_stream_init(&reinterpret_cast<LaneStreamSmem *>(ls_raw)[wib], lane);
     const u64 gid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid >= (u64)a.n_captures * a.agc_max_tiles) return;
     const uint32_t cap = (uint32_t)(gid / a.agc_max_tiles);
     const unsigned k = (unsigned)(gid % a.agc_max_tiles);
-    if (k == 0) return;
-    const AcqResult &acq = a.acq[cap];
     const int L = a.cc.L;
-    const u64 nL = cap_len(a, cap) * L, first = (u64)cap * a.ws_stride * L;
-    const TilePlan plan = agc_plan(a, acq);
-    u64 warm, begin, end;
-    if (!cap_selected(a, cap) || !tile_range(0, nL, plan, k, warm, begin, end)) return;
-    const size_t slot = (size_t)cap * a.agc_max_tiles + k;
-    const LoopState2 truth = ld_state(&a.agc_end[slot - 1]);
-    if (same_bits(ld_state(&a.agc_start[slot]), truth)) return;
+    bool active = cap < a.n_captures && cap_selected(a, cap);
+    u64 warm = 0, begin = 0, end = 0, first = 0;
+    float gain = 1.0f, start_gain = 1.0f;
+    size_t slot = 0;
+    if (active) {
+        const AcqResult &acq = a.acq[cap];
+        const u64 nL = cap_len(a, cap) * L;
+        first = (u64)cap * a.ws_stride * L;
+        const TilePlan plan = agc_plan(a, acq);
+        active = tile_range(0, nL, plan, k, warm, begin, end);
+        if (active) {
+            slot = (size_t)cap * a.agc_max_tiles + k;
+            if (k == 0) gain = acq.norm;                                 // AGC.c:92-96: first call seeds gain with `initial`
+            else        gain = agc_guess(a.y + first, warm);
+        }
+    }
+    if (!__any_sync(0xffffffffu, active)) return;
+    if (!active) { warm = begin = end = 0; first = 0; }
+    agc_tile_warp(sm, lane, a.y + first, a.z + first, warm, begin, end, gain, start_gain, a.cc.agc_attack, a.cc.agc_decay);
+    if (active) {
+        a.agc_start[slot] = LoopState2{start_gain, 0.0f};
+        a.agc_end[slot] = LoopState2{gain, 0.0f};
+    }
+}
+
+__global__ void __launch_bounds__(LS_WARPS * 32) k_agc_fix_par(const TiledArgs a)
+{
+    extern __shared__ __align__(128) unsigned char ls_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    LaneStream sm = lane_stream_init(&reinterpret_cast<LaneStreamSmem *>(ls_raw)[wib], lane);
+    const u64 gid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t cap = (uint32_t)(gid / a.agc_max_tiles);
+    const unsigned k = (unsigned)(gid % a.agc_max_tiles);
+    const int L = a.cc.L;
+    bool active = cap < a.n_captures && k != 0 && cap_selected(a, cap);
+    u64 warm = 0, begin = 0, end = 0, first = 0;
+    size_t slot = 0;
+    LoopState2 truth{0.f, 0.f};
+    if (active) {
+        const AcqResult &acq = a.acq[cap];
+        const u64 nL = cap_len(a, cap) * L;
+        first = (u64)cap * a.ws_stride * L;
+        const TilePlan plan = agc_plan(a, acq);
+        active = tile_range(0, nL, plan, k, warm, begin, end);
+        if (active) {
+            slot = (size_t)cap * a.agc_max_tiles + k;
+            truth = ld_state(&a.agc_end[slot - 1]);
+            active = !same_bits(ld_state(&a.agc_start[slot]), truth);
+        }
+    }
+    if (!__any_sync(0xffffffffu, active)) return;
+    if (!active) { begin = end = 0; first = 0; }
     float gain = truth.a, sg;
-    agc_tile(a.y + first, a.z + first, begin, begin, end, gain, sg, a.cc.agc_attack, a.cc.agc_decay);
-    st_state(&a.agc_start[slot], truth);
-    st_state(&a.agc_end[slot], LoopState2{gain, 0.0f});
-    atomicAdd(&a.counters[1], 1u);
+    agc_tile_warp(sm, lane, a.y + first, a.z + first, begin, begin, end, gain, sg, a.cc.agc_attack, a.cc.agc_decay);
+    if (active) {
+        st_state(&a.agc_start[slot], truth);
+        st_state(&a.agc_end[slot], LoopState2{gain, 0.0f});
+        atomicAdd(&a.counters[1], 1u);
+    }
 }
 
 __global__ void __launch_bounds__(128) k_agc_fix(const TiledArgs a)
