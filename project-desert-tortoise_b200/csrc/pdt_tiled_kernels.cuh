@@ -73,7 +73,7 @@ PDT_DEV TilePlan agc_plan(const TiledArgs &a, const AcqResult &acq)
     if (w < (double)a.agc_min_tile) w = (double)a.agc_min_tile;
     if (w > 1e15) w = 1e15;
     p.W = ((u64)w + 3) & ~3ull;
-    p.T = (p.W / 2 + 3) & ~3ull; p.T0 = p.W; p.max_tiles = a.agc_max_tiles;
+    p.T = (p.W / 2 + 3) & ~3ull; p.T0 = p.W + p.T; p.max_tiles = a.agc_max_tiles;
     return p;
 }
 
@@ -504,7 +504,7 @@ __global__ void __launch_bounds__(LS_WARPS * 32) k_pll_core(const TiledArgs a)
     const uint32_t cap = (uint32_t)(gid / a.pll.max_tiles);      // a warp = consecutive tiles of ONE capture: equal length,
     const unsigned k = (unsigned)(gid % a.pll.max_tiles);         // same pages
     bool active = cap < a.n_captures && cap_selected(a, cap);
-    u64 warm = 0, begin = 0, end = 0;
+    u64 warm = 0, begin = 0, end = 0, mid = 0, keep = 0;
     PllLaneStep st; st.phase = 0.f; st.freq = 0.f; st.k = TrackConst{0.f, 0.f, 0.f, 0.f};
     const float *sp = a.sp; float *ph = a.ph;
     size_t slot = 0;
@@ -521,18 +521,22 @@ __global__ void __launch_bounds__(LS_WARPS * 32) k_pll_core(const TiledArgs a)
                 u64 a0 = (begin + 3) & ~3ull; if (a0 > end) a0 = end;
                 for (u64 i = begin; i < a0; i++) { ph[i] = st.phase; pll_track_step(st.phase, st.freq, sp[i], st.k); }
                 a.pll_start[slot] = LoopState2{acq.phase, acq.freq};
-                warm = begin = a0;
+                // tile 0 needs no warm-up; it is T0 = W + T long and spends its first W samples (stored) while the other
+                // lanes of the warp warm up, so that both passes below are equally long for all 32 lanes
+                warm = a0; mid = a0 + a.pll.W; if (mid > end) mid = end;
+                keep = warm;
             } else {
                 const LoopState2 g = a.guess[slot];
                 st.phase = g.a; st.freq = g.b;
                 if (st.freq > st.k.max_freq) st.freq = st.k.max_freq; else if (st.freq < st.k.min_freq) st.freq = st.k.min_freq;
+                mid = begin; keep = begin;
             }
         }
     }
-    if (!active) warm = begin = end = 0;
-    lane_stream<false>(sm, lane, sp, ph, warm, begin, begin, st);   // warm-up: nothing is stored
+    if (!active) warm = mid = keep = end = 0;
+    lane_stream<true>(sm, lane, sp, ph, warm, keep, mid, st);        // warm-up (nothing kept) / first W samples of tile 0
     if (active && k != 0) a.pll_start[slot] = LoopState2{st.phase, st.freq};
-    lane_stream<true>(sm, lane, sp, ph, begin, begin, end, st);
+    lane_stream<true>(sm, lane, sp, ph, mid, mid, end, st);
     if (active) a.pll_end[slot] = LoopState2{st.phase, st.freq};
 }
 
@@ -693,27 +697,29 @@ struct AgcLaneStep {
     __device__ __forceinline__ float one(float v) { return agc_step(st, v, attack, decay); }
 };
 
-// [warm-up +] tile of every lane of the warp: the proven fast regime first; lanes whose proof fails (and only they) repeat
-// their range with the general recurrence.  Returns the gain at `begin` in start_gain and the final gain in gain.
-__device__ __forceinline__ void agc_tile_warp(LaneStream &sm, const int lane, const float *x, float *z, u64 warm, u64 begin, u64 end,
-                                              float &gain, float &start_gain, float attack, float decay)
+// Two lock-step passes for every lane of the warp: [s0, mid) of which [keep, mid) is stored (a tile's warm-up: keep == mid;
+// the first W samples of tile 0, which needs no warm-up: keep == s0), then [mid, end) stored.  The proven fast regime
+// first; lanes whose proof fails (and only they) repeat their range with the general recurrence.
+// Returns the gain at `mid` in mid_gain and the final gain in gain.
+__device__ __forceinline__ void agc_tile_warp(LaneStream &sm, const int lane, const float *x, float *z, u64 s0, u64 keep, u64 mid, u64 end,
+                                              float &gain, float &mid_gain, float attack, float decay)
 {
     const float g0 = gain;
     AgcFastLaneStep fs; fs.gain = g0; fs.decay = decay; fs.pr.lo = 0.0f; fs.pr.hi = 0.0f;
-    lane_stream<false>(sm, lane, x, z, warm, begin, begin, fs);
-    float gs = fs.gain;
-    lane_stream<true>(sm, lane, x, z, begin, begin, end, fs);
+    lane_stream<true>(sm, lane, x, z, s0, keep, mid, fs);
+    float gm = fs.gain;
+    lane_stream<true>(sm, lane, x, z, mid, mid, end, fs);
     float g = fs.gain;
-    const bool redo = (end > warm) && !agc_proof_ok(fs.pr);
+    const bool redo = (end > s0) && !agc_proof_ok(fs.pr);
     if (__any_sync(0xffffffffu, redo)) {
         AgcLaneStep gsx; gsx.st.init = 1; gsx.st.gain = g0; gsx.attack = attack; gsx.decay = decay;
-        const u64 w2 = redo ? warm : 0, b2 = redo ? begin : 0, e2 = redo ? end : 0;
-        lane_stream<false>(sm, lane, x, z, w2, b2, b2, gsx);
-        if (redo) gs = gsx.st.gain;
-        lane_stream<true>(sm, lane, x, z, b2, b2, e2, gsx);
+        const u64 a2 = redo ? s0 : 0, k2 = redo ? keep : 0, m2 = redo ? mid : 0, e2 = redo ? end : 0;
+        lane_stream<true>(sm, lane, x, z, a2, k2, m2, gsx);
+        if (redo) gm = gsx.st.gain;
+        lane_stream<true>(sm, lane, x, z, m2, m2, e2, gsx);
         if (redo) g = gsx.st.gain;
     }
-    start_gain = gs; gain = g;
+    mid_gain = gm; gain = g;
 }
 
 __global__ void __launch_bounds__(LS_WARPS * 32) k_agc_core(const TiledArgs a)
@@ -743,7 +749,12 @@ __global__ void __launch_bounds__(LS_WARPS * 32) k_agc_core(const TiledArgs a)
     }
     if (!__any_sync(0xffffffffu, active)) return;
     if (!active) { warm = begin = end = 0; first = 0; }
-    agc_tile_warp(sm, lane, a.y + first, a.z + first, warm, begin, end, gain, start_gain, a.cc.agc_attack, a.cc.agc_decay);
+    u64 keep = begin, mid = begin;
+    if (active && k == 0) {                // tile 0: no warm-up, its first W samples run (stored) beside the others' warm-up
+        const TilePlan plan = agc_plan(a, a.acq[cap]);
+        keep = warm; mid = warm + plan.W; if (mid > end) mid = end;
+    }
+    agc_tile_warp(sm, lane, a.y + first, a.z + first, warm, keep, mid, end, gain, start_gain, a.cc.agc_attack, a.cc.agc_decay);
     if (active) {
         a.agc_start[slot] = LoopState2{start_gain, 0.0f};
         a.agc_end[slot] = LoopState2{gain, 0.0f};
@@ -778,7 +789,7 @@ __global__ void __launch_bounds__(LS_WARPS * 32) k_agc_fix_par(const TiledArgs a
     if (!__any_sync(0xffffffffu, active)) return;
     if (!active) { begin = end = 0; first = 0; }
     float gain = truth.a, sg;
-    agc_tile_warp(sm, lane, a.y + first, a.z + first, begin, begin, end, gain, sg, a.cc.agc_attack, a.cc.agc_decay);
+    agc_tile_warp(sm, lane, a.y + first, a.z + first, begin, begin, begin, end, gain, sg, a.cc.agc_attack, a.cc.agc_decay);
     if (active) {
         st_state(&a.agc_start[slot], truth);
         st_state(&a.agc_end[slot], LoopState2{gain, 0.0f});
