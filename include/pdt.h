@@ -168,6 +168,10 @@ int         pdt_kernel_times(pdt_ctx *ctx, const char **names, float *ms, int ca
  * its stream (capture group 0…, 99 = the slow-capture stream) and its END time in ms since the batch was forked. */
 int         pdt_timeline(pdt_ctx *ctx, const char **names, int *groups, float *end_ms, int cap);
 
+/* Debug: cycle accounting of the acquisition pipeline's second pass, summed over captures since the last reset:
+ * [0] steps, [1] step cycles, [2] core-lane busy, [3] EMA-lane busy, [4] helper busy, [5] decision phase, [6] epochs. */
+int         pdt_debug_acq_prof(uint64_t out[8], int reset);
+
 /* Number of kernels launched by this library since load (bench.py reports it as gpu_launches). */
 uint64_t    pdt_launch_count(void);
 

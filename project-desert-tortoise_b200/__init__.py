@@ -160,7 +160,7 @@ EXPORTED_SYMBOLS = [
     "pdt_version", "pdt_last_error", "pdt_real_size", "pdt_device_count", "pdt_set_device", "pdt_params_default",
     "pdt_create", "pdt_destroy", "pdt_get_params", "pdt_get_taps", "pdt_demod_device", "pdt_demod_host", "pdt_fetch",
     "pdt_result_tables", "pdt_format_frames", "pdt_launch_count", "pdt_synth_poes_device", "pdt_engine",
-    "pdt_tiled_counters", "pdt_set_profiling", "pdt_kernel_times", "pdt_timeline",
+    "pdt_tiled_counters", "pdt_set_profiling", "pdt_kernel_times", "pdt_timeline", "pdt_debug_acq_prof",
     # include/pdt_legacy.h
     "FindSignalAmplitude", "Squelch", "StaticGain", "NormalizingAGC", "NormalizingAGCC", "CarrierTrackPLL", "arctan2",
     "Q_rsqrt", "LowPassFilter", "LowPassFilterInterp", "MakeLPFIR", "GardenerClockRecovery", "MMClockRecovery", "sign",

@@ -346,7 +346,7 @@ static int tiled_run(pdt_ctx *c, const void *d_iq, int pcm16, uint32_t n_capture
     if (n_max == 0) return PDT_OK;
     const int L = c->cc.L;
     const u64 acq_first = c->params.acq_first ? c->params.acq_first : 131072;
-    t.acq_first = (n_max > 2 * acq_first) ? ((acq_first + ACQ_B - 1) / ACQ_B) * ACQ_B : 0;
+    t.acq_first = (n_max > 2 * acq_first) ? acq_first : 0;
     const bool two_pass = t.acq_first != 0;
     PDT_CUDA(cudaMemsetAsync(t.counters, 0, 4 * sizeof(uint32_t), s));
     c->n_marks = 0;
@@ -683,6 +683,20 @@ int pdt_timeline(pdt_ctx *c, const char **names, int *groups, float *end_ms, int
 #else
     return 0;
 #endif
+}
+
+int pdt_debug_acq_prof(uint64_t out[8], int reset)
+{
+#if PDT_USE_FLOATS
+    unsigned long long h[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    PDT_CUDA(cudaDeviceSynchronize());
+    PDT_CUDA(cudaMemcpyFromSymbol(h, tiled::g_acq_prof, sizeof h));
+    for (int i = 0; i < 8; i++) out[i] = h[i];
+    if (reset) { unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0}; PDT_CUDA(cudaMemcpyToSymbol(tiled::g_acq_prof, z, sizeof z)); }
+#else
+    for (int i = 0; i < 8; i++) out[i] = 0;
+#endif
+    return PDT_OK;
 }
 
 int pdt_result_tables(pdt_ctx *c, void **d_stats, void **d_frames, uint32_t *max_frames)

@@ -162,67 +162,83 @@ __global__ void __launch_bounds__(256) k_sp(const TiledArgs a)
 // the booleans are compared; on the first difference the block restarts from that sample with the corrected
 // flag.  The committed trajectory is exactly the serial one.
 // ---------------------------------------------------------------------------------------------------
-constexpr int ACQ_B = 512;
+constexpr int ACQ_B = 256;            // samples per pipeline block
+constexpr int ACQ_RING = 4;           // blocks in flight: core | terms | EMAs | decisions
 constexpr int ACQ_THREADS = 256;
+constexpr int ACQ_HELPERS = ACQ_THREADS - 96;     // warps 3..7: feed-forward terms, decisions, loads, commits
 
 struct __align__(16) AcqSmem {
-    float sp[2][ACQ_B], a[2][ACQ_B], b[2][ACQ_B];               // inputs of the current and the next block
-    float ph[2][ACQ_B + 4], fr[2][ACQ_B + 4], sw[2][ACQ_B + 4]; // state BEFORE each sample (and after the last)
-    float aterm[ACQ_B], lterm[ACQ_B];
-    float avg[ACQ_B + 4], lks[ACQ_B + 4];
-    unsigned char nl[2][ACQ_B], nl_true[ACQ_B];
-    int mism, latch;
+    float sp[ACQ_RING][ACQ_B], a[ACQ_RING][ACQ_B], b[ACQ_RING][ACQ_B];               // inputs
+    float ph[ACQ_RING][ACQ_B + 4], fr[ACQ_RING][ACQ_B + 4], sw[ACQ_RING][ACQ_B + 4]; // state BEFORE each sample ([cnt] = after the block)
+    float aterm[ACQ_RING][ACQ_B], lterm[ACQ_RING][ACQ_B];
+    float avg[ACQ_RING][ACQ_B + 4], lks[ACQ_RING][ACQ_B + 4];                        // [0] = before the block, [i+1] = after sample i
+    int mism[2], latch[2];                                                           // by step parity
+    unsigned char spec[ACQ_B];                                                       // per-sample flag prediction for block 0 of an epoch
 };
 
-// [B]+[C]: serial core over samples [r, m) of one block with the flags nl[].  Inputs are fetched a quad ahead and the
-// three state streams leave as float4: the loop is one dependent chain and must never wait on shared memory.
-PDT_DEV void acq_step(float &phase, float &freq, float &sweep, float sp, bool on, const TrackConst &k)
+// [B]+[C] for one sample with the sweep switched on (CarrierTrackingPLL.c:232-246 taken) or off
+template <bool ON>
+PDT_DEV void acq_step(float &phase, float &freq, float &sweep, float sp, const TrackConst &k)
 {
     pll_track_step(phase, freq, sp, k);
-    const float f2 = freq + sweep;                                              // CarrierTrackingPLL.c:232-246
-    float s2 = (f2 >= 0) ? fabsf(sweep) : -fabsf(sweep);
-    s2 = (f2 <= k.min_freq) ? -sweep : s2;
-    s2 = (f2 >= k.max_freq) ? -sweep : s2;
-    freq = on ? f2 : freq;
-    sweep = on ? s2 : sweep;
+    if (ON) {
+        const float f2 = freq + sweep;
+        float s2 = (f2 >= 0) ? fabsf(sweep) : -fabsf(sweep);
+        s2 = (f2 <= k.min_freq) ? -sweep : s2;
+        s2 = (f2 >= k.max_freq) ? -sweep : s2;
+        freq = f2; sweep = s2;
+    }
 }
 
-PDT_DEV void acq_core(float *__restrict__ ph, float *__restrict__ fr, float *__restrict__ sw, const float *__restrict__ sp,
-                      const unsigned char *__restrict__ nl, int r, int m, const TrackConst &k)
+// serial core over one block (cnt samples) with ONE flag value for the whole block (a flag flip ends the pipeline epoch).
+// Inputs are fetched a quad ahead and the three state streams leave as float4: one dependent chain that never waits
+// on shared memory.  ph/fr/sw[i] = state before sample i, [cnt] = state after the block.
+template <bool ON>
+PDT_DEV void acq_core(float *__restrict__ ph, float *__restrict__ fr, float *__restrict__ sw, const float *__restrict__ sp, int cnt,
+                      float phase, float freq, float sweep, const TrackConst &k)
 {
-    float phase = ph[r], freq = fr[r], sweep = sw[r];
-    int i = r;
-    for (; i < m && (i & 3); i++) { ph[i] = phase; fr[i] = freq; sw[i] = sweep; acq_step(phase, freq, sweep, sp[i], nl[i] != 0, k); }
-    if (i + 4 <= m) {
-        float4 c = ld4(sp + i);
-        uchar4 f = *reinterpret_cast<const uchar4 *>(nl + i);
-        for (; i + 4 <= m; i += 4) {
-            float4 cn = c; uchar4 fn = f;
-            if (i + 8 <= m) { cn = ld4(sp + i + 4); fn = *reinterpret_cast<const uchar4 *>(nl + i + 4); }
+    int i = 0;
+    if (cnt >= 4) {
+        float4 c = ld4(sp);
+        for (; i + 4 <= cnt; i += 4) {
+            float4 cn = c;
+            if (i + 8 <= cnt) cn = ld4(sp + i + 4);
             float4 p, q, w;
-            p.x = phase; q.x = freq; w.x = sweep; acq_step(phase, freq, sweep, c.x, f.x != 0, k);
-            p.y = phase; q.y = freq; w.y = sweep; acq_step(phase, freq, sweep, c.y, f.y != 0, k);
-            p.z = phase; q.z = freq; w.z = sweep; acq_step(phase, freq, sweep, c.z, f.z != 0, k);
-            p.w = phase; q.w = freq; w.w = sweep; acq_step(phase, freq, sweep, c.w, f.w != 0, k);
+            p.x = phase; q.x = freq; w.x = sweep; acq_step<ON>(phase, freq, sweep, c.x, k);
+            p.y = phase; q.y = freq; w.y = sweep; acq_step<ON>(phase, freq, sweep, c.y, k);
+            p.z = phase; q.z = freq; w.z = sweep; acq_step<ON>(phase, freq, sweep, c.z, k);
+            p.w = phase; q.w = freq; w.w = sweep; acq_step<ON>(phase, freq, sweep, c.w, k);
             st4(ph + i, p); st4(fr + i, q); st4(sw + i, w);
-            c = cn; f = fn;
+            c = cn;
         }
     }
-    for (; i < m; i++) { ph[i] = phase; fr[i] = freq; sw[i] = sweep; acq_step(phase, freq, sweep, sp[i], nl[i] != 0, k); }
-    ph[m] = phase; fr[m] = freq; sw[m] = sweep;
+    for (; i < cnt; i++) { ph[i] = phase; fr[i] = freq; sw[i] = sweep; acq_step<ON>(phase, freq, sweep, sp[i], k); }
+    ph[cnt] = phase; fr[cnt] = freq; sw[cnt] = sweep;
 }
 
-// x <- (float)((double)x·c + (double)t[i]) over [r, m): the EMA of CarrierTrackingPLL.c:124 / :220 as one dependent chain
-PDT_DEV void acq_ema(float *__restrict__ out, const float *__restrict__ term, int r, int m, double c)
+// block 0 of an epoch that starts at a flag flip: per-sample flags (the prediction in spec[0, spec_n), `tail` behind it)
+PDT_DEV void acq_core_spec(float *__restrict__ ph, float *__restrict__ fr, float *__restrict__ sw, const float *__restrict__ sp,
+                           const unsigned char *__restrict__ spec, int spec_n, bool tail, int cnt, float phase, float freq, float sweep,
+                           const TrackConst &k)
 {
-    float x = out[r];
-    int i = r;
-    for (; i < m && (i & 3); i++) { x = (float)((double)x * c + (double)term[i]); out[i + 1] = x; }
-    if (i + 4 <= m) {
-        float4 t = ld4(term + i);
-        for (; i + 4 <= m; i += 4) {
+    for (int i = 0; i < cnt; i++) {
+        ph[i] = phase; fr[i] = freq; sw[i] = sweep;
+        const bool on = (i < spec_n) ? (spec[i] != 0) : tail;
+        if (on) acq_step<true>(phase, freq, sweep, sp[i], k); else acq_step<false>(phase, freq, sweep, sp[i], k);
+    }
+    ph[cnt] = phase; fr[cnt] = freq; sw[cnt] = sweep;
+}
+
+// x <- (float)((double)x·c + (double)t[i]) over one block: the EMA of CarrierTrackingPLL.c:124 / :220 as one dependent chain
+PDT_DEV void acq_ema(float *__restrict__ out, const float *__restrict__ term, int cnt, float x, double c)
+{
+    out[0] = x;
+    int i = 0;
+    if (cnt >= 4) {
+        float4 t = ld4(term);
+        for (; i + 4 <= cnt; i += 4) {
             float4 tn = t;
-            if (i + 8 <= m) tn = ld4(term + i + 4);
+            if (i + 8 <= cnt) tn = ld4(term + i + 4);
             const double t0 = (double)t.x, t1 = (double)t.y, t2 = (double)t.z, t3 = (double)t.w;
             x = (float)((double)x * c + t0); out[i + 1] = x;
             x = (float)((double)x * c + t1); out[i + 2] = x;
@@ -231,19 +247,34 @@ PDT_DEV void acq_ema(float *__restrict__ out, const float *__restrict__ term, in
             t = tn;
         }
     }
-    for (; i < m; i++) { x = (float)((double)x * c + (double)term[i]); out[i + 1] = x; }
+    for (; i < cnt; i++) { x = (float)((double)x * c + (double)term[i]); out[i + 1] = x; }
 }
 
 // CarrierTrackingPLL.c:232 — |π/2 - averagePhase| < 0.05 (float fabs of a double difference, compared in double)
 PDT_DEV unsigned char acq_noise_like(float avg) { return (double)fabsf((float)(PDT_PI / 2.0 - (double)avg)) < 0.05; }
 
+// Acquisition as a four-stage software pipeline over ACQ_B-sample blocks, one CTA per capture.  In step s
+//     thread 0            runs the serial core of block s        (sweep flag SPECULATED constant = the epoch's flag)
+//     warps 3..7          compute the feed-forward terms of block s-1 ([A] derotate + |phase|, [D] lock-detector input),
+//                         take the decisions of block s-3, stage the inputs of block s+1
+//     threads 32 and 64   run the two EMA chains of block s-2
+// with two barriers per step, so a step costs what the core chain costs (63-100 cycles per sample, tools/microbench.cu)
+// and nothing else.  The decisions of a block are the per-sample sweep flag (compared with the speculation) and the lock
+// latch.  A wrong flag at sample m ends the epoch: samples before m are committed, and the pipeline restarts at m from
+// the exact state it had there with the flag flipped — the committed trajectory is exactly the serial one.
+//
 // pass 0: samples [0, min(n, acq_first)) of every capture.  A capture whose loop has not latched by then is marked
 //         `slow` and its loop state is saved;
 // pass 1: the slow captures only, from where pass 0 stopped to the end of the capture.
 // (The two passes let the host run the rest of the chain for the quickly-locking majority while the few captures
 // that lock late, or never, are still in their serial acquisition.)
+// cycle accounting of the acquisition pipeline (pass 1 only; read with pdt_debug_acq_prof): [0] steps, [1] step cycles,
+// [2] core busy, [3] EMA busy, [4] helper busy in the work phase, [5] decision phase (helper 0), [6] epochs
+__device__ unsigned long long g_acq_prof[8];
+
 __global__ void __launch_bounds__(ACQ_THREADS) k_acquire(const TiledArgs a, const int pass)
 {
+    unsigned long long pf_steps = 0, pf_cyc = 0, pf_busy = 0, pf_dec = 0, pf_epochs = 0;
     __shared__ AcqSmem s;
     const uint32_t cap = blockIdx.x;
     const int tid = threadIdx.x;
@@ -258,6 +289,7 @@ __global__ void __launch_bounds__(ACQ_THREADS) k_acquire(const TiledArgs a, cons
     pll_begin(ps, pp);
     TrackConst kacq; kacq.alpha = ps.alpha; kacq.beta = ps.beta; kacq.max_freq = ps.max_freq; kacq.min_freq = ps.min_freq;
     const float avg_alpha = 0.00005f;
+    const double c_avg = 1.0 - avg_alpha, c_lks = 1.0 - pp.lock_alpha;
     uint32_t restarts = 0;
 
     u64 i_begin = 0, i_stop = n;
@@ -268,16 +300,6 @@ __global__ void __launch_bounds__(ACQ_THREADS) k_acquire(const TiledArgs a, cons
         i_begin = res->resume_at;
         ps.phase = res->phase; ps.freq = res->freq; ps.sweep = res->sweep; ps.avg_phase = res->avg_phase; ps.locksig = res->locksig;
     }
-
-    auto load_inputs = [&](int buf, u64 i0) {
-        const int m = (int)((i_stop - i0 < ACQ_B) ? (i_stop - i0) : ACQ_B);
-        for (int i = tid; i < m; i += ACQ_THREADS) {
-            float p, q;
-            load_iq1(a.iq, a.pcm16, first + i0 + i, p, q);
-            s.a[buf][i] = p; s.b[buf][i] = q; s.sp[buf][i] = a.sp[wfirst + i0 + i];
-        }
-    };
-
     if (n == 0) {
         if (tid == 0) {
             res->locked = 0; res->slow = 0; res->resume_at = 0; res->lock_sample = 0; res->track_begin = 0;
@@ -287,112 +309,161 @@ __global__ void __launch_bounds__(ACQ_THREADS) k_acquire(const TiledArgs a, cons
         }
         return;
     }
-    load_inputs(0, i_begin);
-    {
-        const int m0 = (int)(i_stop - i_begin < ACQ_B ? i_stop - i_begin : ACQ_B);
-        const unsigned char f0 = acq_noise_like(ps.avg_phase);              // true for the initial avg_phase = π/2
-        for (int i = tid; i < m0; i += ACQ_THREADS) s.nl[0][i] = f0;
-        if (tid == 0) {
-            s.ph[0][0] = ps.phase; s.fr[0][0] = ps.freq; s.sw[0][0] = ps.sweep; s.avg[0] = ps.avg_phase; s.lks[0] = ps.locksig;
-        }
-        __syncthreads();
-        if (tid == 0) acq_core(s.ph[0], s.fr[0], s.sw[0], s.sp[0], s.nl[0], 0, m0, kacq);
-        __syncthreads();
-    }
 
-    int r = 0;
-    bool next_loaded = false;
-    for (u64 i0 = i_begin; i0 < i_stop;) {
-        const int cur = (int)(((i0 - i_begin) / ACQ_B) & 1), nxt = cur ^ 1;
-        const int m = (int)((i_stop - i0 < ACQ_B) ? (i_stop - i0) : ACQ_B);
-        const bool has_next = i0 + ACQ_B < i_stop;
-        const int m_next = has_next ? (int)((i_stop - i0 - ACQ_B < ACQ_B) ? (i_stop - i0 - ACQ_B) : ACQ_B) : 0;
-        // ---- P1: [A],[D] feed-forward parts of block `cur` from r; stage the next block's inputs and flag guess ----
-        for (int i = r + tid; i < m; i += ACQ_THREADS) {
-            float ti, tr;
-            sincos_exact(s.ph[cur][i], ti, tr);                                     // :106-107
-            const float p = s.a[cur][i], q = s.b[cur][i], nti = -ti;
-            const float mre = p * tr - q * nti, mim = p * nti + q * tr;            // :110
-            s.aterm[i] = avg_alpha * fabsf(arctan2_approx(mim, mre));               // :117,:124
-            const float mag2 = p * p + q * q;                                       // :193-220
-            const float inv = q_rsqrt(mag2);
-            const float nre = p * inv, nim = q * inv;
-            s.lterm[i] = pp.lock_alpha * (nre * tr + nim * ti);
+    // epoch state (uniform across the CTA): origin, loop state at the origin, speculated flag
+    u64 x0 = i_begin;
+    float e_phase = ps.phase, e_freq = ps.freq, e_sweep = ps.sweep, e_avg = ps.avg_phase, e_lks = ps.locksig;
+    bool flag = acq_noise_like(e_avg) != 0;                  // true for the initial avg_phase = π/2
+    int spec_n = 0;                                          // samples of the epoch's block 0 that carry a per-sample prediction
+    const int hid = tid - 96;                                // helper index (warps 3..7), < 0 for the three serial warps
+
+    // (A ramp of small blocks after a flag flip was tried and lost: a step has ~4k cycles of fixed cost, profiles/README.md r01f.)
+    auto block_off = [&](long long j) -> u64 { return (u64)j * (u64)ACQ_B; };
+    auto block_cnt = [&](long long j) -> int {               // samples in block j of the current epoch (0 = does not exist)
+        if (j < 0) return 0;
+        const u64 b0 = x0 + block_off(j);
+        if (b0 >= i_stop) return 0;
+        return (int)((i_stop - b0 < (u64)ACQ_B) ? (i_stop - b0) : (u64)ACQ_B);
+    };
+    auto load_inputs = [&](long long j) {                    // helpers only
+        const int cnt = block_cnt(j);
+        const int slot = (int)(j % ACQ_RING);
+        const u64 b0 = x0 + block_off(j);
+        for (int i = hid; i < cnt; i += ACQ_HELPERS) {
+            float p, q;
+            load_iq1(a.iq, a.pcm16, first + b0 + i, p, q);
+            s.a[slot][i] = p; s.b[slot][i] = q; s.sp[slot][i] = a.sp[wfirst + b0 + i];
         }
-        if (has_next) {
-            if (!next_loaded) load_inputs(nxt, i0 + ACQ_B);
-            const unsigned char f = s.nl[cur][m - 1];
-            for (int i = tid; i < m_next; i += ACQ_THREADS) s.nl[nxt][i] = f;
-        }
-        next_loaded = true;
-        if (tid == 0) { s.mism = m; s.latch = m; }
+    };
+
+    for (;;) {                                               // one iteration = one epoch
+        pf_epochs++;
+        if (hid >= 0) load_inputs(0);
         __syncthreads();
-        // ---- S: the two EMAs of block `cur` (pure dependent chains), and SPECULATIVELY the core of the next block ----
-        if (tid == 0) {
-            if (has_next) {
-                s.ph[nxt][0] = s.ph[cur][m]; s.fr[nxt][0] = s.fr[cur][m]; s.sw[nxt][0] = s.sw[cur][m];
-                acq_core(s.ph[nxt], s.fr[nxt], s.sw[nxt], s.sp[nxt], s.nl[nxt], 0, m_next, kacq);
-            }
-        } else if (tid == 32) {
-            acq_ema(s.avg, s.aterm, r, m, 1.0 - avg_alpha);                                        // :124
-        } else if (tid == 64) {
-            acq_ema(s.lks, s.lterm, r, m, 1.0 - pp.lock_alpha);                                    // :220
-        }
-        __syncthreads();
-        // ---- P2: the decisions taken from the EMAs, all samples at once ---------------------------------------------
-        for (int i = r + tid; i < m; i += ACQ_THREADS) {
-            const unsigned char t = acq_noise_like(s.avg[i + 1]);                                  // :232
-            s.nl_true[i] = t;
-            if (t != s.nl[cur][i]) atomicMin(&s.mism, i);
-            if (s.lks[i + 1] > pp.lock_thresh) atomicMin(&s.latch, i);                             // :266
-        }
-        __syncthreads();
-        const int mism = s.mism, latch = s.latch;
-        if (latch < mism) {
-            // every flag up to and including the latch sample was right: commit and leave acquisition
-            const int cnt = latch + 1;
-            for (int i = tid; i < cnt; i += ACQ_THREADS) ph_out[i0 + i] = s.ph[cur][i];
+        bool epoch_done = false;
+        for (long long st = 0; !epoch_done; st++) {
+            const int c_core = block_cnt(st), c_term = block_cnt(st - 1), c_ema = block_cnt(st - 2), c_dec = block_cnt(st - 3);
+            if (c_core == 0 && c_term == 0 && c_ema == 0 && c_dec == 0) break;      // pipeline drained: nothing left below i_stop
+            const long long t_step = clock64();
             if (tid == 0) {
-                const float freq = s.fr[cur][cnt];
-                res->locked = 1; res->lock_sample = i0 + latch; res->track_begin = i0 + cnt; res->resume_at = n;
-                if (pass == 0) res->slow = 0;
-                res->phase = s.ph[cur][cnt]; res->freq = freq; res->sweep = s.sw[cur][cnt];
-                res->avg_phase = s.avg[cnt]; res->locksig = s.lks[cnt];
-                res->lock_freq_hz = freq * pp.Fs / (2.0 * PDT_PI);                                  // :269
-                const float bw = pp.bw_track, damp = ps.damp;                                       // :272-273
-                res->alpha = (4.0 * damp * bw) / (1.0 + 2.0 * damp * bw + bw * bw);
-                res->beta  = (4.0 * bw * bw) / (1.0 + 2.0 * damp * bw + bw * bw);
-                if (restarts) atomicAdd(&a.counters[2], restarts);
+                if (c_core) {
+                    const int slot = (int)(st % ACQ_RING), prev = (int)((st + ACQ_RING - 1) % ACQ_RING);
+                    float p = e_phase, f = e_freq, w = e_sweep;
+                    if (st > 0) { const int pc = block_cnt(st - 1); p = s.ph[prev][pc]; f = s.fr[prev][pc]; w = s.sw[prev][pc]; }
+                    const int so = (int)block_off(st);              // the per-sample prediction covers the first spec_n samples of the epoch
+                    if (so < spec_n) acq_core_spec(s.ph[slot], s.fr[slot], s.sw[slot], s.sp[slot], s.spec + so, spec_n - so, flag, c_core, p, f, w, kacq);
+                    else if (flag) acq_core<true>(s.ph[slot], s.fr[slot], s.sw[slot], s.sp[slot], c_core, p, f, w, kacq);
+                    else           acq_core<false>(s.ph[slot], s.fr[slot], s.sw[slot], s.sp[slot], c_core, p, f, w, kacq);
+                }
+                s.mism[st & 1] = ACQ_B + 1; s.latch[st & 1] = ACQ_B + 1;
+            } else if (tid == 32 || tid == 64) {
+                if (c_ema) {
+                    const int slot = (int)((st - 2) % ACQ_RING), prev = (int)((st - 3 + ACQ_RING) % ACQ_RING);
+                    const int pc = block_cnt(st - 3);
+                    if (tid == 32) acq_ema(s.avg[slot], s.aterm[slot], c_ema, (st == 2) ? e_avg : s.avg[prev][pc], c_avg);     // :124
+                    else           acq_ema(s.lks[slot], s.lterm[slot], c_ema, (st == 2) ? e_lks : s.lks[prev][pc], c_lks);     // :220
+                }
+            } else if (hid >= 0) {
+                if (c_term) {                                                        // [A],[D] feed-forward parts of block st-1
+                    const int slot = (int)((st - 1) % ACQ_RING);
+                    for (int i = hid; i < c_term; i += ACQ_HELPERS) {
+                        float ti, tr;
+                        sincos_exact(s.ph[slot][i], ti, tr);                                    // :106-107
+                        const float p = s.a[slot][i], q = s.b[slot][i], nti = -ti;
+                        const float mre = p * tr - q * nti, mim = p * nti + q * tr;            // :110
+                        s.aterm[slot][i] = avg_alpha * fabsf(arctan2_approx(mim, mre));         // :117,:124
+                        const float mag2 = p * p + q * q;                                       // :193-220
+                        const float inv = q_rsqrt(mag2);
+                        const float nre = p * inv, nim = q * inv;
+                        s.lterm[slot][i] = pp.lock_alpha * (nre * tr + nim * ti);
+                    }
+                }
+                if (block_cnt(st + 1)) load_inputs(st + 1);
             }
-            return;
-        }
-        if (mism < m) {
-            // a speculated flag was wrong at sample `mism`: redo the core of THIS block from there (the speculative
-            // next block is discarded).  New speculation for the rest of the block: the flags the EMA just produced.
-            // They were computed from phases that are about to change, but avg_phase moves by < 2e-4 per sample
-            // whatever the phase is, so they are almost always right (a constant guess dithers near the threshold).
-            for (int i = mism + tid; i < m; i += ACQ_THREADS) s.nl[cur][i] = s.nl_true[i];
+            pf_busy += (unsigned long long)(clock64() - t_step);
             __syncthreads();
-            if (tid == 0) { acq_core(s.ph[cur], s.fr[cur], s.sw[cur], s.sp[cur], s.nl[cur], mism, m, kacq); restarts++; }
-            r = mism;
+            const long long t_dec = clock64();
+            // decisions of block st-3 (its EMAs were finished in the previous step)
+            if (c_dec && hid >= 0) {
+                const int slot = (int)((st - 3) % ACQ_RING);
+                for (int i = hid; i < c_dec; i += ACQ_HELPERS) {
+                    const int so = (int)block_off(st - 3) + i;
+                    const bool want = (so < spec_n) ? (s.spec[so] != 0) : flag;
+                    if ((acq_noise_like(s.avg[slot][i + 1]) != 0) != want) atomicMin(&s.mism[st & 1], i);      // :232
+                    if (s.lks[slot][i + 1] > pp.lock_thresh) atomicMin(&s.latch[st & 1], i);                   // :266
+                }
+            }
             __syncthreads();
-            continue;
+            pf_dec += (unsigned long long)(clock64() - t_dec);
+            pf_steps++;
+            auto pf_flush = [&]() {
+                pf_cyc += (unsigned long long)(clock64() - t_step);
+                if (pass == 1) {
+                    if (tid == 0)  { atomicAdd(&g_acq_prof[0], pf_steps); atomicAdd(&g_acq_prof[1], pf_cyc); atomicAdd(&g_acq_prof[2], pf_busy); atomicAdd(&g_acq_prof[6], pf_epochs); }
+                    if (tid == 32) atomicAdd(&g_acq_prof[3], pf_busy);
+                    if (tid == 96) { atomicAdd(&g_acq_prof[4], pf_busy); atomicAdd(&g_acq_prof[5], pf_dec); }
+                }
+            };
+            if (c_dec) {
+                const int slot = (int)((st - 3) % ACQ_RING);
+                const u64 b0 = x0 + block_off(st - 3);
+                const int mism = s.mism[st & 1] < c_dec ? s.mism[st & 1] : c_dec, latch = s.latch[st & 1] < c_dec ? s.latch[st & 1] : c_dec;
+                if (latch < c_dec && latch < mism) {
+                    // every flag up to and including the latch sample was right: commit and leave acquisition
+                    const int cnt = latch + 1;
+                    for (int i = tid; i < cnt; i += ACQ_THREADS) ph_out[b0 + i] = s.ph[slot][i];
+                    if (tid == 0) {
+                        const float freq = s.fr[slot][cnt];
+                        res->locked = 1; res->lock_sample = b0 + latch; res->track_begin = b0 + cnt; res->resume_at = n;
+                        if (pass == 0) res->slow = 0;
+                        res->phase = s.ph[slot][cnt]; res->freq = freq; res->sweep = s.sw[slot][cnt];
+                        res->avg_phase = s.avg[slot][cnt]; res->locksig = s.lks[slot][cnt];
+                        res->lock_freq_hz = freq * pp.Fs / (2.0 * PDT_PI);                                  // :269
+                        const float bw = pp.bw_track, damp = ps.damp;                                       // :272-273
+                        res->alpha = (4.0 * damp * bw) / (1.0 + 2.0 * damp * bw + bw * bw);
+                        res->beta  = (4.0 * bw * bw) / (1.0 + 2.0 * damp * bw + bw * bw);
+                        if (restarts) atomicAdd(&a.counters[2], restarts);
+                    }
+                    pf_flush();
+                    return;
+                }
+                const int good = mism;                                   // samples of the block whose speculated flag was right
+                for (int i = tid; i < good; i += ACQ_THREADS) ph_out[b0 + i] = s.ph[slot][i];
+                if (mism < c_dec) {
+                    // the flag flips at sample `mism`: new epoch there, from the exact state in front of that sample
+                    // The flags the EMA just produced for the rest of this block become the per-sample prediction of the new
+                    // epoch's block 0: they come from phases that are about to change, but avg_phase moves by < 2e-4 per
+                    // sample whatever the phase is, so a burst of flips around a threshold crossing is predicted in one go.
+                    const float np_ = s.ph[slot][mism], nf = s.fr[slot][mism], nw = s.sw[slot][mism];
+                    const float na = s.avg[slot][mism], nl_ = s.lks[slot][mism];
+                    const int nspec = c_dec - mism;
+                    unsigned char mine[2] = {0, 0};
+                    for (int i = tid, q = 0; i < nspec; i += ACQ_THREADS, q++) mine[q] = acq_noise_like(s.avg[slot][mism + i + 1]);
+                    const bool tail = acq_noise_like(s.avg[slot][c_dec]) != 0;
+                    __syncthreads();
+                    for (int i = tid, q = 0; i < nspec; i += ACQ_THREADS, q++) s.spec[i] = mine[q];
+                    x0 = b0 + (u64)mism; e_phase = np_; e_freq = nf; e_sweep = nw; e_avg = na; e_lks = nl_;
+                    spec_n = nspec; flag = tail; restarts++;
+                    epoch_done = true;
+                } else if (b0 + (u64)c_dec >= i_stop) {
+                    // reached the end of this pass without a latch
+                    if (tid == 0) {
+                        const bool done = (i_stop == n);
+                        res->locked = 0; res->lock_sample = 0; res->track_begin = n;
+                        res->resume_at = i_stop;
+                        if (pass == 0) res->slow = done ? 0 : 1;
+                        res->phase = s.ph[slot][c_dec]; res->freq = s.fr[slot][c_dec]; res->sweep = s.sw[slot][c_dec];
+                        res->avg_phase = s.avg[slot][c_dec]; res->locksig = s.lks[slot][c_dec];
+                        res->lock_freq_hz = 0; res->alpha = kacq.alpha; res->beta = kacq.beta;
+                        if (restarts) atomicAdd(&a.counters[2], restarts);
+                    }
+                    pf_flush();
+                    return;
+                }
+            }
+            pf_cyc += (unsigned long long)(clock64() - t_step);
         }
-        // block consistent: commit it; the speculative core of the next block used the right start state and flag
-        for (int i = tid; i < m; i += ACQ_THREADS) ph_out[i0 + i] = s.ph[cur][i];
-        if (tid == 0) { s.avg[0] = s.avg[m]; s.lks[0] = s.lks[m]; }
-        if (!has_next && tid == 0) {
-            const bool done = (i_stop == n);
-            res->locked = 0; res->lock_sample = 0; res->track_begin = n;
-            res->resume_at = i_stop;
-            if (pass == 0) res->slow = done ? 0 : 1;
-            res->phase = s.ph[cur][m]; res->freq = s.fr[cur][m]; res->sweep = s.sw[cur][m];
-            res->avg_phase = s.avg[m]; res->locksig = s.lks[m];
-            res->lock_freq_hz = 0; res->alpha = kacq.alpha; res->beta = kacq.beta;
-            if (restarts) atomicAdd(&a.counters[2], restarts);
-        }
-        i0 += ACQ_B; r = 0; next_loaded = false;
-        __syncthreads();
+        if (!epoch_done) return;        // (not reached: the last block always returns above)
     }
 }
 

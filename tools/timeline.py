@@ -21,10 +21,18 @@ d = pdt.Demod("f32", pdt.default_params("f32", pdt.PDT_MODE_POES, FS), C_, n, in
 for _ in range(3):
     d.demod_device(d_iq.data_ptr(), C_, n, pcm16=a.pcm16)
 torch.cuda.synchronize()
+import ctypes
+prof = (ctypes.c_uint64 * 8)()
+L.pdt_debug_acq_prof(prof, 1)
 d.set_profiling(2)
 d.demod_device(d_iq.data_ptr(), C_, n, pcm16=a.pcm16)
 torch.cuda.synchronize()
+L.pdt_debug_acq_prof(prof, 0)
+p = list(prof)
+if p[0]:
+    print('acq pass-1 pipeline: steps %d epochs %d cycles/step %.0f core busy %.0f ema busy %.0f helper busy %.0f decision phase %.0f' % (p[0], p[6], p[1]/p[0], p[2]/p[0], p[3]/p[0], p[4]/p[0], p[5]/p[0]))
 tl = d.timeline()
+print('speculation counters (pll re-run, agc re-run, acq restarts, pll tiles):', d.tiled_counters())
 by = {}
 for name, g, t in tl:
     by.setdefault(g, []).append((name, t))
