@@ -22,23 +22,20 @@ namespace tiled {
 
 constexpr int LS_R  = 64;            // samples per lane per stage (256-byte rows)
 constexpr int LS_RS = LS_R + 4;      // row stride in floats: 272 B, 16-byte aligned, bank-conflict-free for 128-bit accesses
-constexpr int LS_NIN = 2;            // input stages (the next piece is requested while the current one is consumed)
+constexpr int LS_NIN = 3;            // input stages: pieces are requested two rounds ahead (a round of the fast AGC step is shorter than a DRAM round trip)
 
 struct __align__(128) LaneStreamSmem {
     float in[LS_NIN][32][LS_RS];
     float out[32][LS_RS];
-    unsigned long long src[32], dst[32];     // per lane: global byte address of its stream's first sample (input / output)
-    unsigned n[32], sf[32];                  // per lane: samples in the stream, first sample whose output is kept
 };
 
 struct LaneStream { LaneStreamSmem *sm; };
 
 __device__ __forceinline__ uint32_t ls_smem(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void ls_cp16(void *dst_smem, unsigned long long src_gmem)
+__device__ __forceinline__ void ls_cp16(uint32_t dst_smem, const void *src_gmem)
 {
-    // no "memory" clobber: the copy is ordered against its consumers by ls_wait + __syncwarp (both compiler barriers), and
-    // without it the row metadata loads of the 16 requests of a round can be scheduled ahead of the requests
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ls_smem(dst_smem)), "l"(src_gmem));
+    // no "memory" clobber: the copy is ordered against its consumers by ls_wait + __syncwarp (both compiler barriers)
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src_gmem));
 }
 __device__ __forceinline__ void ls_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -51,10 +48,17 @@ __device__ __forceinline__ LaneStream lane_stream_init(LaneStreamSmem *sm, const
     return h;
 }
 
+__device__ __forceinline__ u64 ls_shfl64(u64 v, int src)
+{
+    const unsigned lo = __shfl_sync(0xffffffffu, (unsigned)v, src), hi = __shfl_sync(0xffffffffu, (unsigned)(v >> 32), src);
+    return ((u64)hi << 32) | lo;
+}
+
 // Run `step` over in[s0, s1) for this lane; outputs are written to out[sb, s1) (s0 <= sb <= s1: [s0, sb) is a warm-up
-// whose outputs are discarded).  s0 and sb must be multiples of 4 (16-byte aligned pieces); s1 may be anything — the
-// last piece is then loaded/stored rounded up to 4 samples, inside the padding every workspace row has.
-// A lane with nothing to do passes s0 == s1.  All 32 lanes of the warp must call this together; s1 - s0 < 2^32.
+// whose outputs are discarded).  `in` / `out` are the SAME for all 32 lanes (the workspace arrays); s0, sb, s1 index them.
+// s0 and sb must be multiples of 4 (16-byte aligned pieces); s1 may be anything — the last piece is then loaded/stored
+// rounded up to 4 samples, inside the padding every workspace row has.  A lane with nothing to do passes s0 == s1.
+// All 32 lanes of the warp must call this together; s1 - s0 < 2^32.
 //   Step:  void quad(const float4 &v, float4 &o);   float one(float v);
 // STORE = false: a pure warm-up (sb == s1), no output row is written at all.
 template <bool STORE, class Step>
@@ -68,22 +72,27 @@ __device__ __forceinline__ void lane_stream(LaneStream &h, const int lane, const
 #pragma unroll
     for (int o = 16; o; o >>= 1) { const unsigned t = __shfl_xor_sync(0xffffffffu, maxch, o); maxch = t > maxch ? t : maxch; }
     if (maxch == 0) return;
+    // this lane's part in the cooperative row copies: 16 lanes cover one row, request i of a round covers rows 2i and 2i+1.
+    // The geometry of "its" 16 rows is fetched once per call (registers), so a round's 16 requests are pure arithmetic.
+    const int half = lane >> 4, piece = (lane & 15) * 4;
+    u64 r_off[16]; unsigned r_n[16], r_sf[16];
+    const unsigned my_sf = (unsigned)(sb - s0);
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        r_off[i] = ls_shfl64(s0, 2 * i + half) + (u64)piece;
+        r_n[i] = __shfl_sync(0xffffffffu, len, 2 * i + half);
+        r_sf[i] = __shfl_sync(0xffffffffu, my_sf, 2 * i + half);
+    }
+    const uint32_t in_u32 = ls_smem(&sm.in[0][0][0]) + 4u * (unsigned)(half * LS_RS + piece);
     __syncwarp();
-    sm.src[lane] = (unsigned long long)(in + s0); sm.dst[lane] = (unsigned long long)(out + s0);
-    sm.n[lane] = len; sm.sf[lane] = (unsigned)(sb - s0);
-    __syncwarp();
-    const int half = lane >> 4, piece = (lane & 15) * 4;       // this lane's part in the cooperative row copies
 
     auto issue = [&](unsigned c) {
         if (c < maxch) {
-            const int st = (int)(c % LS_NIN);
             const unsigned off = c * LS_R + (unsigned)piece;
-            unsigned nr[16]; unsigned long long sr[16];
-#pragma unroll
-            for (int i = 0; i < 16; i++) { nr[i] = sm.n[2 * i + half]; sr[i] = sm.src[2 * i + half]; }
+            const uint32_t dst = in_u32 + 4u * (unsigned)((c % LS_NIN) * 32 * LS_RS);
 #pragma unroll
             for (int i = 0; i < 16; i++)
-                if (off < nr[i]) ls_cp16(&sm.in[st][2 * i + half][piece], sr[i] + 4ull * off);
+                if (off < r_n[i]) ls_cp16(dst + 4u * (unsigned)(2 * i * LS_RS), in + r_off[i] + (u64)c * LS_R);
         }
         ls_commit();
     };
@@ -120,13 +129,10 @@ __device__ __forceinline__ void lane_stream(LaneStream &h, const int lane, const
         if (STORE) {
             __syncwarp();
             const unsigned off = c * LS_R + (unsigned)piece;
-            unsigned nr[16], fr[16];
-#pragma unroll
-            for (int i = 0; i < 16; i++) { nr[i] = sm.n[2 * i + half]; fr[i] = sm.sf[2 * i + half]; }
 #pragma unroll
             for (int i = 0; i < 16; i++)
-                if (off < nr[i] && off >= fr[i])
-                    *reinterpret_cast<float4 *>(sm.dst[2 * i + half] + 4ull * off) = ld4(&sm.out[2 * i + half][piece]);
+                if (off < r_n[i] && off >= r_sf[i])
+                    *reinterpret_cast<float4 *>(out + r_off[i] + (u64)c * LS_R) = ld4(&sm.out[2 * i + half][piece]);
         }
     }
     ls_wait<0>();

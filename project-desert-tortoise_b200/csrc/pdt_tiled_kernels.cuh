@@ -605,9 +605,10 @@ __global__ void __launch_bounds__(LS_WARPS * 32) k_pll_core(const TiledArgs a)
         }
     }
     if (!active) warm = mid = keep = end = 0;
-    lane_stream<true>(sm, lane, sp, ph, warm, keep, mid, st);        // warm-up (nothing kept) / first W samples of tile 0
+    const u64 cb = active ? (u64)cap * a.ws_stride : 0;              // lane streams index the whole workspace arrays
+    lane_stream<true>(sm, lane, a.sp, a.ph, cb + warm, cb + keep, cb + mid, st);   // warm-up (nothing kept) / first W samples of tile 0
     if (active && k != 0) a.pll_start[slot] = LoopState2{st.phase, st.freq};
-    lane_stream<true>(sm, lane, sp, ph, mid, mid, end, st);
+    lane_stream<true>(sm, lane, a.sp, a.ph, cb + mid, cb + mid, cb + end, st);
     if (active) a.pll_end[slot] = LoopState2{st.phase, st.freq};
 }
 
@@ -655,7 +656,7 @@ __global__ void __launch_bounds__(LS_WARPS * 32) k_pll_fix_par(const TiledArgs a
     if (!__any_sync(0xffffffffu, active)) return;
     if (!active) begin = end = 0;
     const u64 off = (u64)(active ? cap : 0) * a.ws_stride;
-    lane_stream<true>(sm, lane, a.sp + off, a.ph + off, begin, begin, end, st);
+    lane_stream<true>(sm, lane, a.sp, a.ph, off + begin, off + begin, off + end, st);
     if (active) {
         st_state(&a.pll_start[slot], truth);
         st_state(&a.pll_end[slot], LoopState2{st.phase, st.freq});
@@ -825,7 +826,7 @@ __global__ void __launch_bounds__(LS_WARPS * 32) k_agc_core(const TiledArgs a)
         const TilePlan plan = agc_plan(a, a.acq[cap]);
         keep = warm; mid = warm + plan.W; if (mid > end) mid = end;
     }
-    agc_tile_warp(sm, lane, a.y + first, a.z + first, warm, keep, mid, end, gain, start_gain, a.cc.agc_attack, a.cc.agc_decay);
+    agc_tile_warp(sm, lane, a.y, a.z, first + warm, first + keep, first + mid, first + end, gain, start_gain, a.cc.agc_attack, a.cc.agc_decay);
     if (active) {
         a.agc_start[slot] = LoopState2{start_gain, 0.0f};
         a.agc_end[slot] = LoopState2{gain, 0.0f};
@@ -860,7 +861,7 @@ __global__ void __launch_bounds__(LS_WARPS * 32) k_agc_fix_par(const TiledArgs a
     if (!__any_sync(0xffffffffu, active)) return;
     if (!active) { begin = end = 0; first = 0; }
     float gain = truth.a, sg;
-    agc_tile_warp(sm, lane, a.y + first, a.z + first, begin, begin, begin, end, gain, sg, a.cc.agc_attack, a.cc.agc_decay);
+    agc_tile_warp(sm, lane, a.y, a.z, first + begin, first + begin, first + begin, first + end, gain, sg, a.cc.agc_attack, a.cc.agc_decay);
     if (active) {
         st_state(&a.agc_start[slot], truth);
         st_state(&a.agc_end[slot], LoopState2{gain, 0.0f});
