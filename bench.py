@@ -29,6 +29,10 @@ import time
 
 import numpy as np
 
+# Each batch in flight uses up to 7 internal streams; beyond the default 8 hardware work queues streams alias and a launch
+# waiting behind a long kernel blocks unrelated streams.  Must be set before CUDA initialises.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for _p in (ROOT, os.path.join(ROOT, "oracle")):
     if _p not in sys.path:
@@ -192,6 +196,10 @@ def main():
     ap.add_argument("--pcm16", action="store_true", help="feed int16 PCM (4 B/sample) instead of cf32")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-single", action="store_true")
+    ap.add_argument("--inflight", type=int, default=3,
+                    help="batches in flight: consecutive steps alternate between this many contexts/streams, so the serial "
+                         "acquisition tail of one batch overlaps the bulk kernels of the next (1 = strictly one batch at a time)")
     ap.add_argument("--cpu-captures", type=int, default=0)
     ap.add_argument("--ref-captures", type=int, default=0)
     ap.add_argument("--ref-samples", type=int, default=1_000_000)
@@ -203,6 +211,7 @@ def main():
     import torch
     import torch.distributed as dist
     pdt = importlib.import_module("project-desert-tortoise_b200")
+    pdist = importlib.import_module("project-desert-tortoise_b200.dist")
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -226,16 +235,38 @@ def main():
     max_frames = int(n / FS * 10) + 8
     d = pdt.Demod("f32", params, C_, n, max_frames)
     ds, df, _ = d.result_tables()
-    frames_t = torch.as_tensor(_Raw(df, C_ * max_frames * 120), device="cuda")
-    gathered = torch.empty(world * frames_t.numel(), dtype=torch.uint8, device="cuda") if world > 1 else None
+    frames_t = torch.as_tensor(_Raw(df, C_ * max_frames * 120), device="cuda").view(C_, max_frames * 120)
+    # batches in flight: context k (own workspaces, own internal streams) on side stream k; joined to the main stream at the end
+    inflight = max(1, args.inflight)
+    ctxs = [d] + [pdt.Demod("f32", params, C_, n, max_frames) for _ in range(inflight - 1)]
+    tables = [frames_t] + [torch.as_tensor(_Raw(c.result_tables()[1], C_ * max_frames * 120), device="cuda").view(C_, max_frames * 120)
+                           for c in ctxs[1:]]
+    side = [torch.cuda.Stream() for _ in range(inflight)] if inflight > 1 else []
+    step_no = [0]
 
     def step():
-        d.demod_device(d_iq.data_ptr(), C_, n, pcm16=args.pcm16, stream=stream)
-        if world > 1:   # the only exchange on this path: gather the decoded minor frames (≤ 104 B x 10 frames/s/capture)
-            dist.all_gather_into_tensor(gathered, frames_t)
+        k = step_no[0] % inflight
+        step_no[0] += 1
+        if inflight == 1:
+            d.demod_device(d_iq.data_ptr(), C_, n, pcm16=args.pcm16, stream=stream)
+            if world > 1:   # the only exchange on this path: gather the decoded minor frames (≤ 104 B x 10 frames/s/capture)
+                pdist.gather_tables(frames_t, [C_] * world)
+            return
+        with torch.cuda.stream(side[k]):
+            ctxs[k].demod_device(d_iq.data_ptr(), C_, n, pcm16=args.pcm16, stream=side[k].cuda_stream)
+            if world > 1:
+                pdist.gather_tables(tables[k], [C_] * world)
 
+    def join():
+        for sk in side:
+            torch.cuda.current_stream().wait_stream(sk)
+
+    for sk in side:
+        sk.wait_stream(torch.cuda.current_stream())
     for _ in range(args.warmup):
         step()
+    if side:
+        join()
     torch.cuda.synchronize()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -250,6 +281,8 @@ def main():
     e0.record()
     for _ in range(args.steps):
         step()
+    if side:
+        join()
     e1.record()
     torch.cuda.synchronize()
     t1 = time.perf_counter()
@@ -300,10 +333,13 @@ def main():
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     Lf = max(d.params.interp, 1)
     # algorithmic bytes per input sample of each kernel: what it must read + write once
+    # k_acquire only touches the samples in front of each capture's lock latch (all of them for a capture that never locks)
+    acq_samples = int(np.where(stats["locked"] == 1, stats["lock_sample"] + 1, stats["n_samples"]).sum())
     alg = {"k_chain_exact": bytes_per_sample, "k_sp": bytes_per_sample + 4, "k_front": bytes_per_sample + 4 + 4 * Lf,
-           "k_pll_core": 8, "k_agc_core": 8 * Lf, "k_gardner": 4 * Lf, "k_bits": 0.8 * Lf, "k_acquire": bytes_per_sample + 8}
+           "k_pll_core": 8, "k_agc_core": 8 * Lf, "k_gardner": 4 * Lf, "k_bits": 0.8 * Lf,
+           "k_acquire": (bytes_per_sample + 8) * acq_samples / float(C_ * n)}
     dom_name, k_ms = kernels[0]
-    alg_bytes = C_ * n * alg.get(dom_name, bytes_per_sample)
+    alg_bytes = int(C_ * n * alg.get(dom_name, bytes_per_sample))
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
@@ -314,7 +350,9 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": dom_name, "kernel_ms": k_ms, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes,
-                "note": "dominant kernel by device time; per-kernel table in `kernels` (ms, GB/s algorithmic, fraction of HBM peak)"}
+                "note": "dominant kernel by device time with all captures in one launch sequence; it is the serial acquisition "
+                        "(latency-bound by the per-sample PLL recurrence), not a streaming kernel; per-kernel table in `kernels` "
+                        "(ms, GB/s algorithmic, fraction of HBM peak); the streaming kernels k_sp / k_front are the HBM-bound ones"}
     ktable = [{"kernel": nm, "ms": round(t_ms, 4),
                "alg_GBps": round(C_ * n * alg[nm] / (t_ms * 1e-3) / 1e9, 1) if nm in alg and t_ms > 0 else None,
                "hbm_frac": round(C_ * n * alg[nm] / (t_ms * 1e-3) / 1e9 / peak, 4) if nm in alg and t_ms > 0 else None}
@@ -332,8 +370,9 @@ def main():
                    "engine": "tiled" if tiled else "exact",
                    "captures_per_gpu": C_, "samples_per_capture": n, "sample_rate": FS, "input": "pcm16" if args.pcm16 else "cf32",
                    "interp": d.params.interp, "taps": d.params.taps, "chunk": d.params.chunk,
-                   "l2": f"inputs {alg_bytes / 1e9:.2f} GB per GPU, far larger than the 126 MB L2 (no flush needed)",
-                   "parallelism": f"captures sharded over {world} GPU(s), frames all-gathered over NCCL" if world > 1 else "one GPU"},
+                   "l2": f"inputs {C_ * n * bytes_per_sample / 1e9:.2f} GB per GPU, far larger than the 126 MB L2 (no flush needed)",
+                   "parallelism": f"captures sharded over {world} GPU(s), frames all-gathered over NCCL" if world > 1 else "one GPU",
+                   "batches_in_flight": inflight},
         "gpu_launches": int(launches), "roofline": roofline, "kernels": ktable,
         "chain_level": {"algorithmic_GBps": chain_gbps, "hbm_frac": chain_gbps / peak,
                         "note": f"{bytes_per_sample} B per input IQ sample over the whole step"},
@@ -348,30 +387,76 @@ def main():
         line["clocks"] = clocks
 
     # ---- e2e: host buffers through the C-ABI --------------------------------------------------------
+    # Same batches-in-flight rotation as above, through pdt_demod_host_async / pdt_fetch: every step copies its batch from
+    # pinned host memory (chunked, overlapped with the kernels) and reads the stats + frame tables back to the host.
     if not args.no_e2e:
         e2e_caps = C_
         host = torch.empty(e2e_caps * n * 2, dtype=elem, pin_memory=True)
         host.copy_(d_iq[: host.numel()])
         torch.cuda.synchronize()
         h_np = host.numpy()
-        for _ in range(1):
-            d.demod_host(h_np, e2e_caps, pcm16=args.pcm16)
+        m = min(inflight, 2)                      # two staging buffers are enough to keep the PCIe link busy
+        e_streams = [torch.cuda.Stream() for _ in range(m)]
+        d2h = [0]
+
+        def e2e_run(steps):
+            pending = [False] * m
+            for i in range(steps):
+                k = i % m
+                if pending[k]:
+                    st_h, fr_h = ctxs[k].fetch(e2e_caps, e_streams[k].cuda_stream)
+                    d2h[0] = st_h.nbytes + fr_h.nbytes
+                ctxs[k].demod_host_async(h_np, e2e_caps, pcm16=args.pcm16, stream=e_streams[k].cuda_stream)
+                pending[k] = True
+            for k in range(m):
+                if pending[k]:
+                    st_h, fr_h = ctxs[k].fetch(e2e_caps, e_streams[k].cuda_stream)
+                    d2h[0] = st_h.nbytes + fr_h.nbytes
+            return st_h
+
+        e2e_run(m)                                # warm-up: staging buffers allocated, streams created
+        torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        e2e_steps = max(2, min(args.steps, 3))
+        e2e_steps = max(4, min(args.steps, 6))
         tt0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            st_h, fr_h = d.demod_host(h_np, e2e_caps, pcm16=args.pcm16)
+        st_last = e2e_run(e2e_steps)
+        torch.cuda.synchronize()
         tt = time.perf_counter() - tt0
         if world > 1:
             t = torch.tensor([tt], dtype=torch.float64, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             tt = float(t.item())
+        assert int(st_last["n_frames"].sum()) == int(stats["n_frames"].sum())
         line["e2e"] = {"value": e2e_caps * n * world * e2e_steps / tt / 1e6, "unit": UNIT,
                        "h2d_bytes_per_step": int(e2e_caps * n * bytes_per_sample),
-                       "d2h_bytes_per_step": int(st_h.nbytes + fr_h.nbytes), "steps": e2e_steps,
-                       "api": "pdt_demod_host (pinned host IQ -> H2D -> fused kernel -> D2H stats+frames)"}
+                       "d2h_bytes_per_step": int(d2h[0]), "steps": e2e_steps, "batches_in_flight": m,
+                       "api": "pdt_demod_host_async + pdt_fetch (pinned host IQ -> chunked H2D overlapped with the kernels -> "
+                              "D2H stats+frames), contexts used in rotation"}
         del host
+
+    # ---- BASELINE configs[1]: one 10 M-sample capture on one GPU (latency of a single stream) ----------
+    if rank == 0 and world == 1 and not args.no_single:
+        n1 = 10_000_000
+        d1_iq = torch.empty(n1 * 2, dtype=elem, device="cuda")
+        L.pdt_synth_poes_device(d1_iq.data_ptr(), int(args.pcm16), 1, n1, n1, float(FS), 4242, stream)
+        d1 = pdt.Demod("f32", params, 1, n1, int(n1 / FS * 10) + 8)
+        for _ in range(2):
+            d1.demod_device(d1_iq.data_ptr(), 1, n1, pcm16=args.pcm16, stream=stream)
+        torch.cuda.synchronize()
+        a1, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a1.record()
+        for _ in range(3):
+            d1.demod_device(d1_iq.data_ptr(), 1, n1, pcm16=args.pcm16, stream=stream)
+        b1.record()
+        torch.cuda.synchronize()
+        st1, _ = d1.fetch(1, stream)
+        ms1 = a1.elapsed_time(b1) / 3
+        line["single_capture_10M"] = {"ms": ms1, "Msamples_per_s": n1 / ms1 / 1e3, "frames": int(st1["n_frames"][0]),
+                                      "locked": int(st1["locked"][0]),
+                                      "note": "BASELINE configs[1] shape: one stream, time-tiled across the SMs of one GPU"}
+        d1.close()
+        del d1_iq
 
     # ---- CPU baseline on a bounded sample of the same captures (rank 0, N=1 only) --------------------
     if rank == 0 and world == 1 and not args.no_cpu:

@@ -142,6 +142,12 @@ int         pdt_demod_device(pdt_ctx *ctx, const void *d_iq, int pcm16, uint32_t
 int         pdt_demod_host(pdt_ctx *ctx, const void *h_iq, int pcm16, uint32_t n_captures, uint64_t stride_samples,
                            const uint64_t *n_samples, pdt_capture_stats *stats_out, pdt_frame *frames_out /* [n_captures·max_frames] */);
 
+/* Asynchronous form: enqueues the chunked H2D (on an internal copy stream) and the kernels (on `stream`) and returns;
+ * collect the results with pdt_fetch(ctx, …, stream).  Two or three contexts used in rotation keep the PCIe link and the
+ * GPU busy at the same time (bench.py e2e).  The host buffer must stay valid (and should be pinned) until the fetch. */
+int         pdt_demod_host_async(pdt_ctx *ctx, const void *h_iq, int pcm16, uint32_t n_captures, uint64_t stride_samples,
+                                 const uint64_t *n_samples, void *stream);
+
 /* Copy results of the last pdt_demod_device() to the host (synchronises `stream`). */
 int         pdt_fetch(pdt_ctx *ctx, uint32_t n_captures, pdt_capture_stats *stats_out, pdt_frame *frames_out, void *stream);
 

@@ -109,6 +109,7 @@ def load(prec: str = "f32"):
     L.pdt_get_taps.argtypes = [vp, vp]
     L.pdt_demod_device.argtypes = [vp, vp, C.c_int, u32, u64, vp, vp, vp]
     L.pdt_demod_host.argtypes = [vp, vp, C.c_int, u32, u64, vp, vp, vp]
+    L.pdt_demod_host_async.argtypes = [vp, vp, C.c_int, u32, u64, vp, vp]
     L.pdt_fetch.argtypes = [vp, u32, vp, vp, vp]
     L.pdt_result_tables.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(u32)]
     L.pdt_format_frames.restype = C.c_long
@@ -158,7 +159,8 @@ def load(prec: str = "f32"):
 EXPORTED_SYMBOLS = [
     # include/pdt.h
     "pdt_version", "pdt_last_error", "pdt_real_size", "pdt_device_count", "pdt_set_device", "pdt_params_default",
-    "pdt_create", "pdt_destroy", "pdt_get_params", "pdt_get_taps", "pdt_demod_device", "pdt_demod_host", "pdt_fetch",
+    "pdt_create", "pdt_destroy", "pdt_get_params", "pdt_get_taps", "pdt_demod_device", "pdt_demod_host", "pdt_demod_host_async",
+    "pdt_fetch",
     "pdt_result_tables", "pdt_format_frames", "pdt_launch_count", "pdt_synth_poes_device", "pdt_engine",
     "pdt_tiled_counters", "pdt_set_profiling", "pdt_kernel_times", "pdt_timeline", "pdt_debug_acq_prof",
     # include/pdt_legacy.h
@@ -218,6 +220,14 @@ class Demod:
         ns = None if n_samples is None else np.ascontiguousarray(n_samples, np.uint64)
         _check(self.L, self.L.pdt_demod_host(self.ctx, _p(iq), int(pcm16), n_captures, stride, _p(ns), _p(stats), _p(frames)))
         return stats, frames
+
+    def demod_host_async(self, iq: np.ndarray, n_captures: int = 1, pcm16: bool = False, n_samples=None, stream: int = 0):
+        """Enqueue H2D + kernels for a host batch and return; collect with fetch(n_captures, stream).  `iq` must stay alive
+        (and should be pinned) until then."""
+        assert iq.flags.c_contiguous and iq.dtype == (np.int16 if pcm16 else self.dt)
+        stride = iq.size // (2 * n_captures)
+        ns = None if n_samples is None else np.ascontiguousarray(n_samples, np.uint64)
+        _check(self.L, self.L.pdt_demod_host_async(self.ctx, _p(iq), int(pcm16), n_captures, stride, _p(ns), C.c_void_p(stream)))
 
     def demod_device(self, d_ptr: int, n_captures: int, stride: int, pcm16: bool = False, n_samples=None, traces=None,
                      stream: int = 0):

@@ -136,11 +136,13 @@ struct pdt_ctx {
     size_t      stage_bytes = 0;
     int         device = 0, sm_count = 0;
     int         engine = PDT_ENGINE_EXACT;
+    static constexpr int MAX_GROUPS = 5;      // + slow-capture stream + staging stream + the caller's = the 8 hardware queues
+    cudaStream_t h2d_stream = nullptr;       // chunked staging of pdt_demod_host
+    cudaEvent_t  ev_h2d[MAX_GROUPS] = {}, ev_done = nullptr;
 #if PDT_USE_FLOATS
     tiled::TiledArgs ta;                 // workspace pointers + plans of the tiled engine (engine == PDT_ENGINE_TILED)
     tiled::TapsRev   taps_rev;
     size_t      front_smem = 0;
-    static constexpr int MAX_GROUPS = 6;      // + the slow-capture stream + the caller's = the 8 hardware queues
     static constexpr int MAX_MARKS = 512;
     int         mark_group[MAX_MARKS] = {};
     cudaStream_t gstream[MAX_GROUPS] = {}, sstream = nullptr;
@@ -150,6 +152,14 @@ struct pdt_ctx {
     const char *mark_names[MAX_MARKS] = {};
 #endif
 };
+
+// how a batch is cut into capture groups (shared by the kernel launches and by the chunked host->device staging)
+static int group_plan(uint32_t n_captures, uint32_t &per)
+{
+    const int groups = (int)std::min<uint32_t>(pdt_ctx::MAX_GROUPS, (n_captures + 63) / 64);
+    per = groups > 0 ? (n_captures + groups - 1) / groups : n_captures;
+    return groups;
+}
 
 #if PDT_USE_FLOATS
 // ---- tiled engine: eligibility, workspace, launch sequence -----------------------------------------------
@@ -333,8 +343,9 @@ static GroupLaunch make_group(pdt_ctx *c, const tiled::TiledArgs &base, uint32_t
 // stream: one group's serial kernels overlap another group's bulk kernels.  Inside a group the captures that have
 // not latched after the first acquisition pass (`acq_first` samples) move to a second stream, where their serial
 // acquisition continues while the majority is already running the rest of the chain.
+// `ready` (optional): one event per capture group, recorded when that group's samples have arrived on the device
 static int tiled_run(pdt_ctx *c, const void *d_iq, int pcm16, uint32_t n_captures, uint64_t stride, const uint64_t *n_samples,
-                     const pdt_traces *traces, cudaStream_t s)
+                     const pdt_traces *traces, cudaStream_t s, const cudaEvent_t *ready = nullptr)
 {
     using namespace tiled;
     TiledArgs t = c->ta;
@@ -350,8 +361,10 @@ static int tiled_run(pdt_ctx *c, const void *d_iq, int pcm16, uint32_t n_capture
     const bool two_pass = t.acq_first != 0;
     PDT_CUDA(cudaMemsetAsync(t.counters, 0, 4 * sizeof(uint32_t), s));
     c->n_marks = 0;
-    int groups = (int)std::min<uint32_t>(pdt_ctx::MAX_GROUPS, (n_captures + 63) / 64);
+    uint32_t per = 0;
+    const int groups = group_plan(n_captures, per);
     if (c->profiling == 1 || traces || groups < 2) {
+        if (ready) for (int gi = 0; gi < groups; gi++) PDT_CUDA(cudaStreamWaitEvent(s, ready[gi], 0));
         GroupLaunch g = make_group(c, t, 0, n_captures, n_max, c->profiling != 0);
         g.head(s);
         g.pipeline(s, 0);
@@ -361,7 +374,6 @@ static int tiled_run(pdt_ctx *c, const void *d_iq, int pcm16, uint32_t n_capture
         if (!c->ev_fork) PDT_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
         if (tl) { GroupLaunch g0 = make_group(c, t, 0, n_captures, n_max, true); g0.gid = -1; g0.mark(s, "fork"); }
         PDT_CUDA(cudaEventRecord(c->ev_fork, s));
-        const uint32_t per = (n_captures + groups - 1) / groups;
         int used = 0;
         for (int gi = 0; gi < groups; gi++) {
             const uint32_t c0 = (uint32_t)gi * per;
@@ -370,6 +382,7 @@ static int tiled_run(pdt_ctx *c, const void *d_iq, int pcm16, uint32_t n_capture
             if (!c->gstream[gi]) PDT_CUDA(cudaStreamCreateWithFlags(&c->gstream[gi], cudaStreamNonBlocking));
             if (!c->ev_join[gi]) PDT_CUDA(cudaEventCreateWithFlags(&c->ev_join[gi], cudaEventDisableTiming));
             PDT_CUDA(cudaStreamWaitEvent(c->gstream[gi], c->ev_fork, 0));
+            if (ready) PDT_CUDA(cudaStreamWaitEvent(c->gstream[gi], ready[gi], 0));
             GroupLaunch g = make_group(c, t, c0, cnt, n_max, tl);
             g.gid = gi;
             g.head(c->gstream[gi]);
@@ -561,6 +574,9 @@ void pdt_destroy(pdt_ctx *c)
     if (c->ev_sjoin) cudaEventDestroy(c->ev_sjoin);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
 #endif
+    if (c->h2d_stream) cudaStreamDestroy(c->h2d_stream);
+    for (cudaEvent_t e : c->ev_h2d) if (e) cudaEventDestroy(e);
+    if (c->ev_done) cudaEventDestroy(c->ev_done);
     delete c;
 }
 
@@ -578,8 +594,17 @@ int pdt_get_taps(const pdt_ctx *c, void *h_out)
     return PDT_OK;
 }
 
+static int demod_device_impl(pdt_ctx *c, const void *d_iq, int pcm16, uint32_t n_captures, uint64_t stride_samples,
+                             const uint64_t *n_samples, const pdt_traces *traces, void *stream, const cudaEvent_t *ready);
+
 int pdt_demod_device(pdt_ctx *c, const void *d_iq, int pcm16, uint32_t n_captures, uint64_t stride_samples,
                      const uint64_t *n_samples, const pdt_traces *traces, void *stream)
+{
+    return demod_device_impl(c, d_iq, pcm16, n_captures, stride_samples, n_samples, traces, stream, nullptr);
+}
+
+static int demod_device_impl(pdt_ctx *c, const void *d_iq, int pcm16, uint32_t n_captures, uint64_t stride_samples,
+                             const uint64_t *n_samples, const pdt_traces *traces, void *stream, const cudaEvent_t *ready)
 {
     if (!c || !d_iq || !n_captures || n_captures > c->max_captures) return fail(PDT_EINVAL, "bad arguments");
     if (!device_ok()) return PDT_ENODEV;
@@ -600,9 +625,10 @@ int pdt_demod_device(pdt_ctx *c, const void *d_iq, int pcm16, uint32_t n_capture
     if (c->engine == PDT_ENGINE_TILED) {
         bool needs_exact = false;      // per-sample frequency / lock-detector taps only exist in the exact engine
         if (traces) for (uint32_t i = 0; i < n_captures; i++) needs_exact |= (traces[i].pll_freq || traces[i].lock);
-        if (!needs_exact) return tiled_run(c, d_iq, pcm16, n_captures, stride_samples, n_samples, traces, s);
+        if (!needs_exact) return tiled_run(c, d_iq, pcm16, n_captures, stride_samples, n_samples, traces, s, ready);
     }
 #endif
+    if (ready) { uint32_t per = 0; const int groups = group_plan(n_captures, per); for (int gi = 0; gi < groups; gi++) PDT_CUDA(cudaStreamWaitEvent(s, ready[gi], 0)); }
     ChainArgs a;
     a.cc = c->cc; a.taps = c->d_taps; a.iq = d_iq; a.pcm16 = pcm16; a.stride = stride_samples;
     a.n_samples = n_samples ? c->d_nsamp : nullptr; a.n_uniform = stride_samples; a.n_captures = n_captures;
@@ -708,20 +734,47 @@ int pdt_result_tables(pdt_ctx *c, void **d_stats, void **d_frames, uint32_t *max
     return PDT_OK;
 }
 
-int pdt_demod_host(pdt_ctx *c, const void *h_iq, int pcm16, uint32_t n_captures, uint64_t stride_samples,
-                   const uint64_t *n_samples, pdt_capture_stats *stats_out, pdt_frame *frames_out)
+int pdt_demod_host_async(pdt_ctx *c, const void *h_iq, int pcm16, uint32_t n_captures, uint64_t stride_samples,
+                         const uint64_t *n_samples, void *stream)
 {
     if (!c || !h_iq) return fail(PDT_EINVAL, "bad arguments");
     if (!device_ok()) return PDT_ENODEV;
+    cudaStream_t s = (cudaStream_t)stream;
     const size_t elem = pcm16 ? 2 * sizeof(int16_t) : 2 * sizeof(real_t);
     const size_t bytes = elem * stride_samples * n_captures;
     if (bytes > c->stage_bytes) {
+        PDT_CUDA(cudaDeviceSynchronize());
         cudaFree(c->d_stage); c->d_stage = nullptr; c->stage_bytes = 0;
         PDT_CUDA(cudaMalloc(&c->d_stage, bytes));
         c->stage_bytes = bytes;
     }
-    PDT_CUDA(cudaMemcpyAsync(c->d_stage, h_iq, bytes, cudaMemcpyHostToDevice, 0));
-    int rc = pdt_demod_device(c, c->d_stage, pcm16, n_captures, stride_samples, n_samples, nullptr, nullptr);
+    // The samples go up one capture group at a time on a copy stream; every group starts its kernels as soon as its own
+    // samples have landed, so all but the first group's transfer is hidden behind the kernels of the groups before it.
+    uint32_t per = 0;
+    const int groups = group_plan(n_captures, per);
+    if (!c->h2d_stream) PDT_CUDA(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
+    if (!c->ev_done) PDT_CUDA(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
+    else PDT_CUDA(cudaStreamWaitEvent(c->h2d_stream, c->ev_done, 0));      // the previous batch has finished reading the staging buffer
+    for (int gi = 0; gi < groups; gi++) {
+        const uint32_t c0 = (uint32_t)gi * per;
+        const uint32_t cnt = c0 < n_captures ? std::min<uint32_t>(per, n_captures - c0) : 0;
+        if (!c->ev_h2d[gi]) PDT_CUDA(cudaEventCreateWithFlags(&c->ev_h2d[gi], cudaEventDisableTiming));
+        if (cnt) {
+            const size_t off = elem * stride_samples * c0, len = elem * stride_samples * cnt;
+            PDT_CUDA(cudaMemcpyAsync((char *)c->d_stage + off, (const char *)h_iq + off, len, cudaMemcpyHostToDevice, c->h2d_stream));
+        }
+        PDT_CUDA(cudaEventRecord(c->ev_h2d[gi], c->h2d_stream));
+    }
+    const int rc = demod_device_impl(c, c->d_stage, pcm16, n_captures, stride_samples, n_samples, nullptr, s, c->ev_h2d);
+    if (rc != PDT_OK) return rc;
+    PDT_CUDA(cudaEventRecord(c->ev_done, s));
+    return PDT_OK;
+}
+
+int pdt_demod_host(pdt_ctx *c, const void *h_iq, int pcm16, uint32_t n_captures, uint64_t stride_samples,
+                   const uint64_t *n_samples, pdt_capture_stats *stats_out, pdt_frame *frames_out)
+{
+    const int rc = pdt_demod_host_async(c, h_iq, pcm16, n_captures, stride_samples, n_samples, nullptr);
     if (rc != PDT_OK) return rc;
     return pdt_fetch(c, n_captures, stats_out, frames_out, nullptr);
 }
