@@ -242,6 +242,7 @@ def main():
     tables = [frames_t] + [torch.as_tensor(_Raw(c.result_tables()[1], C_ * max_frames * 120), device="cuda").view(C_, max_frames * 120)
                            for c in ctxs[1:]]
     side = [torch.cuda.Stream() for _ in range(inflight)] if inflight > 1 else []
+    gathered = [torch.empty((world * C_, max_frames * 120), dtype=torch.uint8, device="cuda") for _ in range(inflight)] if world > 1 else None
     step_no = [0]
 
     def step():
@@ -250,12 +251,12 @@ def main():
         if inflight == 1:
             d.demod_device(d_iq.data_ptr(), C_, n, pcm16=args.pcm16, stream=stream)
             if world > 1:   # the only exchange on this path: gather the decoded minor frames (≤ 104 B x 10 frames/s/capture)
-                pdist.gather_tables(frames_t, [C_] * world)
+                dist.all_gather_into_tensor(gathered[0], frames_t)
             return
         with torch.cuda.stream(side[k]):
             ctxs[k].demod_device(d_iq.data_ptr(), C_, n, pcm16=args.pcm16, stream=side[k].cuda_stream)
-            if world > 1:
-                pdist.gather_tables(tables[k], [C_] * world)
+            if world > 1:   # equal shards: the plain all-gather (dist.gather_tables handles ragged shards)
+                dist.all_gather_into_tensor(gathered[k], tables[k])
 
     def join():
         for sk in side:
