@@ -22,7 +22,7 @@ namespace tiled {
 
 constexpr int LS_R  = 64;            // samples per lane per stage (256-byte rows)
 constexpr int LS_RS = LS_R + 4;      // row stride in floats: 272 B, 16-byte aligned, bank-conflict-free for 128-bit accesses
-constexpr int LS_NIN = 3;            // input stages: pieces are requested two rounds ahead (a round of the fast AGC step is shorter than a DRAM round trip)
+constexpr int LS_NIN = 2;            // input stages (the next piece is requested while the current one is consumed)
 
 struct __align__(128) LaneStreamSmem {
     float in[LS_NIN][32][LS_RS];
