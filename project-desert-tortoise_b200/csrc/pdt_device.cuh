@@ -69,55 +69,51 @@ PDT_DEV double r_rint(double x) { return rint(x); }
 // equals the host libm's for |x| < 120 (the PLL phase lives in [-2π, 2π]).  tests/test_gpu_parity.py
 // checks this against the oracle over the whole phase range.
 // ---------------------------------------------------------------------------------------------------
-struct SinCosTab { double c0, c1, c2, c3, c4, s1, s2, s3; };
-
-PDT_DEV double sc_poly(double x, double x2, double flip, int n)
+// sine / cosine kernels on the reduced argument (s_sincosf.h: sincosf_poly).  Both are evaluated for every sample and
+// swapped / negated afterwards: IEEE +,× are sign-symmetric, so sin_poly(-x) == -sin_poly(x) and a cosine evaluated with
+// the negated coefficient set (glibc's second table entry) is the negated cosine, bit for bit — no per-lane branches.
+PDT_DEV double sc_sin_poly(double x, double x2)
 {
-    // flip = +1 (quadrants 0,1) or -1 (quadrants 2,3): negates the cosine coefficients only
     const double s1 = -0x1.555545995a603p-3, s2 = 0x1.1107605230bc4p-7, s3 = -0x1.994eb3774cf24p-13;
+    const double x3 = x * x2;
+    const double t1 = s2 + x2 * s3;
+    const double x7 = x3 * x2;
+    const double s  = x + x3 * s1;
+    return s + x7 * t1;
+}
+PDT_DEV double sc_cos_poly(double x2)
+{
     const double c0 = 0x1p0, c1 = -0x1.ffffffd0c621cp-2, c2 = 0x1.55553e1068f19p-5,
                  c3 = -0x1.6c087e89a359dp-10, c4 = 0x1.99343027bf8c3p-16;
-    if ((n & 1) == 0) {
-        double x3 = x * x2;
-        double t1 = s2 + x2 * s3;
-        double x7 = x3 * x2;
-        double s  = x + x3 * s1;
-        return s + x7 * t1;
-    } else {
-        double x4 = x2 * x2;
-        double t2 = (flip * c3) + x2 * (flip * c4);
-        double t1 = (flip * c0) + x2 * (flip * c1);
-        double x6 = x4 * x2;
-        double c  = t1 + x4 * (flip * c2);
-        return c + x6 * t2;
-    }
+    const double x4 = x2 * x2;
+    const double t2 = c3 + x2 * c4;
+    const double t1 = c0 + x2 * c1;
+    const double x6 = x4 * x2;
+    const double c  = t1 + x4 * c2;
+    return c + x6 * t2;
 }
 
 PDT_DEV uint32_t abstop12(float x) { return (pdt_f2u(x) >> 20) & 0x7ffu; }
 
 PDT_DEV void sincos_exact(float y, float &s, float &c)
 {
-    double x = (double)y;
-    if (abstop12(y) < 0x3f4u) {                 // |y| < top12(pi/4)
-        double x2 = x * x;
-        if (abstop12(y) < 0x398u) { s = y; c = 1.0f; return; }      // |y| < 2^-12
-        s = (float)sc_poly(x, x2, 1.0, 0);
-        c = (float)sc_poly(x, x2, 1.0, 1);
-        return;
-    }
-    if (abstop12(y) < 0x42fu) {                 // |y| < 120
-        const double hpi_inv = 0x1.45F306DC9C883p+23, hpi = 0x1.921FB54442D18p0;
-        double r = x * hpi_inv;
-        int n = (pdt_d2i_rz(r) + 0x800000) >> 24;
-        x = x - (double)n * hpi;
-        const double sgn  = ((n & 3) == 0 || (n & 3) == 3) ? 1.0 : -1.0;
-        const double flip = (n & 2) ? -1.0 : 1.0;
-        const double xs = x * sgn, x2 = x * x;
-        s = (float)sc_poly(xs, x2, flip, n);
-        c = (float)sc_poly(xs, x2, flip, n ^ 1);
-        return;
-    }
-    s = sinf(y); c = cosf(y);                   // never reached by the PLL (phase is wrapped to ±2π)
+    if (abstop12(y) >= 0x42fu) { s = sinf(y); c = cosf(y); return; }      // |y| >= 120: never reached by the PLL (phase is wrapped to ±2π)
+    // glibc's three ranges collapse into its general path: for |y| < π/4 the quadrant is n = 0 and the reduction x - 0·(π/2)
+    // is exact, which is its small-argument path; its |y| < 2^-12 shortcut (s = y, c = 1) is applied as a select at the end.
+    const double x = (double)y;
+    const double hpi_inv = 0x1.45F306DC9C883p+23, hpi = 0x1.921FB54442D18p0;
+    const double r = x * hpi_inv;
+    const int n = (pdt_d2i_rz(r) + 0x800000) >> 24;
+    const double xr = x - (double)n * hpi;
+    const double x2 = xr * xr;
+    const double sp = sc_sin_poly(xr, x2), cp = sc_cos_poly(x2);
+    const bool neg_sin = ((n & 3) == 1) || ((n & 3) == 2);               // sign of the sine-kernel argument (sgn in the table form)
+    const bool neg_cos = (n & 2) != 0;                                   // second coefficient table = negated cosine
+    const float sv = (float)(neg_sin ? -sp : sp), cv = (float)(neg_cos ? -cp : cp);
+    const bool odd = (n & 1) != 0;
+    float rs = odd ? cv : sv, rc = odd ? sv : cv;
+    if (abstop12(y) < 0x398u) { rs = y; rc = 1.0f; }                     // |y| < 2^-12
+    s = rs; c = rc;
 }
 PDT_DEV void sincos_exact(double y, double &s, double &c)
 {
