@@ -87,6 +87,18 @@ typedef struct pdt_frame {
     uint8_t  bytes[PDT_FRAME_MAX_BYTES];
 } pdt_frame;                 /* 120 bytes */
 
+/* Post-checks of one decoded POES minor frame, computed on the device right behind the frame shifter
+ * (standalone_matlab/Functionized/checkParity.m:20-90, daytimeDecode.m:4): the step after the hot path. */
+typedef struct pdt_frame_quality {
+    uint16_t counter;        /* 9-bit minor-frame counter: (byte4 & 1) << 8 | byte5, 0…319 */
+    uint8_t  spacecraft;     /* byte 2 (8 = NOAA-15, 13 = NOAA-18, 15 = NOAA-19) */
+    uint8_t  parity_ok;      /* the five even-parity bits of word 103 agree with words 2-18 / 19-35 / 36-52 / 53-69 / 70-86 */
+    uint8_t  parity_bits;    /* which of the five groups failed (bit 4 = first group … bit 0 = last) */
+    uint8_t  continuous;     /* counter == previous complete frame's counter + 1 (mod 320); 1 for the first frame */
+    uint8_t  valid;          /* frame complete (104 bytes) — the other fields are meaningful only then */
+    uint8_t  pad;
+} pdt_frame_quality;         /* 8 bytes */
+
 /* Per-capture summary (what the reference prints on its progress line, main.c:461-481). */
 typedef struct pdt_capture_stats {
     uint64_t n_samples, n_symbols, n_bits;
@@ -150,6 +162,10 @@ int         pdt_demod_host_async(pdt_ctx *ctx, const void *h_iq, int pcm16, uint
 
 /* Copy results of the last pdt_demod_device() to the host (synchronises `stream`). */
 int         pdt_fetch(pdt_ctx *ctx, uint32_t n_captures, pdt_capture_stats *stats_out, pdt_frame *frames_out, void *stream);
+
+/* Frame post-checks of the last batch (POES): runs k_frame_checks on `stream` over the device frame table and copies
+ * the [n_captures·max_frames] quality table to the host (synchronises `stream`). */
+int         pdt_frame_checks(pdt_ctx *ctx, uint32_t n_captures, pdt_frame_quality *quality_out, void *stream);
 
 /* Device addresses of the result tables of the last batch (for NCCL gathers without a host bounce). */
 int         pdt_result_tables(pdt_ctx *ctx, void **d_stats, void **d_frames, uint32_t *max_frames);

@@ -65,6 +65,9 @@ class Traces(C.Structure):
 FRAME_DTYPE = np.dtype([("sample_index", "<u8"), ("bit_index", "<u4"), ("inverse", "u1"), ("n_bytes", "u1"),
                         ("complete", "u1"), ("pad", "u1"), ("bytes", "u1", (FRAME_MAX,))])
 assert FRAME_DTYPE.itemsize == C.sizeof(Frame) == 120
+QUALITY_DTYPE = np.dtype([("counter", "<u2"), ("spacecraft", "u1"), ("parity_ok", "u1"), ("parity_bits", "u1"),
+                          ("continuous", "u1"), ("valid", "u1"), ("pad", "u1")])
+assert QUALITY_DTYPE.itemsize == 8
 STATS_DTYPE = np.dtype([("n_samples", "<u8"), ("n_symbols", "<u8"), ("n_bits", "<u8"), ("n_frames", "<u4"),
                         ("locked", "<i4"), ("lock_sample", "<u8"), ("lock_freq_hz", "<f8"), ("norm_factor", "<f8"),
                         ("avg_phase", "<f8"), ("final_phase", "<f8"), ("final_freq", "<f8"), ("final_gain", "<f8"),
@@ -162,7 +165,7 @@ EXPORTED_SYMBOLS = [
     "pdt_create", "pdt_destroy", "pdt_get_params", "pdt_get_taps", "pdt_demod_device", "pdt_demod_host", "pdt_demod_host_async",
     "pdt_fetch",
     "pdt_result_tables", "pdt_format_frames", "pdt_launch_count", "pdt_synth_poes_device", "pdt_engine",
-    "pdt_tiled_counters", "pdt_set_profiling", "pdt_kernel_times", "pdt_timeline", "pdt_debug_acq_prof",
+    "pdt_frame_checks", "pdt_tiled_counters", "pdt_set_profiling", "pdt_kernel_times", "pdt_timeline", "pdt_debug_acq_prof",
     # include/pdt_legacy.h
     "FindSignalAmplitude", "Squelch", "StaticGain", "NormalizingAGC", "NormalizingAGCC", "CarrierTrackPLL", "arctan2",
     "Q_rsqrt", "LowPassFilter", "LowPassFilterInterp", "MakeLPFIR", "GardenerClockRecovery", "MMClockRecovery", "sign",
@@ -276,6 +279,12 @@ class Demod:
         if k < 0:
             raise PdtError(self.L.pdt_last_error().decode())
         return [(names[i].decode(), int(groups[i]), float(ms[i])) for i in range(k)]
+
+    def frame_checks(self, n_captures: int, stream: int = 0) -> np.ndarray:
+        """[n_captures, max_frames] quality records of the last batch (parity word 103, counter continuity, spacecraft id)."""
+        q = np.zeros((n_captures, self.max_frames), QUALITY_DTYPE)
+        _check(self.L, self.L.pdt_frame_checks(self.ctx, n_captures, _p(q), C.c_void_p(stream)))
+        return q
 
     def result_tables(self):
         ds, df, mf = C.c_void_p(), C.c_void_p(), C.c_uint32()

@@ -132,6 +132,7 @@ struct pdt_ctx {
     pdt_frame  *d_frames = nullptr;
     unsigned long long *d_nsamp = nullptr;
     pdt_traces *d_traces = nullptr;
+    pdt_frame_quality *d_quality = nullptr;
     void       *d_stage = nullptr;       // staging for pdt_demod_host
     size_t      stage_bytes = 0;
     int         device = 0, sm_count = 0;
@@ -427,6 +428,45 @@ static int tiled_run(pdt_ctx *c, const void *d_iq, int pcm16, uint32_t n_capture
 }
 #endif
 
+// checkParity.m:20-90 + daytimeDecode.m:4 on the device frame table: one thread per frame slot, then a serial pass per
+// capture for the counter continuity (a capture has tens of frames)
+__global__ void k_frame_checks(const pdt_frame *frames, const pdt_capture_stats *stats, pdt_frame_quality *q, uint32_t n_captures,
+                               uint32_t max_frames)
+{
+    const uint32_t cap = blockIdx.x;
+    if (cap >= n_captures) return;
+    const uint32_t nf = stats[cap].n_frames < max_frames ? stats[cap].n_frames : max_frames;
+    const pdt_frame *fr = frames + (size_t)cap * max_frames;
+    pdt_frame_quality *qq = q + (size_t)cap * max_frames;
+    for (uint32_t f = threadIdx.x; f < max_frames; f += blockDim.x) {
+        pdt_frame_quality r; r.counter = 0; r.spacecraft = 0; r.parity_ok = 0; r.parity_bits = 0; r.continuous = 0; r.valid = 0; r.pad = 0;
+        if (f < nf && fr[f].complete && fr[f].n_bytes == PDT_FRAME_MAX_BYTES) {
+            const uint8_t *b = fr[f].bytes;
+            r.valid = 1;
+            r.counter = (uint16_t)(((b[4] & 1u) << 8) | b[5]);
+            r.spacecraft = b[2];
+            const int lo[5] = {2, 19, 36, 53, 70}, hi[5] = {18, 35, 52, 69, 86};
+            unsigned bad = 0;
+            for (int g = 0; g < 5; g++) {
+                unsigned ones = 0;
+                for (int k = lo[g]; k <= hi[g]; k++) ones += __popc((unsigned)b[k]);
+                if ((ones & 1u) != ((b[103] >> (5 - g)) & 1u)) bad |= 1u << (4 - g);
+            }
+            r.parity_bits = (uint8_t)bad; r.parity_ok = bad == 0;
+        }
+        qq[f] = r;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int prev = -1;
+        for (uint32_t f = 0; f < nf; f++) {
+            if (!qq[f].valid) continue;
+            qq[f].continuous = (prev < 0) || (qq[f].counter == (unsigned)((prev + 1) % 320));
+            prev = qq[f].counter;
+        }
+    }
+}
+
 extern "C" {
 
 const char *pdt_version(void) { return "pdt-b200 0.1 (sm_100a, "
@@ -563,7 +603,7 @@ void pdt_destroy(pdt_ctx *c)
 {
     if (!c) return;
     cudaFree(c->d_taps); cudaFree(c->d_ws); cudaFree(c->d_stats); cudaFree(c->d_frames);
-    cudaFree(c->d_nsamp); cudaFree(c->d_traces); cudaFree(c->d_stage);
+    cudaFree(c->d_nsamp); cudaFree(c->d_traces); cudaFree(c->d_stage); cudaFree(c->d_quality);
 #if PDT_USE_FLOATS
     if (c->engine == PDT_ENGINE_TILED) tiled_free(c);
     for (cudaEvent_t e : c->marks) if (e) cudaEventDestroy(e);
@@ -722,6 +762,21 @@ int pdt_debug_acq_prof(uint64_t out[8], int reset)
 #else
     for (int i = 0; i < 8; i++) out[i] = 0;
 #endif
+    return PDT_OK;
+}
+
+int pdt_frame_checks(pdt_ctx *c, uint32_t n_captures, pdt_frame_quality *quality_out, void *stream)
+{
+    if (!c || !quality_out || n_captures > c->max_captures) return fail(PDT_EINVAL, "bad arguments");
+    if (!device_ok()) return PDT_ENODEV;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t bytes = sizeof(pdt_frame_quality) * (size_t)c->max_captures * c->max_frames;
+    if (!c->d_quality) PDT_CUDA(cudaMalloc(&c->d_quality, bytes));
+    k_frame_checks<<<n_captures, 64, 0, s>>>(c->d_frames, c->d_stats, c->d_quality, n_captures, c->max_frames);
+    count_launch();
+    PDT_CUDA(cudaGetLastError());
+    PDT_CUDA(cudaMemcpyAsync(quality_out, c->d_quality, sizeof(pdt_frame_quality) * (size_t)n_captures * c->max_frames, cudaMemcpyDeviceToHost, s));
+    PDT_CUDA(cudaStreamSynchronize(s));
     return PDT_OK;
 }
 

@@ -305,6 +305,67 @@ def test_tiled_stream_groups_equal_exact_engine(torch_cuda, acq_first):
     assert np.array_equal(fe, ft)
 
 
+def test_async_host_api_contexts_in_rotation(torch_cuda):
+    """pdt_demod_host_async + pdt_fetch with two contexts used in rotation on two streams (what bench.py's e2e leg does):
+    every batch must give exactly the synchronous pdt_demod_host result, whatever overlaps with it."""
+    torch = torch_cuda
+    fs, n, caps = 250000, 150_000, 130                 # > 64 captures: capture groups + chunked staging are exercised
+    batches = []
+    for b in range(3):
+        pcm = np.zeros((caps, n, 2), np.int16)
+        for c in range(0, caps, 13):                   # a few real captures, the rest noise
+            x, _ = make_poes_capture(n, fs, 500 + 31 * b + c, esn0_db=15.0, doppler_hz=-2500.0 + 37.0 * c, amplitude=0.2)
+            pcm[c] = x.reshape(-1, 2)
+        rng = np.random.default_rng(b)
+        noise = (rng.standard_normal((caps, n, 2)) * 200).astype(np.int16)
+        pcm = np.where(pcm.any(axis=(1, 2), keepdims=True), pcm, noise)
+        batches.append(np.ascontiguousarray(pcm))
+    p = pdt.default_params("f32", pdt.PDT_MODE_POES, fs)
+    ref = pdt.Demod("f32", p, caps, n, 16)
+    want = [ref.demod_host(x, caps, pcm16=True) for x in batches]
+    ctxs = [pdt.Demod("f32", p, caps, n, 16) for _ in range(2)]
+    streams = [torch.cuda.Stream() for _ in range(2)]
+    pinned = [torch.from_numpy(x).pin_memory() for x in batches]
+    got = [None] * len(batches)
+    pending = [None, None]
+    for i, x in enumerate(pinned + pinned[:1]):        # 4 submissions: the last one re-uses a context twice in a row
+        k = i % 2
+        if pending[k] is not None:
+            got[pending[k]] = ctxs[k].fetch(caps, streams[k].cuda_stream)
+        ctxs[k].demod_host_async(x.numpy(), caps, pcm16=True, stream=streams[k].cuda_stream)
+        pending[k] = i % len(batches)
+    for k in range(2):
+        got[pending[k]] = ctxs[k].fetch(caps, streams[k].cuda_stream)
+    for (ws, wf), (gs, gf) in zip(want, got):
+        assert ws["n_frames"].sum() > 20
+        assert np.array_equal(ws, gs) and np.array_equal(wf, gf)
+
+
+def test_frame_post_checks_on_device(torch_cuda, golden_dir):
+    """Parity word 103 / counter continuity / spacecraft id computed on the device (checkParity.m, daytimeDecode.m) against
+    the numpy restatement, on the reference's own recording and on a synthetic capture with a corrupted frame."""
+    rate, pcm = po.read_wav_pcm16(_golden(golden_dir, "5sec_clip.wav"))
+    d = pdt.Demod("f32", pdt.default_params("f32", pdt.PDT_MODE_POES, rate), 1, pcm.size // 2, 64)
+    st, fr = d.demod_host(pcm, 1, pcm16=True)
+    q = d.frame_checks(1)[0]
+    nf = int(st[0]["n_frames"])
+    prev = None
+    seen = 0
+    for f in range(nf):
+        b = fr[0][f]["bytes"]
+        full = bool(fr[0][f]["complete"]) and fr[0][f]["n_bytes"] == 104
+        assert bool(q[f]["valid"]) == full
+        if not full:
+            continue
+        seen += 1
+        assert q[f]["counter"] == frame_counter(b) and q[f]["spacecraft"] == b[2]
+        assert bool(q[f]["parity_ok"]) == check_parity(b)
+        assert bool(q[f]["continuous"]) == (prev is None or frame_counter(b) == (prev + 1) % 320)
+        prev = frame_counter(b)
+    assert seen >= 40 and q[:nf]["spacecraft"][q[:nf]["valid"] == 1].tolist() == [8] * seen      # NOAA-15, SURVEY §8c
+    assert not q[nf:]["valid"].any()
+
+
 def test_poes_golden_synth_c2(torch_cuda, golden_dir):
     g = np.load(_golden(golden_dir, "synth_poes_c2_small.npz"))
     p = pdt.default_params("f32", pdt.PDT_MODE_POES, int(g["fs"]))
