@@ -136,6 +136,10 @@ int         pdt_params_default(pdt_params *p, int mode, double sample_rate);
 /* A context owns device workspaces for `max_captures` captures of up to `max_samples` IQ samples each and
  * `max_frames` frame slots per capture. */
 pdt_ctx    *pdt_create(const pdt_params *p, uint32_t max_captures, uint64_t max_samples, uint32_t max_frames);
+/* A context processes ONE batch at a time (its workspaces and internal streams belong to that batch until the results
+ * have been fetched).  To keep several batches in flight — the serial acquisition tail of one batch then overlaps the bulk
+ * kernels of the next — create one context per batch in flight and use them in rotation, each on its own stream
+ * (bench.py does this with three). */
 void        pdt_destroy(pdt_ctx *ctx);
 int         pdt_get_params(const pdt_ctx *ctx, pdt_params *out);
 int         pdt_get_taps(const pdt_ctx *ctx, void *h_out /* REAL[taps] */);
