@@ -157,7 +157,12 @@ struct pdt_ctx {
 // how a batch is cut into capture groups (shared by the kernel launches and by the chunked host->device staging)
 static int group_plan(uint32_t n_captures, uint32_t &per)
 {
-    const int groups = (int)std::min<uint32_t>(pdt_ctx::MAX_GROUPS, (n_captures + 63) / 64);
+    static int max_groups = 0;                        // PDT_MAX_GROUPS: experiment knob (default: pdt_ctx::MAX_GROUPS)
+    if (max_groups == 0) {
+        const char *e = getenv("PDT_MAX_GROUPS");
+        max_groups = e ? std::max(1, std::min(atoi(e), (int)pdt_ctx::MAX_GROUPS)) : (int)pdt_ctx::MAX_GROUPS;
+    }
+    const int groups = (int)std::min<uint32_t>((uint32_t)max_groups, (n_captures + 63) / 64);
     per = groups > 0 ? (n_captures + groups - 1) / groups : n_captures;
     return groups;
 }
@@ -271,7 +276,7 @@ struct GroupLaunch {
     void acquire_rest(cudaStream_t s)
     {
         using namespace tiled;
-        k_acquire<<<cnt, ACQ_THREADS, 0, s>>>(t, 1);
+        k_acquire<<<cnt, ACQ_THREADS_SLOW, 0, s>>>(t, 1);
         mark(s, "k_acquire");
         count_launch(1);
     }

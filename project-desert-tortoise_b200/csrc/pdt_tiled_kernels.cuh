@@ -165,7 +165,8 @@ __global__ void __launch_bounds__(256) k_sp(const TiledArgs a)
 constexpr int ACQ_B = 256;            // samples per pipeline block
 constexpr int ACQ_RING = 4;           // blocks in flight: core | terms | EMAs | decisions
 constexpr int ACQ_THREADS = 256;
-constexpr int ACQ_HELPERS = ACQ_THREADS - 96;     // warps 3..7: feed-forward terms, decisions, loads, commits
+constexpr int ACQ_THREADS_SLOW = 128; // second pass: the few slow captures hold their CTA for tens of ms — a thinner CTA (one helper warp) halves the
+                                      // registers they pin down while several batches are in flight
 
 struct __align__(16) AcqSmem {
     float sp[ACQ_RING][ACQ_B], a[ACQ_RING][ACQ_B], b[ACQ_RING][ACQ_B];               // inputs
@@ -276,6 +277,7 @@ __global__ void __launch_bounds__(ACQ_THREADS) k_acquire(const TiledArgs a, cons
 {
     unsigned long long pf_steps = 0, pf_cyc = 0, pf_busy = 0, pf_dec = 0, pf_epochs = 0;
     __shared__ AcqSmem s;
+    const int n_threads = (int)blockDim.x, n_helpers = n_threads - 96;     // 3 serial warps + the helper warps
     const uint32_t cap = blockIdx.x;
     const int tid = threadIdx.x;
     const u64 n = cap_len(a, cap), first = (u64)cap * a.stride;
@@ -329,7 +331,7 @@ __global__ void __launch_bounds__(ACQ_THREADS) k_acquire(const TiledArgs a, cons
         const int cnt = block_cnt(j);
         const int slot = (int)(j % ACQ_RING);
         const u64 b0 = x0 + block_off(j);
-        for (int i = hid; i < cnt; i += ACQ_HELPERS) {
+        for (int i = hid; i < cnt; i += n_helpers) {
             float p, q;
             load_iq1(a.iq, a.pcm16, first + b0 + i, p, q);
             s.a[slot][i] = p; s.b[slot][i] = q; s.sp[slot][i] = a.sp[wfirst + b0 + i];
@@ -366,7 +368,7 @@ __global__ void __launch_bounds__(ACQ_THREADS) k_acquire(const TiledArgs a, cons
             } else if (hid >= 0) {
                 if (c_term) {                                                        // [A],[D] feed-forward parts of block st-1
                     const int slot = (int)((st - 1) % ACQ_RING);
-                    for (int i = hid; i < c_term; i += ACQ_HELPERS) {
+                    for (int i = hid; i < c_term; i += n_helpers) {
                         float ti, tr;
                         sincos_exact(s.ph[slot][i], ti, tr);                                    // :106-107
                         const float p = s.a[slot][i], q = s.b[slot][i], nti = -ti;
@@ -386,7 +388,7 @@ __global__ void __launch_bounds__(ACQ_THREADS) k_acquire(const TiledArgs a, cons
             // decisions of block st-3 (its EMAs were finished in the previous step)
             if (c_dec && hid >= 0) {
                 const int slot = (int)((st - 3) % ACQ_RING);
-                for (int i = hid; i < c_dec; i += ACQ_HELPERS) {
+                for (int i = hid; i < c_dec; i += n_helpers) {
                     const int so = (int)block_off(st - 3) + i;
                     const bool want = (so < spec_n) ? (s.spec[so] != 0) : flag;
                     if ((acq_noise_like(s.avg[slot][i + 1]) != 0) != want) atomicMin(&s.mism[st & 1], i);      // :232
@@ -411,7 +413,7 @@ __global__ void __launch_bounds__(ACQ_THREADS) k_acquire(const TiledArgs a, cons
                 if (latch < c_dec && latch < mism) {
                     // every flag up to and including the latch sample was right: commit and leave acquisition
                     const int cnt = latch + 1;
-                    for (int i = tid; i < cnt; i += ACQ_THREADS) ph_out[b0 + i] = s.ph[slot][i];
+                    for (int i = tid; i < cnt; i += n_threads) ph_out[b0 + i] = s.ph[slot][i];
                     if (tid == 0) {
                         const float freq = s.fr[slot][cnt];
                         res->locked = 1; res->lock_sample = b0 + latch; res->track_begin = b0 + cnt; res->resume_at = n;
@@ -428,7 +430,7 @@ __global__ void __launch_bounds__(ACQ_THREADS) k_acquire(const TiledArgs a, cons
                     return;
                 }
                 const int good = mism;                                   // samples of the block whose speculated flag was right
-                for (int i = tid; i < good; i += ACQ_THREADS) ph_out[b0 + i] = s.ph[slot][i];
+                for (int i = tid; i < good; i += n_threads) ph_out[b0 + i] = s.ph[slot][i];
                 if (mism < c_dec) {
                     // the flag flips at sample `mism`: new epoch there, from the exact state in front of that sample
                     // The flags the EMA just produced for the rest of this block become the per-sample prediction of the new
@@ -438,10 +440,10 @@ __global__ void __launch_bounds__(ACQ_THREADS) k_acquire(const TiledArgs a, cons
                     const float na = s.avg[slot][mism], nl_ = s.lks[slot][mism];
                     const int nspec = c_dec - mism;
                     unsigned char mine[2] = {0, 0};
-                    for (int i = tid, q = 0; i < nspec; i += ACQ_THREADS, q++) mine[q] = acq_noise_like(s.avg[slot][mism + i + 1]);
+                    for (int i = tid, q = 0; i < nspec; i += n_threads, q++) mine[q] = acq_noise_like(s.avg[slot][mism + i + 1]);
                     const bool tail = acq_noise_like(s.avg[slot][c_dec]) != 0;
                     __syncthreads();
-                    for (int i = tid, q = 0; i < nspec; i += ACQ_THREADS, q++) s.spec[i] = mine[q];
+                    for (int i = tid, q = 0; i < nspec; i += n_threads, q++) s.spec[i] = mine[q];
                     x0 = b0 + (u64)mism; e_phase = np_; e_freq = nf; e_sweep = nw; e_avg = na; e_lks = nl_;
                     spec_n = nspec; flag = tail; restarts++;
                     epoch_done = true;
