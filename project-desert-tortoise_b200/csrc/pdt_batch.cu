@@ -218,6 +218,12 @@ static int tiled_setup(pdt_ctx *c)
     TA(t.guess, np * sizeof(LoopState2)); TA(t.pll_start, np * sizeof(LoopState2)); TA(t.pll_end, np * sizeof(LoopState2));
     TA(t.agc_start, na * sizeof(LoopState2)); TA(t.agc_end, na * sizeof(LoopState2));
     TA(t.counters, 4 * sizeof(uint32_t));
+    // work lists of the persistent lane-stream kernels: one region per pass (fast groups / slow captures run concurrently)
+    t.pll_tasks_per_cap = (t.pll.max_tiles + 31) / 32;
+    t.agc_tasks_per_cap = (t.agc_max_tiles + 31) / 32;
+    TA(t.pll_tasks, 2 * (size_t)c->max_captures * t.pll_tasks_per_cap * sizeof(LaneTask));
+    TA(t.agc_tasks, 2 * (size_t)c->max_captures * t.agc_tasks_per_cap * sizeof(LaneTask));
+    TA(t.task_counts, 2 * (pdt_ctx::MAX_GROUPS + 1) * 2 * sizeof(uint32_t));
     {
         const double S = (double)cc.gardner_fs / (double)cc.baud;        // samples per symbol
         t.sym_cap = (u64)((double)stride * cc.L / (S - 0.2)) + stride / cc.chunk + 64;
@@ -243,7 +249,7 @@ static void tiled_free(pdt_ctx *c)
     tiled::TiledArgs &t = c->ta;
     cudaFree(t.sp); cudaFree(t.ph); cudaFree(t.y); cudaFree(t.z); cudaFree(t.acq); cudaFree(t.guess);
     cudaFree(t.pll_start); cudaFree(t.pll_end); cudaFree(t.agc_start); cudaFree(t.agc_end); cudaFree(t.counters);
-    cudaFree(t.sym); cudaFree(t.gidx); cudaFree(t.gar);
+    cudaFree(t.sym); cudaFree(t.gidx); cudaFree(t.gar); cudaFree(t.pll_tasks); cudaFree(t.agc_tasks); cudaFree(t.task_counts);
 }
 
 // Kernel sequences for captures [c0, c0+cnt) of the batch.  `head` = StaticGain, sample phases and the first
@@ -286,13 +292,24 @@ struct GroupLaunch {
         TiledArgs q = t;
         q.slow_pass = slow_pass;
         const int L = c->cc.L;
+        // work lists: fast pass of group `slot` -> first region, counters 2·slot; slow pass -> second region
+        const int slot = (gid >= 0 && gid < pdt_ctx::MAX_GROUPS) ? gid : pdt_ctx::MAX_GROUPS;
+        if (slow_pass) {
+            q.pll_tasks += (size_t)c->max_captures * q.pll_tasks_per_cap;
+            q.agc_tasks += (size_t)c->max_captures * q.agc_tasks_per_cap;
+        }
+        q.task_counts = c->ta.task_counts + 2 * (size_t)(slow_pass * (pdt_ctx::MAX_GROUPS + 1) + slot);
+        const unsigned ls_cap = 2u * (unsigned)std::max(c->sm_count, 1);          // resident CTAs of a persistent lane-stream launch
+        const unsigned pll_grid = std::min(blocks((u64)cnt * q.pll_tasks_per_cap, LS_WARPS), ls_cap);
+        const unsigned agc_grid = std::min(blocks((u64)cnt * q.agc_tasks_per_cap, LS_WARPS), ls_cap);
+        k_pll_tasks<<<blocks(cnt, 128), 128, 0, s>>>(q);
         if (q.pll.max_tiles > 1)
             k_estimate<<<blocks((u64)cnt * (q.pll.max_tiles - 1), EST_WARPS), EST_WARPS * 32, 0, s>>>(q);
         mark(s, "k_estimate");
-        k_pll_core<<<blocks((u64)cnt * q.pll.max_tiles, LS_WARPS * 32), LS_WARPS * 32, LS_SMEM, s>>>(q);
+        k_pll_core<<<pll_grid, LS_WARPS * 32, LS_SMEM, s>>>(q);
         mark(s, "k_pll_core");
-        k_pll_fix_par<<<blocks((u64)cnt * q.pll.max_tiles, LS_WARPS * 32), LS_WARPS * 32, LS_SMEM, s>>>(q);
-        k_pll_fix_par<<<blocks((u64)cnt * q.pll.max_tiles, LS_WARPS * 32), LS_WARPS * 32, LS_SMEM, s>>>(q);
+        k_pll_fix_par<<<pll_grid, LS_WARPS * 32, LS_SMEM, s>>>(q);
+        k_pll_fix_par<<<pll_grid, LS_WARPS * 32, LS_SMEM, s>>>(q);
         mark(s, "k_pll_fix_par");
         k_pll_fix<<<blocks(cnt, 128), 128, 0, s>>>(q);
         mark(s, "k_pll_fix");
@@ -308,9 +325,9 @@ struct GroupLaunch {
         mark(s, "k_front");
         k_agc_plan<<<blocks((u64)cnt * 32, 128), 128, 0, s>>>(q);
         mark(s, "k_agc_plan");
-        k_agc_core<<<blocks((u64)cnt * q.agc_max_tiles, LS_WARPS * 32), LS_WARPS * 32, LS_SMEM, s>>>(q);
+        k_agc_core<<<agc_grid, LS_WARPS * 32, LS_SMEM, s>>>(q);
         mark(s, "k_agc_core");
-        k_agc_fix_par<<<blocks((u64)cnt * q.agc_max_tiles, LS_WARPS * 32), LS_WARPS * 32, LS_SMEM, s>>>(q);
+        k_agc_fix_par<<<agc_grid, LS_WARPS * 32, LS_SMEM, s>>>(q);
         mark(s, "k_agc_fix_par");
         k_agc_fix<<<blocks(cnt, 128), 128, 0, s>>>(q);
         mark(s, "k_agc_fix");
@@ -318,7 +335,7 @@ struct GroupLaunch {
         mark(s, "k_gardner");
         k_bits<<<blocks(cnt, BITS_WARPS), BITS_WARPS * 32, 0, s>>>(q);
         mark(s, "k_bits");
-        count_launch(q.pll.max_tiles > 1 ? 12 : 11);
+        count_launch(q.pll.max_tiles > 1 ? 13 : 12);
     }
 };
 
@@ -338,6 +355,7 @@ static GroupLaunch make_group(pdt_ctx *c, const tiled::TiledArgs &base, uint32_t
     t.guess += (size_t)c0 * t.pll.max_tiles; t.pll_start += (size_t)c0 * t.pll.max_tiles; t.pll_end += (size_t)c0 * t.pll.max_tiles;
     t.agc_start += (size_t)c0 * t.agc_max_tiles; t.agc_end += (size_t)c0 * t.agc_max_tiles;
     t.sym += (size_t)c0 * t.sym_cap; t.gidx += (size_t)c0 * t.sym_cap; t.gar += c0;
+    t.pll_tasks += (size_t)c0 * t.pll_tasks_per_cap; t.agc_tasks += (size_t)c0 * t.agc_tasks_per_cap;
     t.stats += c0; t.frames += (size_t)c0 * c->max_frames;
     if (t.traces) t.traces += c0;
     return g;
@@ -366,6 +384,7 @@ static int tiled_run(pdt_ctx *c, const void *d_iq, int pcm16, uint32_t n_capture
     t.acq_first = (n_max > 2 * acq_first) ? acq_first : 0;
     const bool two_pass = t.acq_first != 0;
     PDT_CUDA(cudaMemsetAsync(t.counters, 0, 4 * sizeof(uint32_t), s));
+    PDT_CUDA(cudaMemsetAsync(t.task_counts, 0, 2 * (pdt_ctx::MAX_GROUPS + 1) * 2 * sizeof(uint32_t), s));
     c->n_marks = 0;
     uint32_t per = 0;
     const int groups = group_plan(n_captures, per);

@@ -21,6 +21,7 @@ namespace pdt {
 namespace tiled {
 
 struct GarRecord { u64 n_sym; float final_next; float pad; };
+struct LaneTask { uint32_t cap, k0; };      // one warp's work in a lane-stream kernel: tiles k0 … k0+31 of capture cap
 
 struct TiledArgs {
     ChainConst  cc;
@@ -41,6 +42,9 @@ struct TiledArgs {
     float       est_fmax;    // peak search limit (Hz)
     u64         acq_first;   // samples covered by the first acquisition pass (0 = whole capture in one pass)
     int         slow_pass;   // 0: kernels process the captures that latched in the first pass, 1: the slow ones
+    LaneTask   *pll_tasks, *agc_tasks;   // compact work lists of the persistent lane-stream kernels (built on the device)
+    uint32_t   *task_counts; // [0] PLL tasks, [1] AGC tasks
+    unsigned    pll_tasks_per_cap, agc_tasks_per_cap;
     float      *sym;         // [captures][sym_cap]     Gardner symbol stream
     u64        *gidx;        // [captures][sym_cap]     absolute interpolated-sample index of every pick
     GarRecord  *gar;         // [captures]
@@ -77,6 +81,25 @@ PDT_DEV TilePlan agc_plan(const TiledArgs &a, const AcqResult &acq)
     return p;
 }
 
+// tiles a capture has under a plan (tile_range() true for k = 0 … count-1)
+PDT_DEV unsigned tile_count(u64 first, u64 n, const TilePlan &p)
+{
+    if (first >= n) return 0;
+    const u64 a0 = (first + 3) & ~3ull;
+    u64 cnt = 1;
+    if (n > a0 + p.T0) cnt += 1 + (n - 1 - a0 - p.T0) / p.T;
+    return (unsigned)(cnt < p.max_tiles ? cnt : p.max_tiles);
+}
+
+// append ceil(tiles/32) warp tasks for capture `cap` to a work list (order is irrelevant)
+__device__ __forceinline__ void push_tasks(LaneTask *list, uint32_t *count, uint32_t cap, unsigned tiles)
+{
+    const unsigned nt = (tiles + 31) / 32;
+    if (nt == 0) return;
+    const uint32_t at = atomicAdd(count, nt);
+    for (unsigned i = 0; i < nt; i++) list[at + i] = LaneTask{cap, 32u * i};
+}
+
 __global__ void __launch_bounds__(128) k_agc_plan(const TiledArgs a)
 {
     const uint32_t cap = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -94,7 +117,21 @@ __global__ void __launch_bounds__(128) k_agc_plan(const TiledArgs a)
         for (u64 i = 0; i < len; i++) { sum += fabsf(y[b0 + i]); cnt++; }
     }
     for (int o = 16; o; o >>= 1) { sum += __shfl_xor_sync(0xffffffffu, sum, o); cnt += __shfl_xor_sync(0xffffffffu, cnt, o); }
-    if (lane == 0) a.acq[cap].agc_gain_est = (sum > 0.0f) ? (float)cnt / sum : a.acq[cap].norm;
+    if (lane == 0) {
+        AcqResult &acq = a.acq[cap];
+        acq.agc_gain_est = (sum > 0.0f) ? (float)cnt / sum : acq.norm;
+        push_tasks(a.agc_tasks, &a.task_counts[1], cap, tile_count(0, nL, agc_plan(a, acq)));
+    }
+}
+
+// work list of the PLL track kernels: one thread per capture
+__global__ void __launch_bounds__(128) k_pll_tasks(const TiledArgs a)
+{
+    const uint32_t cap = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cap >= a.n_captures || !cap_selected(a, cap)) return;
+    const AcqResult &acq = a.acq[cap];
+    if (!acq.locked) return;
+    push_tasks(a.pll_tasks, &a.task_counts[0], cap, tile_count(acq.track_begin, cap_len(a, cap), a.pll));
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -568,14 +605,8 @@ struct PllLaneStep {
     __device__ __forceinline__ float one(float v) { const float p = phase; pll_track_step(phase, freq, v, k); return p; }
 };
 
-__global__ void __launch_bounds__(LS_WARPS * 32) k_pll_core(const TiledArgs a)
+__device__ __forceinline__ void k_pll_core_task(const TiledArgs &a, LaneStream &sm, const int lane, const uint32_t cap, const unsigned k)
 {
-    extern __shared__ __align__(128) unsigned char ls_raw[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    LaneStream sm = lane_stream_init(&reinterpret_cast<LaneStreamSmem *>(ls_raw)[wib], lane);
-    const u64 gid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t cap = (uint32_t)(gid / a.pll.max_tiles);      // a warp = consecutive tiles of ONE capture: equal length,
-    const unsigned k = (unsigned)(gid % a.pll.max_tiles);         // same pages
     bool active = cap < a.n_captures && cap_selected(a, cap);
     u64 warm = 0, begin = 0, end = 0, mid = 0, keep = 0;
     PllLaneStep st; st.phase = 0.f; st.freq = 0.f; st.k = TrackConst{0.f, 0.f, 0.f, 0.f};
@@ -614,6 +645,19 @@ __global__ void __launch_bounds__(LS_WARPS * 32) k_pll_core(const TiledArgs a)
     if (active) a.pll_end[slot] = LoopState2{st.phase, st.freq};
 }
 
+// persistent: a fixed, resident grid of warps walks the compact work list (no CTA is launched for tiles that do not exist)
+__global__ void __launch_bounds__(LS_WARPS * 32) k_pll_core(const TiledArgs a)
+{
+    extern __shared__ __align__(128) unsigned char ls_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    LaneStream sm = lane_stream_init(&reinterpret_cast<LaneStreamSmem *>(ls_raw)[wib], lane);
+    const uint32_t n_tasks = a.task_counts[0];
+    for (uint32_t t = blockIdx.x * LS_WARPS + wib; t < n_tasks; t += gridDim.x * LS_WARPS) {
+        const LaneTask tk = a.pll_tasks[t];
+        k_pll_core_task(a, sm, lane, tk.cap, tk.k0 + (unsigned)lane);
+    }
+}
+
 PDT_DEV bool same_bits(const LoopState2 &x, const LoopState2 &y) { return pdt_f2u(x.a) == pdt_f2u(y.a) && pdt_f2u(x.b) == pdt_f2u(y.b); }
 
 PDT_DEV LoopState2 ld_state(const LoopState2 *p)
@@ -632,14 +676,8 @@ PDT_DEV void st_state(LoopState2 *p, const LoopState2 &v)
 // from that end state, all such tiles at once.  A predecessor that is itself being repaired in the same pass may
 // still change; the state actually used is recorded in pll_start, so the next pass (or the final serial sweep in
 // k_pll_fix) sees the difference.  Tiles converge long before their end, so one pass almost always suffices.
-__global__ void __launch_bounds__(LS_WARPS * 32) k_pll_fix_par(const TiledArgs a)
+__device__ __forceinline__ void k_pll_fix_par_task(const TiledArgs &a, LaneStream &sm, const int lane, const uint32_t cap, const unsigned k)
 {
-    extern __shared__ __align__(128) unsigned char ls_raw[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    LaneStream sm = lane_stream_init(&reinterpret_cast<LaneStreamSmem *>(ls_raw)[wib], lane);
-    const u64 gid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t cap = (uint32_t)(gid / a.pll.max_tiles);
-    const unsigned k = (unsigned)(gid % a.pll.max_tiles);
     bool active = cap < a.n_captures && k != 0 && cap_selected(a, cap);
     u64 warm = 0, begin = 0, end = 0;
     PllLaneStep st; st.phase = 0.f; st.freq = 0.f; st.k = TrackConst{0.f, 0.f, 0.f, 0.f};
@@ -663,6 +701,19 @@ __global__ void __launch_bounds__(LS_WARPS * 32) k_pll_fix_par(const TiledArgs a
         st_state(&a.pll_start[slot], truth);
         st_state(&a.pll_end[slot], LoopState2{st.phase, st.freq});
         atomicAdd(&a.counters[0], 1u);
+    }
+}
+
+// persistent: a fixed, resident grid of warps walks the compact work list (no CTA is launched for tiles that do not exist)
+__global__ void __launch_bounds__(LS_WARPS * 32) k_pll_fix_par(const TiledArgs a)
+{
+    extern __shared__ __align__(128) unsigned char ls_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    LaneStream sm = lane_stream_init(&reinterpret_cast<LaneStreamSmem *>(ls_raw)[wib], lane);
+    const uint32_t n_tasks = a.task_counts[0];
+    for (uint32_t t = blockIdx.x * LS_WARPS + wib; t < n_tasks; t += gridDim.x * LS_WARPS) {
+        const LaneTask tk = a.pll_tasks[t];
+        k_pll_fix_par_task(a, sm, lane, tk.cap, tk.k0 + (unsigned)lane);
     }
 }
 
@@ -796,14 +847,8 @@ __device__ __forceinline__ void agc_tile_warp(LaneStream &sm, const int lane, co
     mid_gain = gm; gain = g;
 }
 
-__global__ void __launch_bounds__(LS_WARPS * 32) k_agc_core(const TiledArgs a)
+__device__ __forceinline__ void k_agc_core_task(const TiledArgs &a, LaneStream &sm, const int lane, const uint32_t cap, const unsigned k)
 {
-    extern __shared__ __align__(128) unsigned char ls_raw[];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    LaneStream sm = lane_stream_init(&reinterpret_cast<LaneStreamSmem *>(ls_raw)[wib], lane);
-    const u64 gid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t cap = (uint32_t)(gid / a.agc_max_tiles);
-    const unsigned k = (unsigned)(gid % a.agc_max_tiles);
     const int L = a.cc.L;
     bool active = cap < a.n_captures && cap_selected(a, cap);
     u64 warm = 0, begin = 0, end = 0, first = 0;
@@ -835,14 +880,21 @@ __global__ void __launch_bounds__(LS_WARPS * 32) k_agc_core(const TiledArgs a)
     }
 }
 
-__global__ void __launch_bounds__(LS_WARPS * 32) k_agc_fix_par(const TiledArgs a)
+// persistent: a fixed, resident grid of warps walks the compact work list (no CTA is launched for tiles that do not exist)
+__global__ void __launch_bounds__(LS_WARPS * 32) k_agc_core(const TiledArgs a)
 {
     extern __shared__ __align__(128) unsigned char ls_raw[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     LaneStream sm = lane_stream_init(&reinterpret_cast<LaneStreamSmem *>(ls_raw)[wib], lane);
-    const u64 gid = (u64)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t cap = (uint32_t)(gid / a.agc_max_tiles);
-    const unsigned k = (unsigned)(gid % a.agc_max_tiles);
+    const uint32_t n_tasks = a.task_counts[1];
+    for (uint32_t t = blockIdx.x * LS_WARPS + wib; t < n_tasks; t += gridDim.x * LS_WARPS) {
+        const LaneTask tk = a.agc_tasks[t];
+        k_agc_core_task(a, sm, lane, tk.cap, tk.k0 + (unsigned)lane);
+    }
+}
+
+__device__ __forceinline__ void k_agc_fix_par_task(const TiledArgs &a, LaneStream &sm, const int lane, const uint32_t cap, const unsigned k)
+{
     const int L = a.cc.L;
     bool active = cap < a.n_captures && k != 0 && cap_selected(a, cap);
     u64 warm = 0, begin = 0, end = 0, first = 0;
@@ -868,6 +920,19 @@ __global__ void __launch_bounds__(LS_WARPS * 32) k_agc_fix_par(const TiledArgs a
         st_state(&a.agc_start[slot], truth);
         st_state(&a.agc_end[slot], LoopState2{gain, 0.0f});
         atomicAdd(&a.counters[1], 1u);
+    }
+}
+
+// persistent: a fixed, resident grid of warps walks the compact work list (no CTA is launched for tiles that do not exist)
+__global__ void __launch_bounds__(LS_WARPS * 32) k_agc_fix_par(const TiledArgs a)
+{
+    extern __shared__ __align__(128) unsigned char ls_raw[];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    LaneStream sm = lane_stream_init(&reinterpret_cast<LaneStreamSmem *>(ls_raw)[wib], lane);
+    const uint32_t n_tasks = a.task_counts[1];
+    for (uint32_t t = blockIdx.x * LS_WARPS + wib; t < n_tasks; t += gridDim.x * LS_WARPS) {
+        const LaneTask tk = a.agc_tasks[t];
+        k_agc_fix_par_task(a, sm, lane, tk.cap, tk.k0 + (unsigned)lane);
     }
 }
 
