@@ -509,11 +509,13 @@ __global__ void __launch_bounds__(ACQ_THREADS) k_acquire(const TiledArgs a, cons
 // ---------------------------------------------------------------------------------------------------
 // carrier guess per tile: warp per (capture, tile >= 1)
 // ---------------------------------------------------------------------------------------------------
-constexpr int EST_WARPS = 4;
+constexpr int EST_WARPS = 2;
+constexpr int EST_MAX_D = 24;          // staged (coalesced) decimation up to this factor (6 KB per warp), direct strided reads beyond
 
 __global__ void __launch_bounds__(EST_WARPS * 32) k_estimate(const TiledArgs a)
 {
     __shared__ float2 zs[EST_WARPS][EST_FFT];
+    __shared__ float2 stage[EST_WARPS][32 * EST_MAX_D];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const unsigned per_cap = a.pll.max_tiles - 1;
     const u64 wid = (u64)blockIdx.x * EST_WARPS + wib;
@@ -527,15 +529,32 @@ __global__ void __launch_bounds__(EST_WARPS * 32) k_estimate(const TiledArgs a)
     float2 *z = zs[wib];
     const int D = a.est_decim;
     const long long w0 = (long long)warm - (long long)EST_FFT * D;
-    // decimate by block sums, store bit-reversed
-    for (int j = lane; j < EST_FFT; j += 32) {
-        float sr = 0.f, si = 0.f;
-        const long long b0 = w0 + (long long)j * D;
-        for (int d = 0; d < D; d++) {
-            const long long i = b0 + d;
-            if (i >= 0) { float p, q; load_iq1(a.iq, a.pcm16, first + (u64)i, p, q); sr += p; si += q; }
+    // decimate by block sums, store bit-reversed.  The warp reads 32·D consecutive samples at a time (coalesced) into a
+    // staging tile and lane j sums its own D of them: read directly, lane j's samples are D·8 bytes apart from lane j+1's
+    // and every 32-byte sector fetched from HBM would be used for one 8-byte sample.
+    float2 *stg = stage[wib];
+    for (int blk = 0; blk < EST_FFT / 32; blk++) {
+        const long long b0 = w0 + (long long)blk * 32 * D;
+        if (D <= EST_MAX_D) {
+            for (int t = lane; t < 32 * D; t += 32) {
+                const long long i = b0 + t;
+                float p = 0.f, q = 0.f;
+                if (i >= 0) load_iq1(a.iq, a.pcm16, first + (u64)i, p, q);
+                stg[t] = make_float2(p, q);
+            }
+            __syncwarp();
+            float sr = 0.f, si = 0.f;
+            for (int d = 0; d < D; d++) { const float2 v = stg[lane * D + d]; sr += v.x; si += v.y; }
+            z[__brev((unsigned)(blk * 32 + lane)) >> 22] = make_float2(sr, si);
+            __syncwarp();
+        } else {
+            float sr = 0.f, si = 0.f;
+            for (int d = 0; d < D; d++) {
+                const long long i = b0 + (long long)lane * D + d;
+                if (i >= 0) { float p, q; load_iq1(a.iq, a.pcm16, first + (u64)i, p, q); sr += p; si += q; }
+            }
+            z[__brev((unsigned)(blk * 32 + lane)) >> 22] = make_float2(sr, si);
         }
-        z[__brev((unsigned)j) >> 22] = make_float2(sr, si);
     }
     __syncwarp();
     for (int len = 2; len <= EST_FFT; len <<= 1) {
