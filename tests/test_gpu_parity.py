@@ -305,6 +305,48 @@ def test_tiled_stream_groups_equal_exact_engine(torch_cuda, acq_first):
     assert np.array_equal(fe, ft)
 
 
+def test_config1_single_10M_sample_stream_bit_exact_frames(torch_cuda, oracle32):
+    """BASELINE configs[1]: one 10 M-sample capture @ 250 ksps (40 s, ~400 minor frames, ~300 PLL tiles, Doppler drift) on
+    one GPU: counts, lock sample and every frame byte equal to the CPU oracle."""
+    fs, n = 250000, 10_000_000
+    pcm, info = make_poes_capture(n, fs, 77, esn0_db=13.0, doppler_hz=-1800.0, drift_hz_s=40.0, amplitude=0.15)
+    want = oracle32.chain(oracle32.pcm16_to_complex(pcm), fs)
+    p = pdt.default_params("f32", pdt.PDT_MODE_POES, fs)
+    d = pdt.Demod("f32", p, 1, n, 512)
+    assert d.engine == pdt.PDT_ENGINE_TILED
+    st, fr = d.demod_host(pcm, 1, pcm16=True)
+    assert want["total_frames"] >= 390
+    assert (st[0]["n_symbols"], st[0]["n_bits"], st[0]["n_frames"]) == (want["total_symbols"], want["total_bits"], want["total_frames"])
+    assert st[0]["locked"] == 1 and st[0]["lock_sample"] == want["lock_sample"]
+    text = d.format_frames(fr[0], int(st[0]["n_frames"]))
+    _frames_text_equal_bytes(text, want["text"])
+    full = [f for f in parse_frames_text(text) if f[2].size == 104]
+    cnt = [frame_counter(f[2]) for f in full]
+    assert all((b - a) % 320 == 1 for a, b in zip(cnt, cnt[1:]))          # no minor frame lost across ~300 tile seams
+    q = d.frame_checks(1)[0]
+    assert q["valid"].sum() == len(full) and q["parity_ok"][q["valid"] == 1].mean() > 0.98
+
+
+def test_config2_argos_batch_of_bursts(torch_cuda, oracle64):
+    """BASELINE configs[2] shape: many synthetic 401.65 MHz ARGOS bursts as independent double-precision captures in one
+    batch (exact engine): packets and counts of every capture equal to the CPU oracle."""
+    caps, n = 12, 40_000
+    iq = np.zeros((caps, n, 2), np.float64)
+    wants = []
+    for c in range(caps):
+        pcm, _ = make_argos_capture(n, 5000.0, seed=40 + c, n_bursts=2, snr_db=14.0 + c)
+        x = oracle64.pcm16_to_complex(pcm)
+        iq[c] = x.reshape(-1, 2)
+        wants.append(oracle64.chain(x, 5000, argos=True))
+    p = pdt.default_params("f64", pdt.PDT_MODE_ARGOS, 5000)
+    d = pdt.Demod("f64", p, caps, n, 16)
+    st, fr = d.demod_host(iq, caps)
+    assert sum(w["total_frames"] for w in wants) >= caps
+    for c, w in enumerate(wants):
+        assert (st[c]["n_symbols"], st[c]["n_bits"], st[c]["n_frames"]) == (w["total_symbols"], w["total_bits"], w["total_frames"]), c
+        _frames_text_equal_bytes(d.format_frames(fr[c], int(st[c]["n_frames"])), w["text"])
+
+
 def test_async_host_api_contexts_in_rotation(torch_cuda):
     """pdt_demod_host_async + pdt_fetch with two contexts used in rotation on two streams (what bench.py's e2e leg does):
     every batch must give exactly the synchronous pdt_demod_host result, whatever overlaps with it."""
