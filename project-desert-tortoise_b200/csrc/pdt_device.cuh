@@ -23,7 +23,7 @@ typedef double real_t;
 #define PDT_MAX_PHASE_TAPS 64   // taps per polyphase branch (N / L); the reference uses 26 (main.c:104) or 50
 
 // Every stage function is __host__ __device__: the device build is the product; the host build of the very same
-// code is used only by tests/host_emul (CPU emulation of the tiled engine's logic, checked against the oracle).
+// code is used only by host-side study tools (tools/acq_study.cu: CPU emulation of the recurrences).
 #define PDT_DEV __host__ __device__ __forceinline__
 
 #include <cmath>

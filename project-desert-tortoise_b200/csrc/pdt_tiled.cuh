@@ -12,7 +12,7 @@
 //   AGC.c:98-131 (NormalizingAGC), AGC.c:48-75 (StaticGain), GardenerClockRecovery.c:24-111,
 //   ManchesterDecode.c:27-97, POESTIPdemod/ByteSync.c:42-148; driver loop POESTIPdemod/main.c:373-482.
 //
-// Everything that decides a result is __host__ __device__ so that tests/host_emul can run the very same
+// Everything that decides a result is __host__ __device__ so that host-side study tools (tools/acq_study.cu) run the very same
 // arithmetic on the CPU against the oracle; the kernels below only map work items to threads.
 #pragma once
 
