@@ -197,7 +197,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-single", action="store_true")
-    ap.add_argument("--inflight", type=int, default=3,
+    ap.add_argument("--inflight", type=int, default=4,
                     help="batches in flight: consecutive steps alternate between this many contexts/streams, so the serial "
                          "acquisition tail of one batch overlaps the bulk kernels of the next (1 = strictly one batch at a time)")
     ap.add_argument("--cpu-captures", type=int, default=0)

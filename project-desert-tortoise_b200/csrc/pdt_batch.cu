@@ -137,7 +137,7 @@ struct pdt_ctx {
     size_t      stage_bytes = 0;
     int         device = 0, sm_count = 0;
     int         engine = PDT_ENGINE_EXACT;
-    static constexpr int MAX_GROUPS = 5;      // + slow-capture stream + staging stream + the caller's = the 8 hardware queues
+    static constexpr int MAX_GROUPS = 5;      // upper bound; the default in use is 3 (group_plan): with 4 batches in flight, 4·(3 + slow) + callers stay within the 32 hardware queues
     cudaStream_t h2d_stream = nullptr;       // chunked staging of pdt_demod_host
     cudaEvent_t  ev_h2d[MAX_GROUPS] = {}, ev_done = nullptr;
 #if PDT_USE_FLOATS
@@ -160,7 +160,7 @@ static int group_plan(uint32_t n_captures, uint32_t &per)
     static int max_groups = 0;                        // PDT_MAX_GROUPS: experiment knob (default: pdt_ctx::MAX_GROUPS)
     if (max_groups == 0) {
         const char *e = getenv("PDT_MAX_GROUPS");
-        max_groups = e ? std::max(1, std::min(atoi(e), (int)pdt_ctx::MAX_GROUPS)) : (int)pdt_ctx::MAX_GROUPS;
+        max_groups = e ? std::max(1, std::min(atoi(e), (int)pdt_ctx::MAX_GROUPS)) : 3;
     }
     const int groups = (int)std::min<uint32_t>((uint32_t)max_groups, (n_captures + 63) / 64);
     per = groups > 0 ? (n_captures + groups - 1) / groups : n_captures;
@@ -380,7 +380,9 @@ static int tiled_run(pdt_ctx *c, const void *d_iq, int pcm16, uint32_t n_capture
     if (n_samples) { n_max = 0; for (uint32_t i = 0; i < n_captures; i++) n_max = std::max<u64>(n_max, n_samples[i]); }
     if (n_max == 0) return PDT_OK;
     const int L = c->cc.L;
-    const u64 acq_first = c->params.acq_first ? c->params.acq_first : 131072;
+    static u64 acq_env = 0;                           // PDT_ACQ_FIRST: experiment knob
+    if (acq_env == 0) { const char *e = getenv("PDT_ACQ_FIRST"); acq_env = e ? (u64)atoll(e) : 131072; if (acq_env < 1024) acq_env = 131072; }
+    const u64 acq_first = c->params.acq_first ? c->params.acq_first : acq_env;
     t.acq_first = (n_max > 2 * acq_first) ? acq_first : 0;
     const bool two_pass = t.acq_first != 0;
     PDT_CUDA(cudaMemsetAsync(t.counters, 0, 4 * sizeof(uint32_t), s));
