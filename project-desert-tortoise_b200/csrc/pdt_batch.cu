@@ -195,7 +195,7 @@ static int tiled_setup(pdt_ctx *c)
     // constants take a (2 Hz, 0.2 rad) carrier guess down to a bit-identical state (measured).
     u64 W = c->params.pll_warm ? c->params.pll_warm : (u64)(17.0 / (double)cc.pll.bw_track);
     W = (W + 3) & ~3ull; if (W < 1024) W = 1024;
-    u64 T = c->params.pll_tile ? c->params.pll_tile : W / 2;
+    u64 T = c->params.pll_tile ? c->params.pll_tile : W;
     T = (T + 3) & ~3ull; if (T < 1024) T = 1024;
     t.pll.W = W; t.pll.T = T; t.pll.T0 = W + T;
     t.pll.max_tiles = 1 + (unsigned)((stride + T - 1) / T);

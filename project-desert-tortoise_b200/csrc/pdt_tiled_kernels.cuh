@@ -201,8 +201,9 @@ __global__ void __launch_bounds__(256) k_sp(const TiledArgs a)
 // ---------------------------------------------------------------------------------------------------
 constexpr int ACQ_B = 256;            // samples per pipeline block
 constexpr int ACQ_RING = 4;           // blocks in flight: core | terms | EMAs | decisions
-constexpr int ACQ_THREADS = 256;
-constexpr int ACQ_THREADS_SLOW = 128; // second pass: the few slow captures hold their CTA for tens of ms — a thinner CTA (one helper warp) halves the
+constexpr int ACQ_SERIAL = 64;        // warp 0: the core lane; warp 1: the two EMA lanes (same code, own data)
+constexpr int ACQ_THREADS = 224;      // 2 serial warps + 5 helper warps
+constexpr int ACQ_THREADS_SLOW = 96;  // second pass: the few slow captures hold their CTA for tens of ms — a thinner CTA (one helper warp) halves the
                                       // registers they pin down while several batches are in flight
 
 struct __align__(16) AcqSmem {
@@ -314,7 +315,7 @@ __global__ void __launch_bounds__(ACQ_THREADS) k_acquire(const TiledArgs a, cons
 {
     unsigned long long pf_steps = 0, pf_cyc = 0, pf_busy = 0, pf_dec = 0, pf_epochs = 0;
     __shared__ AcqSmem s;
-    const int n_threads = (int)blockDim.x, n_helpers = n_threads - 96;     // 3 serial warps + the helper warps
+    const int n_threads = (int)blockDim.x, n_helpers = n_threads - ACQ_SERIAL;     // 2 serial warps + the helper warps
     const uint32_t cap = blockIdx.x;
     const int tid = threadIdx.x;
     const u64 n = cap_len(a, cap), first = (u64)cap * a.stride;
@@ -354,7 +355,7 @@ __global__ void __launch_bounds__(ACQ_THREADS) k_acquire(const TiledArgs a, cons
     float e_phase = ps.phase, e_freq = ps.freq, e_sweep = ps.sweep, e_avg = ps.avg_phase, e_lks = ps.locksig;
     bool flag = acq_noise_like(e_avg) != 0;                  // true for the initial avg_phase = π/2
     int spec_n = 0;                                          // samples of the epoch's block 0 that carry a per-sample prediction
-    const int hid = tid - 96;                                // helper index (warps 3..7), < 0 for the three serial warps
+    const int hid = tid - ACQ_SERIAL;                        // helper index (warps 2..), < 0 for the two serial warps
 
     // (A ramp of small blocks after a flag flip was tried and lost: a step has ~4k cycles of fixed cost, profiles/README.md r01f.)
     auto block_off = [&](long long j) -> u64 { return (u64)j * (u64)ACQ_B; };
@@ -395,12 +396,15 @@ __global__ void __launch_bounds__(ACQ_THREADS) k_acquire(const TiledArgs a, cons
                     else           acq_core<false>(s.ph[slot], s.fr[slot], s.sw[slot], s.sp[slot], c_core, p, f, w, kacq);
                 }
                 s.mism[st & 1] = ACQ_B + 1; s.latch[st & 1] = ACQ_B + 1;
-            } else if (tid == 32 || tid == 64) {
+            } else if (tid == 32 || tid == 33) {
+                // the two EMA chains run on two lanes of ONE warp: same code, own data — one warp instruction serves both
                 if (c_ema) {
                     const int slot = (int)((st - 2) % ACQ_RING), prev = (int)((st - 3 + ACQ_RING) % ACQ_RING);
-                    const int pc = block_cnt(st - 3);
-                    if (tid == 32) acq_ema(s.avg[slot], s.aterm[slot], c_ema, (st == 2) ? e_avg : s.avg[prev][pc], c_avg);     // :124
-                    else           acq_ema(s.lks[slot], s.lterm[slot], c_ema, (st == 2) ? e_lks : s.lks[prev][pc], c_lks);     // :220
+                    const bool is_avg = tid == 32;
+                    float *out = is_avg ? s.avg[slot] : s.lks[slot];
+                    const float *term = is_avg ? s.aterm[slot] : s.lterm[slot];
+                    const float x0e = (st == 2) ? (is_avg ? e_avg : e_lks) : (is_avg ? s.avg[prev][ACQ_B] : s.lks[prev][ACQ_B]);
+                    acq_ema(out, term, c_ema, x0e, is_avg ? c_avg : c_lks);                  // :124 / :220
                 }
             } else if (hid >= 0) {
                 if (c_term) {                                                        // [A],[D] feed-forward parts of block st-1
@@ -440,7 +444,7 @@ __global__ void __launch_bounds__(ACQ_THREADS) k_acquire(const TiledArgs a, cons
                 if (pass == 1) {
                     if (tid == 0)  { atomicAdd(&g_acq_prof[0], pf_steps); atomicAdd(&g_acq_prof[1], pf_cyc); atomicAdd(&g_acq_prof[2], pf_busy); atomicAdd(&g_acq_prof[6], pf_epochs); }
                     if (tid == 32) atomicAdd(&g_acq_prof[3], pf_busy);
-                    if (tid == 96) { atomicAdd(&g_acq_prof[4], pf_busy); atomicAdd(&g_acq_prof[5], pf_dec); }
+                    if (tid == ACQ_SERIAL) { atomicAdd(&g_acq_prof[4], pf_busy); atomicAdd(&g_acq_prof[5], pf_dec); }
                 }
             };
             if (c_dec) {
@@ -476,7 +480,7 @@ __global__ void __launch_bounds__(ACQ_THREADS) k_acquire(const TiledArgs a, cons
                     const float np_ = s.ph[slot][mism], nf = s.fr[slot][mism], nw = s.sw[slot][mism];
                     const float na = s.avg[slot][mism], nl_ = s.lks[slot][mism];
                     const int nspec = c_dec - mism;
-                    unsigned char mine[2] = {0, 0};
+                    unsigned char mine[4] = {0, 0, 0, 0};              // ceil(ACQ_B / smallest CTA) entries
                     for (int i = tid, q = 0; i < nspec; i += n_threads, q++) mine[q] = acq_noise_like(s.avg[slot][mism + i + 1]);
                     const bool tail = acq_noise_like(s.avg[slot][c_dec]) != 0;
                     __syncthreads();
