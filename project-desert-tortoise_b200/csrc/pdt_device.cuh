@@ -72,9 +72,23 @@ PDT_DEV double r_rint(double x) { return rint(x); }
 // sine / cosine kernels on the reduced argument (s_sincosf.h: sincosf_poly).  Both are evaluated for every sample and
 // swapped / negated afterwards: IEEE +,× are sign-symmetric, so sin_poly(-x) == -sin_poly(x) and a cosine evaluated with
 // the negated coefficient set (glibc's second table entry) is the negated cosine, bit for bit — no per-lane branches.
+#ifdef __CUDACC__
+// the polynomial / reduction constants live in the constant bank: a DMUL/DADD takes them as c[bank][offset] operands,
+// where immediates would be rebuilt in uniform registers (two UMOVs per constant) for every sample
+__constant__ double pdt_sc_tab[10] = {
+    -0x1.555545995a603p-3, 0x1.1107605230bc4p-7, -0x1.994eb3774cf24p-13,                                  // s1 s2 s3
+    -0x1.ffffffd0c621cp-2, 0x1.55553e1068f19p-5, -0x1.6c087e89a359dp-10, 0x1.99343027bf8c3p-16,           // c1 c2 c3 c4
+    0x1.45F306DC9C883p+23, 0x1.921FB54442D18p0, 0x1p0 };                                                  // 2^24·2/π, π/2, 1
+#endif
+#ifdef __CUDA_ARCH__
+#define PDT_SC(i, lit) pdt_sc_tab[i]
+#else
+#define PDT_SC(i, lit) (lit)
+#endif
+
 PDT_DEV double sc_sin_poly(double x, double x2)
 {
-    const double s1 = -0x1.555545995a603p-3, s2 = 0x1.1107605230bc4p-7, s3 = -0x1.994eb3774cf24p-13;
+    const double s1 = PDT_SC(0, -0x1.555545995a603p-3), s2 = PDT_SC(1, 0x1.1107605230bc4p-7), s3 = PDT_SC(2, -0x1.994eb3774cf24p-13);
     const double x3 = x * x2;
     const double t1 = s2 + x2 * s3;
     const double x7 = x3 * x2;
@@ -83,8 +97,8 @@ PDT_DEV double sc_sin_poly(double x, double x2)
 }
 PDT_DEV double sc_cos_poly(double x2)
 {
-    const double c0 = 0x1p0, c1 = -0x1.ffffffd0c621cp-2, c2 = 0x1.55553e1068f19p-5,
-                 c3 = -0x1.6c087e89a359dp-10, c4 = 0x1.99343027bf8c3p-16;
+    const double c0 = PDT_SC(9, 0x1p0), c1 = PDT_SC(3, -0x1.ffffffd0c621cp-2), c2 = PDT_SC(4, 0x1.55553e1068f19p-5),
+                 c3 = PDT_SC(5, -0x1.6c087e89a359dp-10), c4 = PDT_SC(6, 0x1.99343027bf8c3p-16);
     const double x4 = x2 * x2;
     const double t2 = c3 + x2 * c4;
     const double t1 = c0 + x2 * c1;
@@ -101,7 +115,7 @@ PDT_DEV void sincos_exact(float y, float &s, float &c)
     // glibc's three ranges collapse into its general path: for |y| < π/4 the quadrant is n = 0 and the reduction x - 0·(π/2)
     // is exact, which is its small-argument path; its |y| < 2^-12 shortcut (s = y, c = 1) is applied as a select at the end.
     const double x = (double)y;
-    const double hpi_inv = 0x1.45F306DC9C883p+23, hpi = 0x1.921FB54442D18p0;
+    const double hpi_inv = PDT_SC(7, 0x1.45F306DC9C883p+23), hpi = PDT_SC(8, 0x1.921FB54442D18p0);
     const double r = x * hpi_inv;
     const int n = (pdt_d2i_rz(r) + 0x800000) >> 24;
     const double xr = x - (double)n * hpi;

@@ -783,18 +783,44 @@ __global__ void __launch_bounds__(FRONT_THREADS) k_front(const TiledArgs a, cons
     if (base >= n || !cap_selected(a, cap)) return;
     const float *ph = a.ph + (u64)cap * a.ws_stride;
     const pdt_traces *tr = a.traces ? &a.traces[cap] : nullptr;
-    for (int idx = tid; idx < FRONT_SPAN + FIR_K; idx += FRONT_THREADS) {
-        const long long i = (long long)base - FIR_K + idx;
-        float o = 0.0f;
-        if (i >= 0 && (u64)i < n) {
-            float p, q, ti, tr_;
-            load_iq1(a.iq, a.pcm16, first + (u64)i, p, q);
-            sincos_exact(ph[i], ti, tr_);
-            const float nti = -ti;
-            o = p * nti + q * tr_;                                                  // :110,:113
-            if (tr && tr->pll_out && idx >= FIR_K) reinterpret_cast<float *>(tr->pll_out)[i] = o;
+    {
+        // staging pass: sample i = base - FIR_K + idx, valid for idx in [lo, hi); everything is addressed from per-CTA bases
+        // with 32-bit offsets, the (rare) trace pointer is fetched once
+        const int lo = (base >= (u64)FIR_K) ? 0 : (FIR_K - (int)base);
+        const u64 left = n - base;                                              // >= 1
+        const int hi = (left + FIR_K < (u64)(FRONT_SPAN + FIR_K)) ? (int)(left + FIR_K) : (FRONT_SPAN + FIR_K);
+        const float *ph_b = ph + base - FIR_K;                                  // only dereferenced at idx >= lo
+        float *trace_out = (tr && tr->pll_out) ? reinterpret_cast<float *>(tr->pll_out) + base - FIR_K : nullptr;
+        if (a.pcm16) {
+            const short2 *iq_b = reinterpret_cast<const short2 *>(a.iq) + first + base - FIR_K;
+            for (int idx = tid; idx < FRONT_SPAN + FIR_K; idx += FRONT_THREADS) {
+                float o = 0.0f;
+                if (idx >= lo && idx < hi) {
+                    const short2 v = iq_b[idx];
+                    const float p = v.x / 32768.0f, q = v.y / 32768.0f;
+                    float ti, tr_;
+                    sincos_exact(ph_b[idx], ti, tr_);
+                    const float nti = -ti;
+                    o = p * nti + q * tr_;                                          // :110,:113
+                    if (trace_out && idx >= FIR_K) trace_out[idx] = o;
+                }
+                outs[idx] = o;
+            }
+        } else {
+            const float2 *iq_b = reinterpret_cast<const float2 *>(a.iq) + first + base - FIR_K;
+            for (int idx = tid; idx < FRONT_SPAN + FIR_K; idx += FRONT_THREADS) {
+                float o = 0.0f;
+                if (idx >= lo && idx < hi) {
+                    const float2 v = iq_b[idx];
+                    float ti, tr_;
+                    sincos_exact(ph_b[idx], ti, tr_);
+                    const float nti = -ti;
+                    o = v.x * nti + v.y * tr_;                                      // :110,:113
+                    if (trace_out && idx >= FIR_K) trace_out[idx] = o;
+                }
+                outs[idx] = o;
+            }
         }
-        outs[idx] = o;
     }
     __syncthreads();
     {
