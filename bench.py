@@ -188,8 +188,8 @@ class _Raw:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=6)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--captures", type=int, default=1024, help="captures per GPU")
     ap.add_argument("--samples", type=int, default=1_000_000, help="IQ samples per capture")
@@ -197,9 +197,10 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-single", action="store_true")
-    ap.add_argument("--inflight", type=int, default=4,
+    ap.add_argument("--inflight", type=int, default=0,
                     help="batches in flight: consecutive steps alternate between this many contexts/streams, so the serial "
-                         "acquisition tail of one batch overlaps the bulk kernels of the next (1 = strictly one batch at a time)")
+                         "acquisition tail of one batch overlaps the bulk kernels of the next (1 = strictly one batch at a time; "
+                         "0 = 4, or 3 for runs of fewer than 8 steps where the ramp-up of a fourth batch costs more than it brings)")
     ap.add_argument("--cpu-captures", type=int, default=0)
     ap.add_argument("--ref-captures", type=int, default=0)
     ap.add_argument("--ref-samples", type=int, default=1_000_000)
@@ -237,7 +238,8 @@ def main():
     ds, df, _ = d.result_tables()
     frames_t = torch.as_tensor(_Raw(df, C_ * max_frames * 120), device="cuda").view(C_, max_frames * 120)
     # batches in flight: context k (own workspaces, own internal streams) on side stream k; joined to the main stream at the end
-    inflight = max(1, args.inflight)
+    inflight = args.inflight if args.inflight > 0 else (4 if args.steps >= 8 else 3)
+    inflight = max(1, min(inflight, max(args.steps, 1)))
     ctxs = [d] + [pdt.Demod("f32", params, C_, n, max_frames) for _ in range(inflight - 1)]
     tables = [frames_t] + [torch.as_tensor(_Raw(c.result_tables()[1], C_ * max_frames * 120), device="cuda").view(C_, max_frames * 120)
                            for c in ctxs[1:]]
@@ -419,7 +421,7 @@ def main():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
-        e2e_steps = max(4, min(args.steps, 6))
+        e2e_steps = max(4, min(args.steps, 8))
         tt0 = time.perf_counter()
         st_last = e2e_run(e2e_steps)
         torch.cuda.synchronize()
