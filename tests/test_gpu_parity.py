@@ -408,6 +408,24 @@ def test_frame_post_checks_on_device(torch_cuda, golden_dir):
     assert not q[nf:]["valid"].any()
 
 
+def test_frame_table_overflow_same_in_both_engines(torch_cuda):
+    """More frames than max_frames slots: both engines count every accepted sync word but store only the first slots —
+    identical tables, including the trailing partial frame bookkeeping."""
+    fs, n = 250000, 400_000
+    pcm, _ = make_poes_capture(n, fs, 61, esn0_db=16.0, doppler_hz=900.0, amplitude=0.3)
+    res = {}
+    for eng in ("exact", "tiled"):
+        p = pdt.default_params("f32", pdt.PDT_MODE_POES, fs)
+        p.engine = ENGINES[eng]
+        d = pdt.Demod("f32", p, 1, n, 3)
+        res[eng] = d.demod_host(pcm, 1, pcm16=True)
+    (se, fe), (st, ft) = res["exact"], res["tiled"]
+    assert se[0]["n_frames"] > 3
+    for k in ("n_symbols", "n_bits", "n_frames", "lock_sample"):
+        assert se[0][k] == st[0][k], k
+    assert np.array_equal(fe, ft)
+
+
 def test_poes_golden_synth_c2(torch_cuda, golden_dir):
     g = np.load(_golden(golden_dir, "synth_poes_c2_small.npz"))
     p = pdt.default_params("f32", pdt.PDT_MODE_POES, int(g["fs"]))
