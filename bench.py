@@ -186,6 +186,7 @@ class _Raw:
 
 
 def main():
+    global FS
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -193,6 +194,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--captures", type=int, default=1024, help="captures per GPU")
     ap.add_argument("--samples", type=int, default=1_000_000, help="IQ samples per capture")
+    ap.add_argument("--fs", type=int, default=FS, help="sample rate: 250000 -> L=1 (headline), 75000 -> 2, 50000 -> 3, 37500 -> 4 "
+                                                       "(tiled engine), 18750 -> the historical 8x interpolator (exact engine)")
     ap.add_argument("--pcm16", action="store_true", help="feed int16 PCM (4 B/sample) instead of cf32")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -205,6 +208,7 @@ def main():
     ap.add_argument("--ref-captures", type=int, default=0)
     ap.add_argument("--ref-samples", type=int, default=1_000_000)
     args = ap.parse_args()
+    FS = args.fs
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     if args.impl == "reference":
         return reference_arm(args)

@@ -169,6 +169,14 @@ static int group_plan(uint32_t n_captures, uint32_t &per)
 
 #if PDT_USE_FLOATS
 // ---- tiled engine: eligibility, workspace, launch sequence -----------------------------------------------
+typedef void (*FrontKernel)(const tiled::TiledArgs, const tiled::TapsRev);
+static FrontKernel front_kernel(int L)          // one instantiation per interpolation factor the reference can choose (main.c:354)
+{
+    static const FrontKernel k[tiled::FIR_MAX_L] = {tiled::k_front<1>, tiled::k_front<2>, tiled::k_front<3>, tiled::k_front<4>,
+                                                    tiled::k_front<5>, tiled::k_front<6>, tiled::k_front<7>, tiled::k_front<8>};
+    return k[L - 1];
+}
+
 static bool tiled_applicable(const pdt_params &p, const ChainConst &cc, uint32_t max_captures)
 {
     if (cc.argos || cc.L < 1 || cc.L > tiled::FIR_MAX_L || cc.N != tiled::FIR_K * cc.L) return false;
@@ -234,9 +242,8 @@ static int tiled_setup(pdt_ctx *c)
     }
 #undef TA
     for (int u = 0; u < cc.N; u++) c->taps_rev.hr[u] = c->taps_h[cc.N - 1 - u];
-    c->front_smem = sizeof(float) * ((size_t)FRONT_SPAN + FIR_K + 2 + (size_t)FRONT_SPAN * cc.L);
-    void (*kf)(const TiledArgs, const TapsRev) = cc.L == 1 ? k_front<1> : cc.L == 2 ? k_front<2> : cc.L == 3 ? k_front<3> : k_front<4>;
-    if ((e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->front_smem)) != cudaSuccess)
+    c->front_smem = front_smem_bytes(cc.L);
+    if ((e = cudaFuncSetAttribute(front_kernel(cc.L), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->front_smem)) != cudaSuccess)
         return fail(PDT_ECUDA, "cudaFuncSetAttribute(k_front): %s", cudaGetErrorString(e));
     for (void (*kl)(const TiledArgs) : {k_pll_core, k_pll_fix_par, k_agc_core, k_agc_fix_par})
         if ((e = cudaFuncSetAttribute(kl, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LS_SMEM)) != cudaSuccess)
@@ -314,13 +321,8 @@ struct GroupLaunch {
         k_pll_fix<<<blocks(cnt, 128), 128, 0, s>>>(q);
         mark(s, "k_pll_fix");
         {
-            dim3 g(blocks(n_max, FRONT_SPAN), cnt);
-            switch (L) {
-            case 1: k_front<1><<<g, FRONT_THREADS, c->front_smem, s>>>(q, c->taps_rev); break;
-            case 2: k_front<2><<<g, FRONT_THREADS, c->front_smem, s>>>(q, c->taps_rev); break;
-            case 3: k_front<3><<<g, FRONT_THREADS, c->front_smem, s>>>(q, c->taps_rev); break;
-            default: k_front<4><<<g, FRONT_THREADS, c->front_smem, s>>>(q, c->taps_rev); break;
-            }
+            dim3 g(blocks(n_max, front_span(L)), cnt);
+            front_kernel(L)<<<g, front_threads(L), c->front_smem, s>>>(q, c->taps_rev);
         }
         mark(s, "k_front");
         k_agc_plan<<<blocks((u64)cnt * 32, 128), 128, 0, s>>>(q);
@@ -582,7 +584,7 @@ pdt_ctx *pdt_create(const pdt_params *p, uint32_t max_captures, uint64_t max_sam
     if (c->params.engine != PDT_ENGINE_EXACT && tiled_applicable(c->params, c->cc, max_captures)) c->engine = PDT_ENGINE_TILED;
 #endif
     if (c->params.engine == PDT_ENGINE_TILED && c->engine != PDT_ENGINE_TILED) {
-        fail(PDT_EINVAL, "the tiled engine needs the float POES chain with 1 <= interp <= 4 and taps = 26*interp");
+        fail(PDT_EINVAL, "the tiled engine needs the float POES chain with 1 <= interp <= 8 and taps = 26*interp");
         delete c;
         return nullptr;
     }

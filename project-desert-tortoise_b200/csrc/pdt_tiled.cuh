@@ -281,7 +281,7 @@ PDT_DEV void load_iq1(const void *base, int pcm16, u64 idx, float &a, float &b)
 // straight from the kernel-parameter constant bank.
 // ---------------------------------------------------------------------------------------------------
 constexpr int FIR_K = 26;
-constexpr int FIR_MAX_L = 4;
+constexpr int FIR_MAX_L = 8;         // 8 = the historical 8x interpolator (18.75 ksps recordings)
 struct TapsRev { float hr[FIR_K * FIR_MAX_L]; };
 
 template <int L, typename OUT>
@@ -296,6 +296,30 @@ PDT_DEV void fir_block26(const float (&prev)[FIR_K], const float (&cur)[FIR_K], 
             for (int s = 0; s <= c; s++) acc += t.hr[p + L * (c - s)] * cur[s];
 #pragma unroll
             for (int s = c + 1; s < FIR_K; s++) acc += t.hr[p + L * (c - s + FIR_K)] * prev[s];
+            put(c * L + p, acc);
+        }
+    }
+}
+
+// The same sums for L >= 2, one polyphase branch at a time: for a fixed p the 26 outputs y[L·j + p] are the L = 1 block
+// with the branch taps hp[k] = hr[p + L·k].  The branch loop is NOT unrolled — the body is the 676-MAC L = 1 block with
+// its taps in registers (26 indexed constant-bank loads per branch), so the code stays ~22 KB for every L instead of
+// L x 22 KB (k_front<8> fully unrolled is 170 KB of straight-line code and runs out of the instruction cache).
+template <int L, typename OUT>
+PDT_DEV void fir_block26_branches(const float (&prev)[FIR_K], const float (&cur)[FIR_K], const TapsRev &t, OUT &&put)
+{
+#pragma unroll 1
+    for (int p = 0; p < L; p++) {
+        float hp[FIR_K];
+#pragma unroll
+        for (int k = 0; k < FIR_K; k++) hp[k] = t.hr[p + L * k];
+#pragma unroll
+        for (int c = 0; c < FIR_K; c++) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int s = 0; s <= c; s++) acc += hp[c - s] * cur[s];
+#pragma unroll
+            for (int s = c + 1; s < FIR_K; s++) acc += hp[c - s + FIR_K] * prev[s];
             put(c * L + p, acc);
         }
     }

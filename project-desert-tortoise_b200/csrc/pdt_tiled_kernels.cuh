@@ -767,15 +767,24 @@ __global__ void __launch_bounds__(128) k_pll_fix(const TiledArgs a)
 // ---------------------------------------------------------------------------------------------------
 // front: out = Im(x·e^{-jφ}) (CarrierTrackingPLL.c:106-113) then the ×L zero-stuff FIR (LowPassFilter.c:43-70)
 // ---------------------------------------------------------------------------------------------------
-constexpr int FRONT_THREADS = 128;
-constexpr int FRONT_SPAN = FRONT_THREADS * FIR_K;      // 3328 input samples per CTA
+// geometry per interpolation factor: 26 input samples per thread; the CTA shrinks for L >= 5 so that the L-times larger
+// output staging still leaves several CTAs per SM.  For L >= 2 every thread's 26·L output row is padded to an odd stride
+// (26·L is ≡ 8 / 16 mod 32 for L = 4 / 8: 8- and 16-way bank conflicts on the row-major stores otherwise).
+__host__ __device__ constexpr int front_threads(int L) { return L >= 5 ? 64 : 128; }
+__host__ __device__ constexpr int front_span(int L) { return front_threads(L) * FIR_K; }          // 3328 / 1664 input samples per CTA
+__host__ __device__ constexpr int front_row(int L) { return L == 1 ? FIR_K : FIR_K * L + 1; }
+__host__ __device__ constexpr size_t front_smem_bytes(int L)
+{
+    return sizeof(float) * ((size_t)front_span(L) + FIR_K + 2 + (size_t)front_threads(L) * front_row(L));
+}
 
 template <int L>
-__global__ void __launch_bounds__(FRONT_THREADS) k_front(const TiledArgs a, const __grid_constant__ TapsRev taps)
+__global__ void __launch_bounds__(front_threads(L)) k_front(const TiledArgs a, const __grid_constant__ TapsRev taps)
 {
+    constexpr int FRONT_THREADS = front_threads(L), FRONT_SPAN = front_span(L), ROW = front_row(L);
     extern __shared__ __align__(16) float fsm[];
     float *outs = fsm;                                  // [FRONT_SPAN + FIR_K]  (one block of history in front)
-    float *ys = fsm + FRONT_SPAN + FIR_K + 2;           // [FRONT_SPAN·L]
+    float *ys = fsm + FRONT_SPAN + FIR_K + 2;           // [FRONT_THREADS][ROW]
     const uint32_t cap = blockIdx.y;
     const int tid = threadIdx.x;
     const u64 n = cap_len(a, cap), first = (u64)cap * a.stride;
@@ -829,14 +838,20 @@ __global__ void __launch_bounds__(FRONT_THREADS) k_front(const TiledArgs a, cons
             float prev[FIR_K], cur[FIR_K];
 #pragma unroll
             for (int s = 0; s < FIR_K; s++) { prev[s] = outs[tid * FIR_K + s]; cur[s] = outs[(tid + 1) * FIR_K + s]; }
-            float *dst = ys + (size_t)tid * FIR_K * L;
-            fir_block26<L>(prev, cur, taps, [&](int o, float v) { dst[o] = v; });
+            float *dst = ys + (size_t)tid * ROW;
+            if constexpr (L == 1) fir_block26<1>(prev, cur, taps, [&](int o, float v) { dst[o] = v; });
+            else                  fir_block26_branches<L>(prev, cur, taps, [&](int o, float v) { dst[o] = v; });
         }
     }
     __syncthreads();
     const u64 span = (n - base < FRONT_SPAN) ? (n - base) : FRONT_SPAN;
     float *y = a.y + (u64)cap * a.ws_stride * L + base * L;
-    for (u64 o = tid; o < span * L; o += FRONT_THREADS) y[o] = ys[o];
+    if constexpr (L == 1) {
+        for (u64 o = tid; o < span; o += FRONT_THREADS) y[o] = ys[o];
+    } else {
+        const unsigned total = (unsigned)span * L;
+        for (unsigned o = tid; o < total; o += FRONT_THREADS) y[o] = ys[o + o / (unsigned)(FIR_K * L)];      // skip one pad word per row
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -157,14 +157,16 @@ def test_argos_wav_packets(torch_cuda, oracle64, golden_dir):
 
 @pytest.mark.parametrize("fs,chunk,seed,engine", [(250000, 10000, 7, "exact"), (250000, 4096, 8, "exact"), (50000, 10000, 9, "exact"),
                                                   (18750, 10000, 10, "exact"), (250000, 10000, 7, "tiled"), (250000, 4096, 8, "tiled"),
-                                                  (50000, 10000, 9, "tiled"), (75000, 10000, 11, "tiled"), (37500, 7000, 12, "tiled")])
+                                                  (50000, 10000, 9, "tiled"), (75000, 10000, 11, "tiled"), (37500, 7000, 12, "tiled"),
+                                                  (30000, 10000, 13, "tiled"), (25000, 10000, 15, "tiled"), (21430, 5000, 14, "tiled"),
+                                                  (18750, 10000, 10, "tiled")])
 def test_poes_synthetic_vs_oracle(torch_cuda, oracle32, fs, chunk, seed, engine):
-    """L = 1 / 2 / 3 / 4 / 8 (the historical 8x interpolator), ragged last chunk, non-default chunk length, both engines."""
+    """L = 1 ... 8 (8 = the historical 8x interpolator), ragged last chunk, non-default chunk length, both engines."""
     pcm, info = make_poes_capture(int(1.3 * fs) + 123, fs, seed, esn0_db=11.0, doppler_hz=-2000.0 + 300 * seed)
     iq = oracle32.pcm16_to_complex(pcm)
     want = oracle32.chain(iq, fs, chunk=chunk, trace=True)
     d, st, fr, tr = _run_batch_with_traces(torch_cuda, "f32", pdt.PDT_MODE_POES, fs, iq, chunk=chunk, engine=engine)
-    assert d.params.interp == {250000: 1, 75000: 2, 50000: 3, 37500: 4, 18750: 8}[fs]
+    assert d.params.interp == {250000: 1, 75000: 2, 50000: 3, 37500: 4, 30000: 5, 25000: 6, 21430: 7, 18750: 8}[fs]
     assert want["total_frames"] >= 8
     ns, nb = int(st["n_symbols"]), int(st["n_bits"])
     assert (ns, nb, st["n_frames"]) == (want["total_symbols"], want["total_bits"], want["total_frames"])
