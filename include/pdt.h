@@ -147,7 +147,9 @@ int         pdt_get_taps(const pdt_ctx *ctx, void *h_out /* REAL[taps] */);
 /* Demodulate a batch that is ALREADY in device memory.
  *   d_iq        REAL[2·n] interleaved I,Q per capture; capture c starts at d_iq + 2·c·stride_samples
  *               (pcm16 != 0: int16_t[2·n] raw PCM as in a WAV data chunk, normalised /32768 in-kernel, wave.c:141-166)
- *   n_samples   host array [n_captures] (NULL: every capture has stride_samples samples)
+ *   n_samples   host array [n_captures] (NULL: every capture has stride_samples samples).  Entries may EXCEED
+ *               stride_samples: the captures then overlap in memory (segments of one stream, see pdt_stream_plan);
+ *               the input is only ever read.
  *   traces      host array [n_captures] of device trace taps, or NULL
  *   stream      cudaStream_t (NULL = default stream).  Asynchronous: results are valid after the stream is synchronised.
  * Results stay on the device until pdt_fetch(). */
@@ -170,6 +172,45 @@ int         pdt_fetch(pdt_ctx *ctx, uint32_t n_captures, pdt_capture_stats *stat
 /* Frame post-checks of the last batch (POES): runs k_frame_checks on `stream` over the device frame table and copies
  * the [n_captures·max_frames] quality table to the host (synchronises `stream`). */
 int         pdt_frame_checks(pdt_ctx *ctx, uint32_t n_captures, pdt_frame_quality *quality_out, void *stream);
+
+/* ---- one long stream cut into overlapping segments (BASELINE configs[4]) ------------------------
+ * The reference processes a recording strictly serially (POESTIPdemod/main.c:373-482).  A long stream is cut into
+ * segments that start every `segment` samples and are lead + segment + tail samples long; each one is demodulated as an
+ * independent capture of a batch (re-acquiring carrier, gain, symbol clock and frame sync inside its lead), and the frame
+ * tables are stitched: segment s keeps the frames whose sync word completed in ITS window
+ *     [s·segment + lead, (s+1)·segment + lead)      (segment 0: from 0; the last segment: to the end of the stream),
+ * `tail` (> one minor frame) lets the last owned frame complete.  Segment 0 is bit-identical to the serial chain by
+ * construction; later segments decode the same bits once locked but are not guaranteed bit-identical around a seam, so
+ * the acceptance test is frame-counter continuity across the seams plus equality with the serial result on a prefix
+ * (SURVEY §8d "C5").  Segments are independent units: they shard across GPUs like captures do (rank r takes a
+ * contiguous range of segments; the only exchange is the gather of the frame tables before the stitch). */
+/*
+ * Segments behind the first do not repeat the reference's acquisition sweep from zero (CarrierTrackingPLL.c:115-262; a
+ * serial, seconds-long search that the serial chain runs exactly once per recording): pdt_demod_segments_device starts
+ * every capture with index >= n_serial directly in TRACK mode from a carrier estimate over its first 1024·D samples —
+ * the same guess + warm-up with which the tiled engine starts the PLL tiles inside a capture.  Captures below n_serial
+ * (the stream's first segment, on the rank that holds it) run the reference chain unchanged. */
+typedef struct pdt_stream_plan {
+    uint64_t total_samples, segment, lead, tail;
+    uint32_t n_segments;
+    uint32_t interp;             /* samples of pdt_frame.sample_index per input sample (max(params.interp, 1)) */
+} pdt_stream_plan;
+/* lead / tail 0 = defaults (0.3 s and 0.13 s + 4096 samples of signal).  Captures handed to pdt_demod_segments_device():
+ * d_iq = stream base (+ first·segment), stride_samples = segment, n_samples[s] = pdt_stream_segment_length(plan, s). */
+int         pdt_stream_plan_make(pdt_stream_plan *plan, const pdt_params *p, uint64_t total_samples, uint64_t segment,
+                                 uint64_t lead, uint64_t tail);
+int         pdt_demod_segments_device(pdt_ctx *ctx, const void *d_iq, int pcm16, uint32_t n_segments, uint64_t stride_samples,
+                                      const uint64_t *n_samples, uint32_t n_serial, void *stream);
+uint64_t    pdt_stream_segment_length(const pdt_stream_plan *plan, uint32_t s);
+/* Stitch the tables of segments [first, first + n) (stats[n], frames[n·max_frames]) into out[]: owned frames only, in
+ * stream order, sample_index rewritten to the stream-global interpolated-sample index (bit_index is left segment-local).
+ * Returns the number of frames written, or <0. */
+long        pdt_stream_stitch(const pdt_stream_plan *plan, uint32_t first, uint32_t n, const pdt_capture_stats *stats,
+                              const pdt_frame *frames, uint32_t max_frames, pdt_frame *out, uint32_t out_cap);
+/* Synthetic stream slice: samples [start, start + n) of ONE seeded POES stream of total_samples (Doppler crossing from
+ * f0 to -f0 over the whole stream), written at d_iq. */
+int         pdt_synth_poes_stream_device(void *d_iq, int pcm16, uint64_t start_sample, uint64_t n_samples,
+                                         uint64_t total_samples, double sample_rate, uint64_t seed, void *stream);
 
 /* Device addresses of the result tables of the last batch (for NCCL gathers without a host bounce). */
 int         pdt_result_tables(pdt_ctx *ctx, void **d_stats, void **d_frames, uint32_t *max_frames);

@@ -141,6 +141,7 @@ struct pdt_ctx {
     cudaStream_t h2d_stream = nullptr;       // chunked staging of pdt_demod_host
     cudaEvent_t  ev_h2d[MAX_GROUPS] = {}, ev_done = nullptr;
 #if PDT_USE_FLOATS
+    uint32_t prelock_from = 0xFFFFFFFFu; // this call: captures >= this index start pre-locked (pdt_demod_segments_device)
     tiled::TiledArgs ta;                 // workspace pointers + plans of the tiled engine (engine == PDT_ENGINE_TILED)
     tiled::TapsRev   taps_rev;
     size_t      front_smem = 0;
@@ -282,14 +283,16 @@ struct GroupLaunch {
         dim3 g(std::min<unsigned>(blocks(n_max, 1024), 4096), cnt);
         k_sp<<<g, 256, 0, s>>>(t);
         mark(s, "k_sp");
-        k_acquire<<<cnt, ACQ_THREADS, 0, s>>>(t, 0);
+        const uint32_t serial = std::min(cnt, t.prelock_from);        // captures that run the reference's acquisition
+        if (serial) k_acquire<<<serial, ACQ_THREADS, 0, s>>>(t, 0);
         mark(s, "k_acquire");
-        count_launch(3);
+        if (serial < cnt) { k_prelock<<<blocks(cnt - serial, EST_WARPS), EST_WARPS * 32, 0, s>>>(t); mark(s, "k_prelock"); count_launch(1); }
+        count_launch(serial ? 3 : 2);
     }
     void acquire_rest(cudaStream_t s)
     {
         using namespace tiled;
-        k_acquire<<<cnt, ACQ_THREADS_SLOW, 0, s>>>(t, 1);
+        k_acquire<<<std::max(1u, std::min(cnt, t.prelock_from)), ACQ_THREADS_SLOW, 0, s>>>(t, 1);
         mark(s, "k_acquire");
         count_launch(1);
     }
@@ -351,6 +354,7 @@ static GroupLaunch make_group(pdt_ctx *c, const tiled::TiledArgs &base, uint32_t
     t.iq = (const char *)base.iq + (size_t)c0 * t.stride * elem;
     if (t.n_samples) t.n_samples += c0;
     t.n_captures = cnt;
+    t.prelock_from = base.prelock_from > c0 ? std::min(base.prelock_from - c0, cnt) : 0;
     t.sp += (size_t)c0 * t.ws_stride; t.ph += (size_t)c0 * t.ws_stride;
     t.y += (size_t)c0 * t.ws_stride * L; t.z += (size_t)c0 * t.ws_stride * L;
     t.acq += c0;
@@ -386,6 +390,8 @@ static int tiled_run(pdt_ctx *c, const void *d_iq, int pcm16, uint32_t n_capture
     if (acq_env == 0) { const char *e = getenv("PDT_ACQ_FIRST"); acq_env = e ? (u64)atoll(e) : 131072; if (acq_env < 1024) acq_env = 131072; }
     const u64 acq_first = c->params.acq_first ? c->params.acq_first : acq_env;
     t.acq_first = (n_max > 2 * acq_first) ? acq_first : 0;
+    t.prelock_from = std::min(c->prelock_from, n_captures);
+    if (t.prelock_from == 0) t.acq_first = 0;          // nobody runs the acquisition sweep: no slow-capture pass
     const bool two_pass = t.acq_first != 0;
     PDT_CUDA(cudaMemsetAsync(t.counters, 0, 4 * sizeof(uint32_t), s));
     PDT_CUDA(cudaMemsetAsync(t.task_counts, 0, 2 * (pdt_ctx::MAX_GROUPS + 1) * 2 * sizeof(uint32_t), s));
@@ -681,7 +687,7 @@ static int demod_device_impl(pdt_ctx *c, const void *d_iq, int pcm16, uint32_t n
     PDT_CUDA(cudaMemsetAsync(c->d_frames, 0, sizeof(pdt_frame) * (size_t)n_captures * c->max_frames, s));
     if (n_samples) {
         for (uint32_t i = 0; i < n_captures; i++)
-            if (n_samples[i] > c->max_samples || n_samples[i] > stride_samples) return fail(PDT_EINVAL, "capture %u too long", i);
+            if (n_samples[i] > c->max_samples) return fail(PDT_EINVAL, "capture %u too long", i);      // > stride: overlapping segments
         PDT_CUDA(cudaMemcpyAsync(c->d_nsamp, n_samples, sizeof(uint64_t) * n_captures, cudaMemcpyHostToDevice, s));
     } else if (stride_samples > c->max_samples) return fail(PDT_EINVAL, "captures longer than the context allows");
     if (traces) PDT_CUDA(cudaMemcpyAsync(c->d_traces, traces, sizeof(pdt_traces) * n_captures, cudaMemcpyHostToDevice, s));
@@ -831,6 +837,9 @@ int pdt_demod_host_async(pdt_ctx *c, const void *h_iq, int pcm16, uint32_t n_cap
         PDT_CUDA(cudaMalloc(&c->d_stage, bytes));
         c->stage_bytes = bytes;
     }
+    if (n_samples)
+        for (uint32_t i = 0; i < n_captures; i++)
+            if (n_samples[i] > stride_samples) return fail(PDT_EINVAL, "overlapping captures (segments of a stream) need device-resident input");
     // The samples go up one capture group at a time on a copy stream; every group starts its kernels as soon as its own
     // samples have landed, so all but the first group's transfer is hidden behind the kernels of the groups before it.
     uint32_t per = 0;
@@ -902,6 +911,84 @@ long pdt_format_frames(const pdt_ctx *c, const pdt_frame *frames, uint32_t n_fra
     if (pos >= cap) return fail(PDT_EINVAL, "buffer too small");
     buf[pos] = 0;
     return (long)pos;
+}
+
+int pdt_demod_segments_device(pdt_ctx *c, const void *d_iq, int pcm16, uint32_t n_segments, uint64_t stride_samples,
+                              const uint64_t *n_samples, uint32_t n_serial, void *stream)
+{
+#if PDT_USE_FLOATS
+    if (!c || !n_samples) return fail(PDT_EINVAL, "bad arguments");
+    if (c->engine != PDT_ENGINE_TILED) return fail(PDT_EINVAL, "stream segments need the tiled engine");
+    const uint64_t pre = tiled::prelock_span(c->ta.est_decim);
+    for (uint32_t i = n_serial; i < n_segments; i++)
+        if (n_samples[i] < 2 * pre) return fail(PDT_EINVAL, "segment %u is shorter than twice the carrier-estimate span (%llu samples)", i, (unsigned long long)pre);
+    c->prelock_from = n_serial;
+    const int rc = demod_device_impl(c, d_iq, pcm16, n_segments, stride_samples, n_samples, nullptr, stream, nullptr);
+    c->prelock_from = 0xFFFFFFFFu;
+    return rc;
+#else
+    (void)c; (void)d_iq; (void)pcm16; (void)n_segments; (void)stride_samples; (void)n_samples; (void)n_serial; (void)stream;
+    return fail(PDT_EINVAL, "stream segments exist for the float POES chain only");
+#endif
+}
+
+// ---- one long stream as overlapping segments (pdt.h) ---------------------------------------------------------
+int pdt_stream_plan_make(pdt_stream_plan *plan, const pdt_params *p, uint64_t total_samples, uint64_t segment, uint64_t lead,
+                         uint64_t tail)
+{
+    if (!plan || !p || !total_samples || !segment || !(p->sample_rate > 0)) return fail(PDT_EINVAL, "bad arguments");
+    plan->total_samples = total_samples;
+    plan->segment = segment;
+    plan->lead = lead ? lead : (uint64_t)std::ceil(0.3 * p->sample_rate);
+    plan->tail = tail ? tail : (uint64_t)std::ceil(0.13 * p->sample_rate) + 4096;
+    plan->interp = (uint32_t)std::max(p->interp, 1);
+    // the last segment owns everything from its window start to the end of the stream
+    const uint64_t k = total_samples > plan->lead ? (total_samples - plan->lead + segment - 1) / segment : 1;
+    if (k > 0xFFFFFFFFull) return fail(PDT_EINVAL, "too many segments");
+    plan->n_segments = (uint32_t)std::max<uint64_t>(k, 1);
+    return PDT_OK;
+}
+
+uint64_t pdt_stream_segment_length(const pdt_stream_plan *plan, uint32_t s)
+{
+    if (!plan || s >= plan->n_segments) return 0;
+    const uint64_t start = (uint64_t)s * plan->segment, full = plan->lead + plan->segment + plan->tail;
+    return std::min(full, plan->total_samples - start);
+}
+
+long pdt_stream_stitch(const pdt_stream_plan *plan, uint32_t first, uint32_t n, const pdt_capture_stats *stats,
+                       const pdt_frame *frames, uint32_t max_frames, pdt_frame *out, uint32_t out_cap)
+{
+    if (!plan || !stats || !frames || !out || (uint64_t)first + n > plan->n_segments) return fail(PDT_EINVAL, "bad arguments");
+    const uint64_t L = plan->interp;
+    uint32_t k = 0;
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t s = first + i;
+        const uint64_t start = (uint64_t)s * plan->segment;
+        const bool last = s + 1 == plan->n_segments;
+        const uint64_t lo = s == 0 ? 0 : (start + plan->lead) * L;
+        const uint64_t hi = last ? ~0ull : (start + plan->segment + plan->lead) * L;
+        const uint32_t nf = std::min(stats[i].n_frames, max_frames);
+        for (uint32_t f = 0; f < nf; f++) {
+            const pdt_frame &fr = frames[(size_t)i * max_frames + f];
+            const uint64_t g = start * L + fr.sample_index;
+            if (g < lo || g >= hi) continue;
+            if (!fr.complete && !last) continue;            // cannot happen with tail > one frame; never emit a seam fragment
+            if (k >= out_cap) return fail(PDT_EINVAL, "stitched frame table too small");
+            out[k] = fr;
+            out[k].sample_index = g;
+            k++;
+        }
+    }
+    return (long)k;
+}
+
+int pdt_synth_poes_stream_device(void *d_iq, int pcm16, uint64_t start_sample, uint64_t n_samples, uint64_t total_samples,
+                                 double sample_rate, uint64_t seed, void *stream)
+{
+    if (!device_ok()) return PDT_ENODEV;
+    if (!d_iq || !n_samples || start_sample + n_samples > total_samples) return fail(PDT_EINVAL, "bad arguments");
+    return synth_poes_launch(d_iq, pcm16, 1, n_samples, n_samples, sample_rate, seed, (cudaStream_t)stream, start_sample, total_samples);
 }
 
 int pdt_synth_poes_device(void *d_iq, int pcm16, uint32_t n_captures, uint64_t stride_samples, uint64_t n_samples,

@@ -24,8 +24,10 @@ struct SynthCap { double f0, drift, amp, sigma, theta0; unsigned bit_start, n_fr
 
 constexpr int SYNTH_FRAME_BYTES = 104;
 
+// stream_seconds > 0: ONE long stream (capture 0) — the linear drift is chosen so that the carrier crosses from f0 to -f0
+// over the whole stream (a pass-like Doppler S-curve stays inside the PLL's +-4500 Hz range however long the stream is).
 __global__ void k_synth_frames(unsigned char *tab, SynthCap *caps, uint32_t n_captures, unsigned frames_per_cap,
-                               double sps, unsigned long long seed)
+                               double sps, unsigned long long seed, double stream_seconds)
 {
     const uint32_t c = blockIdx.x;
     if (c >= n_captures) return;
@@ -42,6 +44,7 @@ __global__ void k_synth_frames(unsigned char *tab, SynthCap *caps, uint32_t n_ca
         sc.n_frames = frames_per_cap;
         sc.bit_start = (unsigned)(mix64(hc + 5) % (unsigned long long)(2 * SYNTH_FRAME_BYTES * 8u));   // < 2 frames: counter stays continuous
         sc.counter0 = (unsigned)(mix64(hc + 6) % 320u);
+        if (stream_seconds > 0.0) sc.drift = -2.0 * sc.f0 / stream_seconds;
         caps[c] = sc;
     }
     const unsigned counter0 = (unsigned)(mix64(hc + 6) % 320u);
@@ -68,15 +71,17 @@ __global__ void k_synth_frames(unsigned char *tab, SynthCap *caps, uint32_t n_ca
 
 template <typename OUT>
 __global__ void k_synth_iq(OUT *iq, const unsigned char *tab, const SynthCap *caps, unsigned long long stride,
-                           unsigned long long n, double fs, double sps, unsigned long long seed, int pcm16)
+                           unsigned long long n, double fs, double sps, unsigned long long seed, int pcm16,
+                           unsigned long long i0)           // i0: stream index of the first sample written (slices of one stream)
 {
     const uint32_t c = blockIdx.y;
     const SynthCap sc = caps[c];
     const unsigned long long hc = mix64(seed * 0x100000001B3ull + c) ^ 0x5EEDull;
     const unsigned total_bits = sc.n_frames * SYNTH_FRAME_BYTES * 8u;
     const unsigned char *ft = tab + (size_t)c * sc.n_frames * SYNTH_FRAME_BYTES;
-    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-         i += (unsigned long long)gridDim.x * blockDim.x) {
+    for (unsigned long long k = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; k < n;
+         k += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long i = i0 + k;
         const unsigned long long chip = (unsigned long long)floor((double)i / sps);
         const unsigned bitpos = (unsigned)((sc.bit_start + (chip >> 1)) % total_bits);
         const int bit = (ft[bitpos >> 3] >> (7 - (bitpos & 7))) & 1;
@@ -92,7 +97,7 @@ __global__ void k_synth_iq(OUT *iq, const unsigned char *tab, const SynthCap *ca
         double n1, n2;
         sincospi(2.0 * u2, &n1, &n2);
         const double re = sc.amp * cs + mag * n2, im = sc.amp * sn + mag * n1;
-        OUT *o = iq + ((size_t)c * stride + i) * 2;
+        OUT *o = iq + ((size_t)c * stride + k) * 2;
         if (pcm16) {
             o[0] = (OUT)fmin(fmax(rint(re * 32768.0), -32768.0), 32767.0);
             o[1] = (OUT)fmin(fmax(rint(im * 32768.0), -32768.0), 32767.0);
@@ -101,18 +106,19 @@ __global__ void k_synth_iq(OUT *iq, const unsigned char *tab, const SynthCap *ca
 }
 
 inline int synth_poes_launch(void *d_iq, int pcm16, uint32_t n_captures, uint64_t stride, uint64_t n, double fs,
-                             uint64_t seed, cudaStream_t s)
+                             uint64_t seed, cudaStream_t s, uint64_t stream_start = 0, uint64_t stream_total = 0)
 {
     const double sps = fs / (8320 * 2 + 0.3);
-    const unsigned frames_per_cap = (unsigned)(n / sps / (SYNTH_FRAME_BYTES * 16.0)) + 5;
+    const uint64_t span = stream_total ? stream_total : n;
+    const unsigned frames_per_cap = (unsigned)(span / sps / (SYNTH_FRAME_BYTES * 16.0)) + 5;
     unsigned char *tab = nullptr; SynthCap *caps = nullptr;
     PDT_CUDA(cudaMalloc(&tab, (size_t)n_captures * frames_per_cap * SYNTH_FRAME_BYTES));
     PDT_CUDA(cudaMalloc(&caps, sizeof(SynthCap) * n_captures));
-    k_synth_frames<<<n_captures, 64, 0, s>>>(tab, caps, n_captures, frames_per_cap, sps, seed);
+    k_synth_frames<<<n_captures, 64, 0, s>>>(tab, caps, n_captures, frames_per_cap, sps, seed, stream_total ? (double)stream_total / fs : 0.0);
     const unsigned bx = (unsigned)std::min<uint64_t>((n + 255) / 256, 2048);
     dim3 grid(bx, n_captures);
-    if (pcm16) k_synth_iq<short><<<grid, 256, 0, s>>>((short *)d_iq, tab, caps, stride, n, fs, sps, seed, 1);
-    else       k_synth_iq<real_t><<<grid, 256, 0, s>>>((real_t *)d_iq, tab, caps, stride, n, fs, sps, seed, 0);
+    if (pcm16) k_synth_iq<short><<<grid, 256, 0, s>>>((short *)d_iq, tab, caps, stride, n, fs, sps, seed, 1, stream_start);
+    else       k_synth_iq<real_t><<<grid, 256, 0, s>>>((real_t *)d_iq, tab, caps, stride, n, fs, sps, seed, 0, stream_start);
     count_launch(2);
     cudaError_t e = cudaGetLastError();
     cudaStreamSynchronize(s);

@@ -42,6 +42,8 @@ struct TiledArgs {
     float       est_fmax;    // peak search limit (Hz)
     u64         acq_first;   // samples covered by the first acquisition pass (0 = whole capture in one pass)
     int         slow_pass;   // 0: kernels process the captures that latched in the first pass, 1: the slow ones
+    uint32_t    prelock_from;// captures >= this index skip the acquisition sweep and start in track mode from a carrier
+                             // estimate (k_prelock): segments of one stream behind the first (pdt_demod_segments_device)
     LaneTask   *pll_tasks, *agc_tasks;   // compact work lists of the persistent lane-stream kernels (built on the device)
     uint32_t   *task_counts; // [0] PLL tasks, [1] AGC tasks
     unsigned    pll_tasks_per_cap, agc_tasks_per_cap;
@@ -323,6 +325,7 @@ __global__ void __launch_bounds__(ACQ_THREADS) k_acquire(const TiledArgs a, cons
     AcqResult *res = &a.acq[cap];
     const u64 wfirst = (u64)cap * a.ws_stride;
     float *ph_out = a.ph + wfirst;
+    if (cap >= a.prelock_from) return;                       // k_prelock's captures
 
     PllState ps;
     pll_reset(ps);
@@ -516,27 +519,15 @@ __global__ void __launch_bounds__(ACQ_THREADS) k_acquire(const TiledArgs a, cons
 constexpr int EST_WARPS = 2;
 constexpr int EST_MAX_D = 24;          // staged (coalesced) decimation up to this factor (6 KB per warp), direct strided reads beyond
 
-__global__ void __launch_bounds__(EST_WARPS * 32) k_estimate(const TiledArgs a)
+// carrier frequency (rad/sample) and phase at sample `warm` of a capture, from the EST_FFT·D samples in front of it.
+// One warp; z / stg are its shared-memory scratch.  The result is valid on lane 0.
+__device__ __forceinline__ LoopState2 est_carrier(const TiledArgs &a, const u64 first, const u64 warm, float2 *z, float2 *stg, const int lane)
 {
-    __shared__ float2 zs[EST_WARPS][EST_FFT];
-    __shared__ float2 stage[EST_WARPS][32 * EST_MAX_D];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const unsigned per_cap = a.pll.max_tiles - 1;
-    const u64 wid = (u64)blockIdx.x * EST_WARPS + wib;
-    if (per_cap == 0 || wid >= (u64)a.n_captures * per_cap) return;
-    const uint32_t cap = (uint32_t)(wid / per_cap);
-    const unsigned k = 1 + (unsigned)(wid % per_cap);
-    const AcqResult &acq = a.acq[cap];
-    const u64 n = cap_len(a, cap), first = (u64)cap * a.stride;
-    u64 warm, begin, end;
-    if (!cap_selected(a, cap) || !acq.locked || !tile_range(acq.track_begin, n, a.pll, k, warm, begin, end)) return;
-    float2 *z = zs[wib];
     const int D = a.est_decim;
     const long long w0 = (long long)warm - (long long)EST_FFT * D;
     // decimate by block sums, store bit-reversed.  The warp reads 32·D consecutive samples at a time (coalesced) into a
     // staging tile and lane j sums its own D of them: read directly, lane j's samples are D·8 bytes apart from lane j+1's
     // and every 32-byte sector fetched from HBM would be used for one 8-byte sample.
-    float2 *stg = stage[wib];
     for (int blk = 0; blk < EST_FFT / 32; blk++) {
         const long long b0 = w0 + (long long)blk * 32 * D;
         if (D <= EST_MAX_D) {
@@ -604,11 +595,69 @@ __global__ void __launch_bounds__(EST_WARPS * 32) k_estimate(const TiledArgs a)
         }
     }
     for (int o = 16; o; o >>= 1) { ar += __shfl_xor_sync(0xffffffffu, ar, o); ai += __shfl_xor_sync(0xffffffffu, ai, o); }
+    LoopState2 g;
+    g.a = atan2f(ai, ar);
+    g.b = 6.283185307179586f * cyc;
+    return g;
+}
+
+__global__ void __launch_bounds__(EST_WARPS * 32) k_estimate(const TiledArgs a)
+{
+    __shared__ float2 zs[EST_WARPS][EST_FFT];
+    __shared__ float2 stage[EST_WARPS][32 * EST_MAX_D];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const unsigned per_cap = a.pll.max_tiles - 1;
+    const u64 wid = (u64)blockIdx.x * EST_WARPS + wib;
+    if (per_cap == 0 || wid >= (u64)a.n_captures * per_cap) return;
+    const uint32_t cap = (uint32_t)(wid / per_cap);
+    const unsigned k = 1 + (unsigned)(wid % per_cap);
+    const AcqResult &acq = a.acq[cap];
+    const u64 n = cap_len(a, cap), first = (u64)cap * a.stride;
+    u64 warm, begin, end;
+    if (!cap_selected(a, cap) || !acq.locked || !tile_range(acq.track_begin, n, a.pll, k, warm, begin, end)) return;
+    const LoopState2 g = est_carrier(a, first, warm, zs[wib], stage[wib], lane);
+    if (lane == 0) a.guess[(size_t)cap * a.pll.max_tiles + k] = g;
+}
+
+// Pre-locked start of the captures >= prelock_from (segments of one stream behind the first, pdt.h): instead of the
+// reference's acquisition sweep from zero (CarrierTrackingPLL.c:115-262), the loop starts in TRACK mode at sample
+// pre = EST_FFT·D from the carrier estimated over [0, pre) — the same guess + warm-up the PLL tiles of a capture use.
+// The phase stream of [0, pre) is the estimate extrapolated backwards, so the FIR/AGC see a derotated signal from sample 0.
+// Writes the AcqResult k_acquire would have written at a lock latch on sample pre-1.
+__host__ __device__ inline u64 prelock_span(int est_decim) { return (u64)EST_FFT * (u64)est_decim; }
+
+__global__ void __launch_bounds__(EST_WARPS * 32) k_prelock(const TiledArgs a)
+{
+    __shared__ float2 zs[EST_WARPS][EST_FFT];
+    __shared__ float2 stage[EST_WARPS][32 * EST_MAX_D];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const u64 wid = (u64)blockIdx.x * EST_WARPS + wib;
+    const u64 cap64 = (u64)a.prelock_from + wid;
+    if (cap64 >= a.n_captures) return;
+    const uint32_t cap = (uint32_t)cap64;
+    const u64 n = cap_len(a, cap), first = (u64)cap * a.stride;
+    AcqResult *res = &a.acq[cap];
+    u64 pre = prelock_span(a.est_decim);
+    if (pre > n) pre = n;                                   // (the host refuses segments this short; keep the kernel safe)
+    LoopState2 g = est_carrier(a, first, pre, zs[wib], stage[wib], lane);
+    g.a = __shfl_sync(0xffffffffu, g.a, 0); g.b = __shfl_sync(0xffffffffu, g.b, 0);
+    PllState ps; pll_reset(ps); pll_begin(ps, a.cc.pll);
+    if (g.b > ps.max_freq) g.b = ps.max_freq; else if (g.b < ps.min_freq) g.b = ps.min_freq;
+    float *ph = a.ph + (u64)cap * a.ws_stride;
+    for (u64 i = lane; i < pre; i += 32) {
+        double p = (double)g.a - (double)g.b * (double)(pre - i);
+        p -= 6.283185307179586 * rint(p / 6.283185307179586);
+        ph[i] = (float)p;
+    }
     if (lane == 0) {
-        LoopState2 g;
-        g.a = atan2f(ai, ar);
-        g.b = 6.283185307179586f * cyc;
-        a.guess[(size_t)cap * a.pll.max_tiles + k] = g;
+        res->locked = 1; res->slow = 0; res->resume_at = n;
+        res->lock_sample = pre ? pre - 1 : 0; res->track_begin = pre;
+        res->phase = g.a; res->freq = g.b; res->sweep = 0.0f;
+        res->avg_phase = 0.0f; res->locksig = 1.0f;
+        res->lock_freq_hz = g.b * a.cc.pll.Fs / (2.0 * PDT_PI);
+        const float bw = a.cc.pll.bw_track, damp = ps.damp;                                         // CarrierTrackingPLL.c:272-273
+        res->alpha = (4.0 * damp * bw) / (1.0 + 2.0 * damp * bw + bw * bw);
+        res->beta  = (4.0 * bw * bw) / (1.0 + 2.0 * damp * bw + bw * bw);
     }
 }
 

@@ -329,6 +329,76 @@ def test_config1_single_10M_sample_stream_bit_exact_frames(torch_cuda, oracle32)
     assert q["valid"].sum() == len(full) and q["parity_ok"][q["valid"] == 1].mean() > 0.98
 
 
+@pytest.mark.parametrize("fs,total,segment,min_frames", [(250000, 10_000_000, 1_000_000, 390), (2_000_000, 12_000_000, 2_000_000, 50)])
+def test_config4_stream_as_segments_matches_serial_capture(torch_cuda, fs, total, segment, min_frames):
+    """BASELINE configs[4] in small (one GPU): ONE synthetic stream (Doppler crossing zero), demodulated (a) serially as a single
+    capture — the path the other tests pin bit-exact against the oracle — and (b) as overlapping segments stitched by
+    ownership windows (pdt_stream_*).  Acceptance: every complete minor frame of the serial result appears
+    with identical bytes, sync positions within one symbol, no counter break across the seams; and a rank that holds only
+    its slice of the stream produces exactly its part of the stitched list.  2 Msps uses the declared L = 1 deviation."""
+    torch = torch_cuda
+    stream_mod = importlib.import_module("project-desert-tortoise_b200.stream")
+    L = stream_mod._bind(pdt.load("f32"))
+    p = pdt.default_params("f32", pdt.PDT_MODE_POES, fs)
+    if fs > 300000:
+        p.force_min_interp1 = 1
+    cs = torch.cuda.current_stream().cuda_stream
+    d_iq = torch.empty(total * 2, dtype=torch.float32, device="cuda")
+    assert L.pdt_synth_poes_stream_device(d_iq.data_ptr(), 0, 0, total, total, float(fs), 99, cs) == 0
+    # (a) serial
+    d = pdt.Demod("f32", p, 1, total, int(total / fs * 10) + 8)
+    d.demod_device(d_iq.data_ptr(), 1, total, stream=cs)
+    st, fr = d.fetch(1, cs)
+    serial = fr[0][: int(st[0]["n_frames"])]
+    serial_full = serial[serial["complete"] == 1]
+    serial_locked = int(st[0]["locked"]) == 1
+    # (b) segments
+    plan = stream_mod.make_plan("f32", d.params, total, segment)
+    k = plan.n_segments
+    assert k >= 4
+    sd = stream_mod.StreamDemod("f32", p, plan, 0, k)
+    assert (sd.start, sd.n_slice) == (0, total)
+    sd.run_device(d_iq.data_ptr(), stream=cs)
+    s_st, s_fr = sd.fetch(cs)
+    assert np.all(s_st["locked"][1:] == 1)                                   # segments behind the first start pre-locked
+    out = sd.stitch_local(s_st, s_fr)
+    c = stream_mod.continuity(out)
+    out_full = out[out["complete"] == 1]
+    sps = d.params.interp * fs / 16640.3
+    if serial_locked:
+        # the reference chain itself decodes this stream: the stitched result must be the same list of minor frames
+        assert serial_full.size >= min_frames and stream_mod.continuity(serial)["counter_breaks"] == 0
+        assert c["counter_breaks"] == 0, c
+        assert out_full.size == serial_full.size
+        assert np.array_equal(out_full["bytes"], serial_full["bytes"])
+        assert np.abs(out_full["sample_index"].astype(np.int64) - serial_full["sample_index"].astype(np.int64)).max() <= sps
+    else:
+        # the reference's own acquisition sweep never latches on this stream (2 Msps: -1 dB per-sample SNR), so the serial
+        # chain decodes little or nothing; the segments behind the first still do.  Segment 0 IS the serial chain.
+        own = out[out["sample_index"] >= (segment + plan.lead) * d.params.interp]
+        own_full = own[own["complete"] == 1]
+        assert stream_mod.continuity(own)["counter_breaks"] == 0
+        assert own_full.size >= int((total - segment - plan.lead) / fs * 10) - 1
+        assert np.mean([check_parity(f["bytes"]) for f in own_full]) > 0.98
+    # segment 0 is the serial chain itself: the frames it owns are bit-identical including positions
+    n0 = int((out["sample_index"] < (segment + plan.lead) * d.params.interp).sum())
+    ns = int((serial["sample_index"] < (segment + plan.lead) * d.params.interp).sum())
+    assert n0 == ns and np.array_equal(out[:n0], serial[:n0])
+    assert n0 >= 3 or not serial_locked
+    # a second "rank": only the slice for segments [h, k), generated separately from the same seed
+    h = k // 2
+    sd2 = stream_mod.StreamDemod("f32", p, plan, h, k - h)
+    d_slice = torch.empty(sd2.n_slice * 2, dtype=torch.float32, device="cuda")
+    assert L.pdt_synth_poes_stream_device(d_slice.data_ptr(), 0, sd2.start, sd2.n_slice, total, float(fs), 99, cs) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(d_slice, d_iq[sd2.start * 2: (sd2.start + sd2.n_slice) * 2])
+    sd2.run_device(d_slice.data_ptr(), stream=cs)
+    st2, fr2 = sd2.fetch(cs)
+    part2 = sd2.stitch_local(st2, fr2)
+    part1 = stream_mod.stitch("f32", plan, 0, h, s_st[:h], s_fr[:h])
+    assert np.array_equal(np.concatenate([part1, part2]), out)
+
+
 def test_config2_argos_batch_of_bursts(torch_cuda, oracle64):
     """BASELINE configs[2] shape: many synthetic 401.65 MHz ARGOS bursts as independent double-precision captures in one
     batch (exact engine): packets and counts of every capture equal to the CPU oracle."""

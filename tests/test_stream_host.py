@@ -1,0 +1,132 @@
+"""Host logic of the stream mode (include/pdt.h pdt_stream_*): segment geometry, ownership windows, stitch, and the
+world_size-2 gloo gather.  No device work: pdt_stream_plan_make / _segment_length / _stitch are host-only entry points."""
+import importlib
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pdt = importlib.import_module("project-desert-tortoise_b200")
+stream = importlib.import_module("project-desert-tortoise_b200.stream")
+
+
+def _params(fs=250000):
+    return pdt.default_params("f32", pdt.PDT_MODE_POES, fs)
+
+
+@pytest.mark.parametrize("total,segment,lead,tail", [(10_000_000, 1_000_000, 0, 0), (1_000_000, 1_000_000, 0, 0), (100, 1000, 0, 0),
+                                                     (3_333_333, 500_000, 100_000, 40_000), (2_150_000, 1_000_000, 150_000, 36_596)])
+def test_plan_geometry(total, segment, lead, tail):
+    p = _params()
+    plan = stream.make_plan("f32", p, total, segment, lead, tail)
+    assert plan.lead == (lead or 75000) and plan.tail == (tail or 32500 + 4096) and plan.interp == 1
+    k = plan.n_segments
+    lens = stream.segment_lengths("f32", plan, 0, k)
+    starts = np.arange(k, dtype=np.uint64) * np.uint64(segment)
+    assert k >= 1 and np.all(lens >= 1) and np.all(starts + lens <= total)
+    assert int(starts[-1] + lens[-1]) == total                                 # the last segment runs to the end of the stream
+    # ownership windows tile [0, total): segment s owns [s·seg + lead, (s+1)·seg + lead), first from 0, last to the end,
+    # and every window but the last is followed by at least `tail` samples inside its segment
+    for s in range(k - 1):
+        hi = (s + 1) * segment + plan.lead
+        assert hi + plan.tail <= int(starts[s] + lens[s])
+        assert hi < total
+    if k > 1:
+        assert (k - 1) * segment + plan.lead < total                           # the last window is not empty
+    s0, n0 = stream.slice_range(plan, lens[1:], 1) if k > 1 else (0, 0)
+    if k > 1:
+        assert s0 == segment and s0 + n0 == total
+
+
+def _fake_tables(plan, rng, max_frames=64):
+    """Every segment "decodes" a frame every 25 000 interpolated samples of the stream (same global grid for all segments),
+    starting somewhere inside its lead; bytes carry the global frame number."""
+    k, L, period = plan.n_segments, plan.interp, 25000
+    stats = np.zeros(k, pdt.STATS_DTYPE)
+    frames = np.zeros((k, max_frames), pdt.FRAME_DTYPE)
+    lens = stream.segment_lengths("f32", plan, 0, k)
+    for s in range(k):
+        start = s * plan.segment * L
+        end = start + int(lens[s]) * L
+        first = start + (0 if s == 0 else int(rng.integers(0, plan.lead * L // 2)))
+        g = -(-first // period) * period + 7
+        n = 0
+        while g + period <= end and n < max_frames:                              # only frames that complete inside the segment
+            f = frames[s, n]
+            f["sample_index"], f["n_bytes"], f["complete"] = g - start, 104, 1
+            num = g // period
+            f["bytes"][4], f["bytes"][5] = (num % 320) >> 8, (num % 320) & 0xFF
+            f["bytes"][6:14] = np.frombuffer(np.uint64(num).tobytes(), np.uint8)
+            g += period
+            n += 1
+        stats[s]["n_frames"] = n
+    return stats, frames
+
+
+def test_stitch_keeps_every_frame_exactly_once():
+    rng = np.random.default_rng(1)
+    plan = stream.make_plan("f32", _params(), 10_000_000, 1_000_000)
+    stats, frames = _fake_tables(plan, rng)
+    out = stream.stitch("f32", plan, 0, plan.n_segments, stats, frames)
+    nums = np.array([int(np.frombuffer(f["bytes"][6:14].tobytes(), np.uint64)[0]) for f in out])
+    assert np.array_equal(nums, np.arange(nums[0], nums[0] + nums.size))          # no duplicate, no hole, stream order
+    assert nums[0] == 0 and nums[-1] == (10_000_000 - 7) // 25000 - 1
+    assert np.array_equal(out["sample_index"], nums * 25000 + 7)                  # stream-global positions
+    c = stream.continuity(out)
+    assert c["counter_breaks"] == 0 and c["complete"] == nums.size
+    # a segment that failed to lock inside its lead shows up as a counter break, not as silent loss
+    stats2 = stats.copy()
+    stats2[4]["n_frames"] = 0
+    c2 = stream.continuity(stream.stitch("f32", plan, 0, plan.n_segments, stats2, frames))
+    assert c2["counter_breaks"] == 1 and c2["missing_frames"] == 40
+    # stitching ranges separately and concatenating is the same as stitching everything (what the ranks do)
+    a = stream.stitch("f32", plan, 0, 4, stats[:4], frames[:4])
+    b = stream.stitch("f32", plan, 4, plan.n_segments - 4, stats[4:], frames[4:])
+    assert np.array_equal(np.concatenate([a, b]), out)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    pd = importlib.import_module("project-desert-tortoise_b200.dist")
+    st = importlib.import_module("project-desert-tortoise_b200.stream")
+    pk = importlib.import_module("project-desert-tortoise_b200")
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        plan = st.make_plan("f32", pk.default_params("f32", pk.PDT_MODE_POES, 250000), 7_300_000, 1_000_000)
+        stats, frames = _fake_tables(plan, np.random.default_rng(5))               # same seed: every rank knows the "truth"
+        first, cnt = pd.shard_range(plan.n_segments, rank, world)
+        counts = [pd.shard_range(plan.n_segments, r, world)[1] for r in range(world)]
+        out = st.gather_and_stitch("f32", plan, stats[first:first + cnt], frames[first:first + cnt], counts)
+        want = st.stitch("f32", plan, 0, plan.n_segments, stats, frames)
+        q.put((rank, first, cnt, bool(np.array_equal(out, want)), int(out.size)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_stream_shards_and_stitch_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][1] == 0 and res[0][1] + res[0][2] == res[1][1]                   # contiguous segment ranges
+    assert all(r[3] for r in res) and res[0][4] == res[1][4] > 250
