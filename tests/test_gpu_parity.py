@@ -206,6 +206,27 @@ def test_tiled_long_capture_many_tiles_bit_exact(torch_cuda, oracle32):
     assert tiles >= 12 and pll_rerun <= 3 and agc_rerun <= 3
 
 
+@pytest.mark.parametrize("fs,n,seed", [(50000, 600_000, 31), (18750, 230_000, 32)])
+def test_tiled_long_interpolating_capture_bit_exact(torch_cuda, oracle32, fs, n, seed):
+    """L = 3 (12 s) and L = 8 (12 s): many PLL tiles and AGC tiles on the interpolated rate, the branch-looped FIR of k_front<L>
+    over hundreds of CTAs — every stream bit-identical to the serial oracle."""
+    pcm, info = make_poes_capture(n, fs, seed, esn0_db=14.0, doppler_hz=700.0, drift_hz_s=20.0, amplitude=0.2)
+    iq = oracle32.pcm16_to_complex(pcm)
+    want = oracle32.chain(iq, fs, trace=True)
+    d, st, fr, tr = _run_batch_with_traces(torch_cuda, "f32", pdt.PDT_MODE_POES, fs, iq, engine="tiled")
+    ns, nb = int(st["n_symbols"]), int(st["n_bits"])
+    assert d.params.interp == {50000: 3, 18750: 8}[fs] and want["total_frames"] >= 100
+    assert st["locked"] == 1 and st["lock_sample"] == want["lock_sample"]
+    for k_dev, k_or in (("pll_phase", "tr_phase"), ("pll_out", "tr_pll_out"), ("lpf", "tr_lpf"), ("agc", "tr_agc")):
+        bad = np.nonzero(tr.host(k_dev) != want[k_or])[0]
+        assert bad.size == 0, (k_dev, bad[:5], bad.size)
+    assert (ns, nb, st["n_frames"]) == (want["total_symbols"], want["total_bits"], want["total_frames"])
+    assert np.array_equal(tr.host("gardner_idx", ns).astype(np.uint64), want["tr_gidx"])
+    assert np.array_equal(tr.host("bits", nb), want["tr_bits"])
+    _frames_text_equal_bytes(d.format_frames(fr, int(st["n_frames"])), want["text"])
+    assert d.tiled_counters()[3] >= 4
+
+
 def test_tiled_failed_speculation_is_repaired(torch_cuda, oracle32):
     """Warm-up windows far too short to converge: the verification must reject them and the re-run must restore the
     exact serial result (this is what makes the tiled engine exact by construction, not by luck)."""
@@ -400,13 +421,13 @@ def test_config4_stream_as_segments_matches_serial_capture(torch_cuda, fs, total
 
 
 def test_config2_argos_batch_of_bursts(torch_cuda, oracle64):
-    """BASELINE configs[2] shape: many synthetic 401.65 MHz ARGOS bursts as independent double-precision captures in one
-    batch (exact engine): packets and counts of every capture equal to the CPU oracle."""
-    caps, n = 12, 40_000
+    """BASELINE configs[2] shape: 256 synthetic 401.65 MHz ARGOS bursts (128 captures x 2) as independent double-precision
+    captures in one batch (exact engine): packets and counts of every capture equal to the CPU oracle."""
+    caps, n = 128, 40_000
     iq = np.zeros((caps, n, 2), np.float64)
     wants = []
     for c in range(caps):
-        pcm, _ = make_argos_capture(n, 5000.0, seed=40 + c, n_bursts=2, snr_db=14.0 + c)
+        pcm, _ = make_argos_capture(n, 5000.0, seed=40 + c, n_bursts=2, snr_db=14.0 + (c % 12))
         x = oracle64.pcm16_to_complex(pcm)
         iq[c] = x.reshape(-1, 2)
         wants.append(oracle64.chain(x, 5000, argos=True))
