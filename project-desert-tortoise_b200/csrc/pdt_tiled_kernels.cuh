@@ -507,6 +507,9 @@ __global__ void __launch_bounds__(ACQ_THREADS) k_acquire(const TiledArgs a, cons
                     return;
                 }
             }
+            // the commit above read ring slot (st-3) % 4, which is the slot the core lane fills in the next step: close the
+            // step before anybody runs ahead (compute-sanitizer racecheck; ~30 of a step's ~20 000 cycles)
+            if (c_dec && !epoch_done) __syncthreads();
             pf_cyc += (unsigned long long)(clock64() - t_step);
         }
         if (!epoch_done) return;        // (not reached: the last block always returns above)
