@@ -14,6 +14,12 @@ through the host-buffer C-ABI call (pdt_demod_host: pinned host IQ -> H2D -> ker
 bounded sample of the same captures on the box's host cores.
 
 `--impl reference` times only that CPU reference arm (rank 0; other ranks exit) and prints the same JSON shape.
+
+Extras on the same line (N=1): `e2e_pcm16` (the e2e leg fed with raw int16 PCM, 4 B/sample over PCIe), `kernels` (per-kernel
+device times and HBM fractions), `single_capture_10M` (configs[1]: one stream, serial semantics, time-tiled on one GPU) and
+`stream_256M` (configs[4] shape in small: one stream as overlapping segments).  Other workloads, one JSON line each:
+`--fs 50000|18750` (the ×3 / ×8 interpolating rates), `--pcm16`, and `--stream N [--fs 2000000]` — ONE stream of N samples
+time-tiled across the GPUs (strong scaling; also under torchrun).
 """
 from __future__ import annotations
 
@@ -612,6 +618,39 @@ def main():
                                       "note": "BASELINE configs[1] shape: one stream, time-tiled across the SMs of one GPU"}
         d1.close()
         del d1_iq
+
+    # ---- BASELINE configs[4] shape in small: ONE 256 M-sample stream as overlapping segments (full runs: --stream) ----
+    if rank == 0 and world == 1 and not args.no_single and FS <= 300000 and not args.pcm16:
+        try:
+            sm = importlib.import_module("project-desert-tortoise_b200.stream")
+            Ls = sm._bind(L)
+            tot = 256_000_000
+            plan = sm.make_plan("f32", params, tot, int(2.0 * FS))
+            sd = sm.StreamDemod("f32", params, plan, 0, plan.n_segments)
+            d_s = torch.empty(sd.n_slice * 2, dtype=torch.float32, device="cuda")
+            if Ls.pdt_synth_poes_stream_device(d_s.data_ptr(), 0, 0, sd.n_slice, tot, float(FS), 20261017, stream) != 0:
+                raise RuntimeError(L.pdt_last_error().decode())
+            for _ in range(2):
+                sd.run_device(d_s.data_ptr(), stream=stream)
+            torch.cuda.synchronize()
+            a2, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a2.record()
+            for _ in range(3):
+                sd.run_device(d_s.data_ptr(), stream=stream)
+            b2.record()
+            torch.cuda.synchronize()
+            st_s, fr_s = sd.fetch(stream)
+            chk = sm.continuity(sd.stitch_local(st_s, fr_s))
+            ms_s = a2.elapsed_time(b2) / 3
+            line["stream_256M"] = {"ms": ms_s, "Msamples_per_s": tot / ms_s / 1e3, "segments": int(plan.n_segments),
+                                   "frames_complete": chk["complete"], "expected_frames": int(tot / FS * 10),
+                                   "counter_breaks": chk["counter_breaks"],
+                                   "note": "one stream, time-tiled into overlapping segments with pre-locked PLL starts, stitched by "
+                                           "ownership windows (DESIGN §8); one batch at a time; full-size and multi-GPU runs: --stream"}
+            sd.demod.close()
+            del d_s
+        except Exception as e:                      # an extra, never the headline: report instead of failing the bench line
+            line["stream_256M"] = {"error": f"{type(e).__name__}: {e}"}
 
     # ---- CPU baseline on a bounded sample of the same captures (rank 0, N=1 only) --------------------
     if rank == 0 and world == 1 and not args.no_cpu:
