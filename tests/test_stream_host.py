@@ -130,3 +130,31 @@ def test_stream_shards_and_stitch_world2():
         assert p.exitcode == 0
     assert res[0][1] == 0 and res[0][1] + res[0][2] == res[1][1]                   # contiguous segment ranges
     assert all(r[3] for r in res) and res[0][4] == res[1][4] > 250
+
+
+def test_plan_edge_cases_and_stitch_capacity():
+    p = _params()
+    # a stream shorter than the lead is one segment that owns everything
+    plan = stream.make_plan("f32", p, 50_000, 1_000_000)
+    assert plan.n_segments == 1 and int(stream.segment_lengths("f32", plan, 0, 1)[0]) == 50_000
+    # window of the last segment may be tiny but is never empty, and no segment starts at or behind the end of the stream
+    for total in (1_075_001, 1_075_000, 2_000_000, 2_074_999):
+        plan = stream.make_plan("f32", p, total, 1_000_000)
+        k = plan.n_segments
+        assert (k - 1) * plan.segment + (plan.lead if k > 1 else 0) < total
+        assert k * plan.segment + plan.lead >= total
+    # bad arguments are refused by the library, not silently planned
+    with pytest.raises(pdt.PdtError):
+        stream.make_plan("f32", p, 0, 1000)
+    with pytest.raises(pdt.PdtError):
+        stream.make_plan("f32", p, 1000, 0)
+    # the stitched table must fit: too small an output is an error, not a truncation
+    import ctypes as C
+    plan = stream.make_plan("f32", p, 3_000_000, 1_000_000)
+    stats, frames = _fake_tables(plan, np.random.default_rng(2))
+    L = stream._bind(pdt.load("f32"))
+    out = np.zeros(5, pdt.FRAME_DTYPE)
+    rc = L.pdt_stream_stitch(C.byref(plan), 0, plan.n_segments, pdt._p(stats), pdt._p(frames), frames.shape[1], pdt._p(out), out.size)
+    assert rc < 0 and b"too small" in L.pdt_last_error()
+    # a range that runs past the plan is refused
+    assert L.pdt_stream_stitch(C.byref(plan), 1, plan.n_segments, pdt._p(stats), pdt._p(frames), frames.shape[1], pdt._p(out), out.size) < 0
