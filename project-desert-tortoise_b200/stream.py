@@ -78,6 +78,13 @@ def stitch(prec: str, plan: StreamPlan, first: int, count: int, stats: np.ndarra
     return out[:k]
 
 
+def frame_times(frames: np.ndarray, sample_rate: float, interp: int = 1) -> np.ndarray:
+    """True time of every frame's sync word in seconds (float64) from its stream-global sample index.  The reference's own
+    time column (`pdt_format_frames`, which emulates it) is a float accumulated once per sample (wave.c:91-167): at 250 ksps
+    it runs fast beyond 64 s and stops advancing at 128 s, so for long streams this is the column to use."""
+    return frames["sample_index"].astype(np.float64) / (float(sample_rate) * max(int(interp), 1))
+
+
 def continuity(frames: np.ndarray) -> dict:
     """The scale-test acceptance metric: 9-bit minor-frame counter (bytes 4-5, daytimeDecode.m:4) must
     step by one, modulo 320, from each complete frame to the next."""

@@ -77,6 +77,8 @@ def test_stitch_keeps_every_frame_exactly_once():
     assert np.array_equal(out["sample_index"], nums * 25000 + 7)                  # stream-global positions
     c = stream.continuity(out)
     assert c["counter_breaks"] == 0 and c["complete"] == nums.size
+    t = stream.frame_times(out, 250000.0, plan.interp)
+    assert np.allclose(np.diff(t), 0.1) and abs(t[0] - 7 / 250000.0) < 1e-12
     # a segment that failed to lock inside its lead shows up as a counter break, not as silent loss
     stats2 = stats.copy()
     stats2[4]["n_frames"] = 0
