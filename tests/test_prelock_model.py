@@ -105,3 +105,81 @@ def test_agc_forgets_its_start_gain_bit_exactly(oracle32, fs, scale):
     W = int(22.0 * max(g0, 0.25) / decay)
     print("AGC merged after", merged_at, "samples; warm-up window", W, "gain", g0)
     assert merged_at <= W and z_serial.size - merged_at > W
+
+
+def _carrier_guess(iq_c, fs, at):
+    """What k_estimate / k_prelock compute (pdt_tiled_kernels.cuh est_carrier): decimate the 1024·D samples in front of `at`
+    by block sums, 1024-point DFT, 3-bin peak interpolation, then the phase at `at` from a coherent sum of the last 1024
+    samples.  Returns (phase, freq in rad/sample)."""
+    D = max(int(fs / (2.5 * (4500.0 + 600.0))), 1)
+    seg = iq_c[at - 1024 * D: at]
+    z = np.fft.fft(seg.reshape(1024, D).sum(axis=1))
+    bin_hz = fs / D / 1024.0
+    kmax = min(int(5100.0 / bin_hz) + 1, 510)
+    ks = np.arange(-kmax, kmax + 1)
+    k = int(ks[np.argmax(np.abs(z[ks]) ** 2)])
+    xm, x0, xp = z[k - 1], z[k], z[(k + 1) % 1024]
+    d = np.real((xm - xp) / (2.0 * x0 - xm - xp))
+    f_hz = (k + float(np.clip(d, -0.5, 0.5))) * bin_hz
+    cyc = f_hz / fs
+    j = np.arange(-1024, 0)
+    acc = np.sum(iq_c[at - 1024: at] * np.exp(-2j * np.pi * cyc * j))
+    return float(np.angle(acc)), float(2.0 * np.pi * cyc)
+
+
+def _parse(text, t_offset):
+    """frames of the chain's text output -> [(time of the sync bit in stream seconds, bytes)], complete frames only"""
+    out = []
+    for line in text.splitlines():
+        f = line.split()
+        if len(f) == 105:
+            out.append((float(f[0].rstrip("i")) + t_offset, bytes(int(b, 16) for b in f[1:])))
+    return out
+
+
+def test_stream_as_prelocked_segments_equals_serial_chain_cpu_model(oracle32):
+    """The stream mode of DESIGN §8 restated with the CPU oracle only: a 12 s stream cut into 2 s segments (+0.3 s lead,
+    +0.15 s tail), every segment behind the first started in TRACK mode from the FFT carrier guess, frames kept by ownership
+    windows — the stitched list must be the serial chain's list of minor frames, byte for byte."""
+    fs, total, segment = 250000, 3_000_000, 500_000
+    lead, tail = int(0.3 * fs), int(0.13 * fs) + 4096
+    pcm, _ = make_poes_capture(total, fs, 9, esn0_db=14.0, doppler_hz=1200.0, drift_hz_s=-150.0, amplitude=0.2)
+    iq = oracle32.pcm16_to_complex(pcm)
+    iq_c = iq.astype(np.float64).view(np.complex128)
+    serial = _parse(oracle32.chain(iq, fs)["text"], 0.0)
+    assert len(serial) >= 115
+    CH = oracle32._chain_struct()
+    D = max(int(fs / (2.5 * 5100.0)), 1)
+    pre = 1024 * D
+    n_seg = -(-(total - lead) // segment)
+    stitched = []
+    for s in range(n_seg):
+        start = s * segment
+        stop = min(start + lead + segment + tail, total)
+        lo = 0.0 if s == 0 else (start + lead) / fs
+        hi = np.inf if s == n_seg - 1 else (start + segment + lead) / fs
+        c = oracle32.lib.pdto_chain_new(0, float(fs), 10000, 0)
+        try:
+            first = start
+            if s > 0:
+                ch = CH.from_address(c)
+                phase, freq = _carrier_guess(iq_c, fs, start + pre)
+                bw, damp = np.float32(10.3451 * (2.0 * np.pi / fs)), np.float32(0.999)
+                p = ch.pll
+                p.first_lock, p.damp = 0, damp                                                  # latched: track mode
+                p.alpha = (4.0 * damp * bw) / (1.0 + 2.0 * damp * bw + bw * bw)                # CarrierTrackingPLL.c:272-273
+                p.beta = (4.0 * bw * bw) / (1.0 + 2.0 * damp * bw + bw * bw)
+                p.max_freq, p.min_freq = 2.0 * np.pi * 4500.0 / fs, -2.0 * np.pi * 4500.0 / fs
+                p.phase, p.freq, p.locksig = phase, freq, 1.0
+                first = start + pre
+            oracle32.lib.pdto_chain_feed(c, iq[2 * first: 2 * stop].ctypes.data, stop - first)
+            ln = C.c_size_t(0)
+            text = C.string_at(oracle32.lib.pdto_chain_text(c, C.byref(ln)), ln.value).decode()
+        finally:
+            oracle32.lib.pdto_chain_free(c)
+        stitched += [(t, b) for t, b in _parse(text, first / fs) if lo <= t < hi]
+    assert [b for _, b in stitched] == [b for _, b in serial]
+    # (the time columns themselves are not compared: the reference accumulates its time axis in float, wave.c:167, which
+    # drifts by several per cent within seconds — each segment restarts it, the serial chain does not)
+    ts = [t for t, _ in stitched]
+    assert all(0.07 < b - a < 0.13 for a, b in zip(ts, ts[1:]))                                # one frame per 0.1 s (float time axis), none twice
