@@ -207,6 +207,9 @@ uint64_t    pdt_stream_segment_length(const pdt_stream_plan *plan, uint32_t s);
  * Returns the number of frames written, or <0. */
 long        pdt_stream_stitch(const pdt_stream_plan *plan, uint32_t first, uint32_t n, const pdt_capture_stats *stats,
                               const pdt_frame *frames, uint32_t max_frames, pdt_frame *out, uint32_t out_cap);
+/* Post-checks of a stitched list (parity word 103, counter, continuity ACROSS the seams): the host twin of
+ * pdt_frame_checks, whose device table is per segment. */
+int         pdt_stream_frame_checks(const pdt_frame *frames, uint32_t n_frames, pdt_frame_quality *quality_out);
 /* Synthetic stream slice: samples [start, start + n) of ONE seeded POES stream of total_samples (Doppler crossing from
  * f0 to -f0 over the whole stream), written at d_iq. */
 int         pdt_synth_poes_stream_device(void *d_iq, int pcm16, uint64_t start_sample, uint64_t n_samples,

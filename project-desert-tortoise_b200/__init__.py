@@ -165,7 +165,7 @@ EXPORTED_SYMBOLS = [
     "pdt_create", "pdt_destroy", "pdt_get_params", "pdt_get_taps", "pdt_demod_device", "pdt_demod_host", "pdt_demod_host_async",
     "pdt_fetch",
     "pdt_result_tables", "pdt_format_frames", "pdt_launch_count", "pdt_synth_poes_device", "pdt_engine",
-    "pdt_demod_segments_device", "pdt_stream_plan_make", "pdt_stream_segment_length", "pdt_stream_stitch", "pdt_synth_poes_stream_device",
+    "pdt_demod_segments_device", "pdt_stream_plan_make", "pdt_stream_segment_length", "pdt_stream_stitch", "pdt_stream_frame_checks", "pdt_synth_poes_stream_device",
     "pdt_frame_checks", "pdt_tiled_counters", "pdt_set_profiling", "pdt_kernel_times", "pdt_timeline", "pdt_debug_acq_prof",
     # include/pdt_legacy.h
     "FindSignalAmplitude", "Squelch", "StaticGain", "NormalizingAGC", "NormalizingAGCC", "CarrierTrackPLL", "arctan2",

@@ -983,6 +983,35 @@ long pdt_stream_stitch(const pdt_stream_plan *plan, uint32_t first, uint32_t n, 
     return (long)k;
 }
 
+// Host twin of k_frame_checks for a STITCHED frame list (the device table is per segment; continuity across the seams only
+// exists after the stitch).  A few hundred bytes per frame, ten frames per second of signal: host work by nature.
+int pdt_stream_frame_checks(const pdt_frame *frames, uint32_t n_frames, pdt_frame_quality *quality_out)
+{
+    if ((!frames || !quality_out) && n_frames) return fail(PDT_EINVAL, "bad arguments");
+    int prev = -1;
+    for (uint32_t f = 0; f < n_frames; f++) {
+        pdt_frame_quality r; memset(&r, 0, sizeof r);
+        if (frames[f].complete && frames[f].n_bytes == PDT_FRAME_MAX_BYTES) {
+            const uint8_t *b = frames[f].bytes;
+            r.valid = 1;
+            r.counter = (uint16_t)(((b[4] & 1u) << 8) | b[5]);                          // daytimeDecode.m:4
+            r.spacecraft = b[2];
+            const int lo[5] = {2, 19, 36, 53, 70}, hi[5] = {18, 35, 52, 69, 86};        // checkParity.m:20-90
+            unsigned bad = 0;
+            for (int g = 0; g < 5; g++) {
+                unsigned ones = 0;
+                for (int k = lo[g]; k <= hi[g]; k++) ones += (unsigned)__builtin_popcount((unsigned)b[k]);
+                if ((ones & 1u) != ((b[103] >> (5 - g)) & 1u)) bad |= 1u << (4 - g);
+            }
+            r.parity_bits = (uint8_t)bad; r.parity_ok = bad == 0;
+            r.continuous = (prev < 0) || (r.counter == (unsigned)((prev + 1) % 320));
+            prev = r.counter;
+        }
+        quality_out[f] = r;
+    }
+    return PDT_OK;
+}
+
 int pdt_synth_poes_stream_device(void *d_iq, int pcm16, uint64_t start_sample, uint64_t n_samples, uint64_t total_samples,
                                  double sample_rate, uint64_t seed, void *stream)
 {

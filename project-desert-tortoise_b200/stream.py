@@ -35,6 +35,7 @@ def _bind(L):
     L.pdt_stream_stitch.restype = C.c_long
     L.pdt_stream_stitch.argtypes = [C.POINTER(StreamPlan), u32, u32, vp, vp, u32, vp, u32]
     L.pdt_demod_segments_device.argtypes = [vp, vp, C.c_int, u32, u64, vp, u32, vp]
+    L.pdt_stream_frame_checks.argtypes = [vp, u32, vp]
     L.pdt_synth_poes_stream_device.argtypes = [vp, C.c_int, u64, u64, u64, C.c_double, u64, vp]
     L._stream_bound = True
     return L
@@ -76,6 +77,16 @@ def stitch(prec: str, plan: StreamPlan, first: int, count: int, stats: np.ndarra
     if k < 0:
         raise _pkg.PdtError(L.pdt_last_error().decode())
     return out[:k]
+
+
+def frame_checks(prec: str, frames: np.ndarray) -> np.ndarray:
+    """Parity word 103, 9-bit counter, spacecraft id and counter continuity of a stitched frame list (QUALITY_DTYPE);
+    `continuous` now spans the seams between segments."""
+    L = _bind(_pkg.load(prec))
+    frames = np.ascontiguousarray(frames, _pkg.FRAME_DTYPE)
+    q = np.zeros(frames.size, _pkg.QUALITY_DTYPE)
+    _pkg._check(L, L.pdt_stream_frame_checks(_pkg._p(frames), frames.size, _pkg._p(q)))
+    return q
 
 
 def frame_times(frames: np.ndarray, sample_rate: float, interp: int = 1) -> np.ndarray:

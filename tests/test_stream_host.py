@@ -77,13 +77,20 @@ def test_stitch_keeps_every_frame_exactly_once():
     assert np.array_equal(out["sample_index"], nums * 25000 + 7)                  # stream-global positions
     c = stream.continuity(out)
     assert c["counter_breaks"] == 0 and c["complete"] == nums.size
+    q = stream.frame_checks("f32", out)                                         # host twin of the device post-checks
+    assert q["valid"].all() and q["continuous"].all() and np.array_equal(q["counter"], nums % 320)
+    from tests.synth_ref import check_parity
+    assert np.array_equal(q["parity_ok"].astype(bool), np.array([check_parity(f["bytes"]) for f in out]))
+    assert 0 < q["parity_ok"].sum() < q.size                                    # random fake payload: both outcomes occur
     t = stream.frame_times(out, 250000.0, plan.interp)
     assert np.allclose(np.diff(t), 0.1) and abs(t[0] - 7 / 250000.0) < 1e-12
     # a segment that failed to lock inside its lead shows up as a counter break, not as silent loss
     stats2 = stats.copy()
     stats2[4]["n_frames"] = 0
-    c2 = stream.continuity(stream.stitch("f32", plan, 0, plan.n_segments, stats2, frames))
+    out2 = stream.stitch("f32", plan, 0, plan.n_segments, stats2, frames)
+    c2 = stream.continuity(out2)
     assert c2["counter_breaks"] == 1 and c2["missing_frames"] == 40
+    assert int((stream.frame_checks("f32", out2)["continuous"] == 0).sum()) == 1
     # stitching ranges separately and concatenating is the same as stitching everything (what the ranks do)
     a = stream.stitch("f32", plan, 0, 4, stats[:4], frames[:4])
     b = stream.stitch("f32", plan, 4, plan.n_segments - 4, stats[4:], frames[4:])
