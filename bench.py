@@ -4,22 +4,25 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N … bench.py --gpus N …
 
-A "step" is one pass of the fused chain kernel over one batch of synthetic POES-TIP captures that is already
-resident in HBM (weak scaling: every GPU owns `--captures` captures of `--samples` IQ samples; at N=1 this is
-BASELINE.json configs[3]'s 1024 x 1 M-sample batch @ 250 ksps on one GPU, with configs[1]'s signal parameters).
-`value` is whole-job Msamples/s from CUDA events on the launch stream (max over ranks); `e2e` is the same metric
-through the host-buffer C-ABI call (pdt_demod_host: pinned host IQ -> H2D -> kernel -> D2H of stats+frames).
-`roofline` is for the dominant (only) kernel of the step; `cpu_baseline` times the UNMODIFIED reference
-(oracle/_ref/libref_f32.so, one process per capture — the reference is single-threaded with static state) on a
-bounded sample of the same captures on the box's host cores.
+A "step" is one pass of the whole chain (tiled engine: ~16 kernels, StaticGain -> PLL acquisition/track -> derotation + FIR
+-> AGC -> Gardner -> Manchester -> ByteSync) over one batch of synthetic POES-TIP captures that is already resident in HBM
+(weak scaling: every GPU owns `--captures` captures of `--samples` IQ samples; at N=1 this is BASELINE.json configs[3]'s
+1024 x 1 M-sample batch @ 250 ksps on one GPU, with configs[1]'s signal parameters).  `value` is whole-job Msamples/s
+from CUDA events on the launch stream (max over ranks); `e2e` is the same metric through the host-buffer C-ABI call
+(pdt_demod_host_async + pdt_fetch: pinned host IQ -> H2D -> kernels -> D2H of stats+frames).  `roofline` is for `k_front`,
+the fused NCO-derotation + FIR/interpolator kernel that BASELINE.json's north_star sets the HBM target on, by SURVEY §8d's
+contract bytes (8 + 4·L per input sample); the per-kernel table is in `kernels`.  `cpu_baseline` times the UNMODIFIED
+reference (oracle/_ref/libref_f32.so, one process per capture — the reference is single-threaded with static state) on a
+bounded sample of the same captures on the box's host cores and checks the GPU's frame BYTES of those captures against it.
 
 `--impl reference` times only that CPU reference arm (rank 0; other ranks exit) and prints the same JSON shape.
 
-Extras on the same line (N=1): `e2e_pcm16` (the e2e leg fed with raw int16 PCM, 4 B/sample over PCIe), `kernels` (per-kernel
-device times and HBM fractions), `single_capture_10M` (configs[1]: one stream, serial semantics, time-tiled on one GPU) and
-`stream_256M` (configs[4] shape in small: one stream as overlapping segments).  Other workloads, one JSON line each:
-`--fs 50000|18750` (the ×3 / ×8 interpolating rates), `--pcm16`, and `--stream N [--fs 2000000]` — ONE stream of N samples
-time-tiled across the GPUs (strong scaling; also under torchrun).
+Extras on the same line: `e2e_pcm16` (the e2e leg fed with raw int16 PCM, 4 B/sample over PCIe), `kernels`, `single_capture_10M`
+(configs[1]: one stream, serial semantics, time-tiled on one GPU), `stream_256M` (configs[4] shape in small), and for N > 1
+`strong_scaling` (configs[3] as written: the FIXED `--captures`-file batch sharded over the N GPUs) and `per_rank`.
+Other workloads, one JSON line each: `--fs 50000|18750` (the x3 / x8 interpolating rates), `--pcm16`, `--mode argos`
+(configs[2]: double-precision ARGOS bursts), and `--stream N [--fs 2000000]` — ONE stream of N samples time-tiled across the
+GPUs (strong scaling; also under torchrun).
 """
 from __future__ import annotations
 
@@ -67,10 +70,15 @@ def _cpu_worker_run(path):
     iq = np.ascontiguousarray(iq, np.float32)
     t0 = time.perf_counter()
     if _W["kind"] == "reference":
-        frames = po.ref_chain_poes(iq, FS)
+        frames = po.ref_chain_poes(iq, FS, out_path=path + ".txt")
+        dt = time.perf_counter() - t0
+        text = open(path + ".txt").read()
+        os.remove(path + ".txt")
     else:
-        frames = po.Oracle("f32").chain(iq, FS)["total_frames"]
-    return time.perf_counter() - t0, int(frames)
+        r = po.Oracle("f32").chain(iq, FS)
+        dt = time.perf_counter() - t0
+        frames, text = r["total_frames"], r["text"]
+    return dt, int(frames), text
 
 
 def cpu_arm(captures, steps, warmup, cores=None):
@@ -104,7 +112,7 @@ def cpu_arm(captures, steps, warmup, cores=None):
             os.remove(p)
         os.rmdir(tmp)
     return dict(value=n_samples * steps / dt / 1e6, ms_per_step=dt / steps * 1e3, cores=cores, kind=kind,
-                frames=frames, n_captures=len(captures), n_samples=n_samples)
+                frames=frames, n_captures=len(captures), n_samples=n_samples, texts=[r[2] for r in res])
 
 
 def reference_arm(args):
@@ -329,8 +337,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--captures", type=int, default=1024, help="captures per GPU")
     ap.add_argument("--samples", type=int, default=1_000_000, help="IQ samples per capture")
-    ap.add_argument("--fs", type=int, default=FS, help="sample rate: 250000 -> L=1 (headline), 75000 -> 2, 50000 -> 3, 37500 -> 4 "
-                                                       "(tiled engine), 18750 -> the historical 8x interpolator (exact engine)")
+    ap.add_argument("--fs", type=int, default=FS, help="sample rate: 250000 -> L=1 (headline), 75000 -> 2, 50000 -> 3, 37500 -> 4, "
+                                                       "18750 -> the historical 8x interpolator (all on the tiled engine)")
     ap.add_argument("--stream", type=int, default=0, help="BASELINE configs[4]: ONE stream of this many samples, time-tiled into "
                                                           "overlapping segments over the GPUs (strong scaling); not the default bench")
     ap.add_argument("--segment", type=int, default=0, help="--stream: samples owned per segment (default 2 s of signal)")
@@ -338,6 +346,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-single", action="store_true")
+    ap.add_argument("--no-gather", action="store_true", help="N > 1 diagnostic: skip the NCCL all-gather of the frame tables")
+    ap.add_argument("--strong-shards", type=int, default=0,
+                    help="N = 1 diagnostic: also run this GPU's share of an N-way strong-scaling step (--captures / N captures per step)")
     ap.add_argument("--inflight", type=int, default=0,
                     help="batches in flight: consecutive steps alternate between this many contexts/streams, so the serial "
                          "acquisition tail of one batch overlaps the bulk kernels of the next (1 = strictly one batch at a time; "
@@ -369,6 +380,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
+    numa = pdist.bind_to_gpu_numa(local)      # before any pinned allocation: first-touch puts the staging buffers next to the GPU
     C_, n = args.captures, args.samples
     elem = torch.int16 if args.pcm16 else torch.float32
     bytes_per_sample = 4 if args.pcm16 else 8
@@ -379,73 +391,139 @@ def main():
         raise SystemExit("synth failed: " + L.pdt_last_error().decode())
     params = pdt.default_params("f32", pdt.PDT_MODE_POES, FS)
     max_frames = int(n / FS * 10) + 8
-    d = pdt.Demod("f32", params, C_, n, max_frames)
-    ds, df, _ = d.result_tables()
-    frames_t = torch.as_tensor(_Raw(df, C_ * max_frames * 120), device="cuda").view(C_, max_frames * 120)
+    row_bytes = max_frames * 120
+
+    def frame_table(ctx, rows):
+        return torch.as_tensor(_Raw(ctx.result_tables()[1], rows * row_bytes), device="cuda").view(rows, row_bytes)
+
+    class Rotation:
+        """`m` contexts of `caps` captures used in rotation, each on its own side stream; the only exchange (N > 1) is the
+        all-gather of the decoded minor-frame tables.  The table of a finished batch is copied (device to device, a few MB)
+        into a staging ring on the batch's own stream and gathered from there on ONE communication stream, so a compute
+        stream never waits for a collective: ranks are coupled only through the depth of the ring (2·m steps)."""
+
+        def __init__(self, caps, m, groups=0):
+            self.caps, self.m = caps, m
+            self.ctxs = [pdt.Demod("f32", params, caps, n, max_frames) for _ in range(m)]
+            for c in self.ctxs:
+                if groups:
+                    c.set_groups(groups)
+            self.tables = [frame_table(c, caps) for c in self.ctxs]
+            self.side = [torch.cuda.Stream() for _ in range(m)]
+            self.step_no = 0
+            self.gather = world > 1 and not args.no_gather
+            if self.gather:
+                self.rows = caps if caps == C_ else max(caps, (C_ + world - 1) // world)     # rows per rank in the gathered table
+                self.comm = torch.cuda.Stream()
+                self.ring = [torch.zeros((self.rows, row_bytes), dtype=torch.uint8, device="cuda") for _ in range(2 * m)]
+                self.done = [None] * (2 * m)
+                self.gathered = [torch.empty((world * self.rows, row_bytes), dtype=torch.uint8, device="cuda") for _ in range(2)]
+
+        def step(self):
+            k, slot = self.step_no % self.m, self.step_no % (2 * self.m)
+            self.step_no += 1
+            sk = self.side[k]
+            with torch.cuda.stream(sk):
+                self.ctxs[k].demod_device(d_iq.data_ptr(), self.caps, n, pcm16=args.pcm16, stream=sk.cuda_stream)
+                if self.gather:
+                    if self.done[slot] is not None:
+                        sk.wait_event(self.done[slot])                 # the gather that last read this ring slot (2·m steps ago)
+                    self.ring[slot][: self.caps].copy_(self.tables[k], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(sk)
+            if self.gather:
+                with torch.cuda.stream(self.comm):
+                    self.comm.wait_event(ev)
+                    dist.all_gather_into_tensor(self.gathered[slot & 1], self.ring[slot])
+                    self.done[slot] = torch.cuda.Event()
+                    self.done[slot].record(self.comm)
+
+        def fork(self):
+            for sk in self.side:
+                sk.wait_stream(torch.cuda.current_stream())
+
+        def join(self):
+            for sk in self.side:
+                torch.cuda.current_stream().wait_stream(sk)
+            if self.gather:
+                torch.cuda.current_stream().wait_stream(self.comm)
+
+        def close(self, keep=0):
+            for c in self.ctxs[keep:]:
+                c.close()
+            del self.tables[keep:]
+            del self.ctxs[keep:]
+
+    def timed(rot, steps, warmup, sampler=None):
+        """W untimed + K timed steps bracketed by barrier + synchronize; device time (CUDA events), max over ranks."""
+        rot.fork()
+        for _ in range(warmup):
+            rot.step()
+        rot.join()
+        torch.cuda.synchronize()
+        if sampler:
+            sampler.start()
+            time.sleep(0.3)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        launches0 = L.pdt_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        rot.fork()
+        for _ in range(steps):
+            rot.step()
+        rot.join()
+        e1.record()
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        if world > 1:
+            dist.barrier()
+        ms_own = e0.elapsed_time(e1)
+        launches = L.pdt_launch_count() - launches0
+        clocks = sampler.stop(t0, t1) if sampler else None
+        ms, per_rank = ms_own, None
+        if world > 1:
+            mine = torch.tensor([ms_own, (clocks or {}).get("sm_mhz", 0.0)], dtype=torch.float64, device="cuda")
+            allr = torch.empty((world, 2), dtype=torch.float64, device="cuda")
+            dist.all_gather_into_tensor(allr, mine)
+            allr = allr.cpu().numpy()
+            ms = float(allr[:, 0].max())
+            per_rank = {"ms_per_step": [round(float(x) / steps, 3) for x in allr[:, 0]],
+                        "sm_mhz": [float(x) for x in allr[:, 1]]}
+        return ms / steps, launches, clocks, per_rank
+
     # batches in flight: context k (own workspaces, own internal streams) on side stream k; joined to the main stream at the end
     inflight = args.inflight if args.inflight > 0 else (4 if args.steps >= 8 else 3)
     inflight = max(1, min(inflight, max(args.steps, 1)))
-    ctxs = [d] + [pdt.Demod("f32", params, C_, n, max_frames) for _ in range(inflight - 1)]
-    tables = [frames_t] + [torch.as_tensor(_Raw(c.result_tables()[1], C_ * max_frames * 120), device="cuda").view(C_, max_frames * 120)
-                           for c in ctxs[1:]]
-    side = [torch.cuda.Stream() for _ in range(inflight)] if inflight > 1 else []
-    gathered = [torch.empty((world * C_, max_frames * 120), dtype=torch.uint8, device="cuda") for _ in range(inflight)] if world > 1 else None
-    step_no = [0]
-
-    def step():
-        k = step_no[0] % inflight
-        step_no[0] += 1
-        if inflight == 1:
-            d.demod_device(d_iq.data_ptr(), C_, n, pcm16=args.pcm16, stream=stream)
-            if world > 1:   # the only exchange on this path: gather the decoded minor frames (≤ 104 B x 10 frames/s/capture)
-                dist.all_gather_into_tensor(gathered[0], frames_t)
-            return
-        with torch.cuda.stream(side[k]):
-            ctxs[k].demod_device(d_iq.data_ptr(), C_, n, pcm16=args.pcm16, stream=side[k].cuda_stream)
-            if world > 1:   # equal shards: the plain all-gather (dist.gather_tables handles ragged shards)
-                dist.all_gather_into_tensor(gathered[k], tables[k])
-
-    def join():
-        for sk in side:
-            torch.cuda.current_stream().wait_stream(sk)
-
-    for sk in side:
-        sk.wait_stream(torch.cuda.current_stream())
-    for _ in range(args.warmup):
-        step()
-    if side:
-        join()
-    torch.cuda.synchronize()
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
-        time.sleep(0.3)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    launches0 = L.pdt_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    if side:
-        join()
-    e1.record()
-    torch.cuda.synchronize()
-    t1 = time.perf_counter()
-    if world > 1:
-        dist.barrier()
-    ms = e0.elapsed_time(e1)
-    launches = L.pdt_launch_count() - launches0
-    clocks = sampler.stop(t0, t1) if sampler else None
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    ms_step = ms / args.steps
+    rot = Rotation(C_, inflight)
+    d, ctxs = rot.ctxs[0], rot.ctxs
+    ms_step, launches, clocks, per_rank = timed(rot, args.steps, args.warmup, ClockSampler(local))
     total_samples = C_ * n * world
     value = total_samples / (ms_step * 1e-3) / 1e6
+
+    # ---- BASELINE configs[3] as written: the FIXED batch of `--captures` files sharded over the N GPUs (strong scaling) ----
+    strong = None
+    shards = world if world > 1 else args.strong_shards
+    if shards > 1:
+        cs = pdist.shard_range(C_, rank if world > 1 else 0, shards)[1]
+        m_s = max(1, min(16, 4 * shards, 2048 // max(cs, 1)))
+        rot.close(keep=2)                              # two contexts stay for the e2e leg; the rest make room
+        rs = Rotation(cs, m_s, groups=1 if cs <= 256 else 0)
+        k_s = max(args.steps, 3 * m_s)
+        ms_s, _, _, pr_s = timed(rs, k_s, max(args.warmup, m_s))
+        strong = {"scaling": "strong", "value": C_ * n / (ms_s * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms_s, "steps": k_s, "captures_total": C_, "captures_per_gpu": cs, "shards": shards,
+                  "batches_in_flight": m_s, "per_rank": pr_s,
+                  "note": "BASELINE configs[3] as written: ONE fixed batch of captures sharded over the GPUs, frames gathered over "
+                          "NCCL every step; per-GPU work shrinks with N while the serial acquisition tail of a batch does not, so "
+                          "more (smaller) batches are kept in flight"}
+        if world == 1:
+            strong["value"] = cs * n / (ms_s * 1e-3) / 1e6
+            strong["note"] = (f"single-GPU view of an N={shards} strong-scaling run: this GPU's shard ({cs} captures per step); "
+                              f"whole-job value would be {shards}x if all ranks keep this pace")
+        rs.close()
+        del rs
 
     # ---- per-kernel device times of one more step (CUDA events on the launch stream, recorded by the library) ----
     tiled = d.engine == pdt.PDT_ENGINE_TILED
@@ -486,8 +564,15 @@ def main():
     alg = {"k_chain_exact": bytes_per_sample, "k_sp": bytes_per_sample + 4, "k_front": bytes_per_sample + 4 + 4 * Lf,
            "k_pll_core": 8, "k_agc_core": 8 * Lf, "k_gardner": 4 * Lf, "k_bits": 0.8 * Lf,
            "k_acquire": (bytes_per_sample + 8) * acq_samples / float(C_ * n)}
-    dom_name, k_ms = kernels[0]
-    alg_bytes = int(C_ * n * alg.get(dom_name, bytes_per_sample))
+    # roofline: k_front, the kernel BASELINE.json's north_star puts the >= 60 % HBM target on ("fused FIR+interp+PLL kernel":
+    # NCO sincos + derotation + xL interpolating FIR).  Algorithmic bytes by SURVEY §8d's CONTRACT: 8 + 4·L per input sample
+    # (cf32 in, L filtered floats out; 4 + 4·L with PCM ingest).  What the kernel really moves is 4 B more (the NCO phase
+    # stream, which exists because the PLL recurrence is a separate, serial kernel): `achieved_actual` below.
+    kd = dict(kernels)
+    dom_name = "k_front" if "k_front" in kd else kernels[0][0]
+    k_ms = kd[dom_name]
+    contract = (bytes_per_sample + 4 * Lf) if dom_name == "k_front" else alg.get(dom_name, bytes_per_sample)
+    alg_bytes = int(C_ * n * contract)
     achieved = alg_bytes / (k_ms * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
@@ -497,10 +582,14 @@ def main():
         traffic = tj.get(key, {}).get("dram_bytes_per_launch")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": dom_name, "kernel_ms": k_ms, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes,
-                "note": "dominant kernel by device time with all captures in one launch sequence; it is the serial acquisition "
-                        "(latency-bound by the per-sample PLL recurrence), not a streaming kernel; per-kernel table in `kernels` "
-                        "(ms, GB/s algorithmic, fraction of HBM peak); the streaming kernels k_sp / k_front are the HBM-bound ones"}
+                "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_bytes_per_sample": contract,
+                "achieved_actual": C_ * n * alg.get(dom_name, contract) / (k_ms * 1e-3) / 1e9,
+                "frac_actual": C_ * n * alg.get(dom_name, contract) / (k_ms * 1e-3) / 1e9 / peak,
+                "note": f"k_front<{Lf}> over the whole batch ({C_} x {n} samples; both launches of a batch — the captures that "
+                        "latched in the first acquisition pass and the slow ones — summed), CUDA events on the launch stream with "
+                        "the batch's kernels in one sequence; `achieved` uses the SURVEY §8d contract bytes (8 + 4L per sample), "
+                        "`achieved_actual` the bytes the kernel must move today (+4 B/sample NCO phase stream); the step's largest "
+                        "kernel by TIME is the serial acquisition (k_acquire, latency-bound), see `kernels`"}
     ktable = [{"kernel": nm, "ms": round(t_ms, 4),
                "alg_GBps": round(C_ * n * alg[nm] / (t_ms * 1e-3) / 1e9, 1) if nm in alg and t_ms > 0 else None,
                "hbm_frac": round(C_ * n * alg[nm] / (t_ms * 1e-3) / 1e9 / peak, 4) if nm in alg and t_ms > 0 else None}
@@ -520,7 +609,9 @@ def main():
                    "interp": d.params.interp, "taps": d.params.taps, "chunk": d.params.chunk,
                    "l2": f"inputs {C_ * n * bytes_per_sample / 1e9:.2f} GB per GPU, far larger than the 126 MB L2 (no flush needed)",
                    "parallelism": f"captures sharded over {world} GPU(s), frames all-gathered over NCCL" if world > 1 else "one GPU",
-                   "batches_in_flight": inflight},
+                   "batches_in_flight": inflight, "numa": numa,
+                   "gather": (None if world == 1 else ("off (--no-gather)" if args.no_gather else
+                              "frame table copied to a staging ring, all-gathered on one communication stream"))},
         "gpu_launches": int(launches), "roofline": roofline, "kernels": ktable,
         "chain_level": {"algorithmic_GBps": chain_gbps, "hbm_frac": chain_gbps / peak,
                         "note": f"{bytes_per_sample} B per input IQ sample over the whole step"},
@@ -533,6 +624,10 @@ def main():
     }
     if clocks:
         line["clocks"] = clocks
+    if per_rank:
+        line["per_rank"] = per_rank
+    if strong:
+        line["strong_scaling"] = strong
 
     # ---- e2e: host buffers through the C-ABI --------------------------------------------------------
     # Same batches-in-flight rotation as above, through pdt_demod_host_async / pdt_fetch: every step copies its batch from
@@ -583,6 +678,9 @@ def main():
             if primary:
                 assert frames_ok, (got, want)
             bps = 4 if pcm else 8
+            if not frames_ok:       # a leg whose decode regressed has no throughput number
+                return {"value": None, "unit": UNIT, "invalid": f"decoded {got} frames, the cf32 batch gives {want}",
+                        "input": "pcm16" if pcm else "cf32", "frames_check_ok": False}
             return {"value": e2e_caps * n * world * e2e_steps / tt / 1e6, "unit": UNIT,
                     "h2d_bytes_per_step": int(e2e_caps * n * bps),
                     "d2h_bytes_per_step": int(d2h[0]), "steps": e2e_steps, "batches_in_flight": m,
@@ -665,10 +763,25 @@ def main():
             x = d_iq[c * n * 2:(c + 1) * n * 2].cpu().numpy()
             caps.append(x.astype(np.float32) / np.float32(32768.0) if args.pcm16 else x)
         r = cpu_arm(caps, 1, 1, cores)
+        # parity of the bench batch itself: every minor frame the CPU arm printed for these captures, byte for byte
+        # (row count, inverted-sync mark, all bytes incl. a trailing partial frame) against the GPU's frame table
+        from tests.synth_ref import parse_frames_text
+        rows_cpu = rows_gpu = mismatched = 0
+        for c in range(k):
+            want_rows = parse_frames_text(r["texts"][c])
+            nf = min(int(stats["n_frames"][c]), max_frames)
+            got_rows = [(bool(f["inverse"]), bytes(f["bytes"][: f["n_bytes"]])) for f in frames[c][:nf]]
+            rows_cpu += len(want_rows)
+            rows_gpu += len(got_rows)
+            if [(w[1], bytes(w[2])) for w in want_rows] != got_rows:
+                mismatched += 1
         line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
                                 "sample": f"first {k} captures of the GPU batch ({k} x {n} samples), one process per capture",
                                 "frames": r["frames"],
-                                "gpu_frames_same_captures": int(stats["n_frames"][:k].sum())}
+                                "gpu_frames_same_captures": int(stats["n_frames"][:k].sum()),
+                                "frame_bytes_check": {"captures": k, "rows_cpu": rows_cpu, "rows_gpu": rows_gpu,
+                                                      "captures_with_any_difference": mismatched, "equal": mismatched == 0}}
+        assert mismatched == 0, "GPU frame bytes differ from the reference's on the bench batch"
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

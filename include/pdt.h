@@ -109,7 +109,15 @@ typedef struct pdt_capture_stats {
     double   norm_factor;    /* StaticGain result */
     double   avg_phase;      /* last CarrierTrackPLL return value */
     double   final_phase, final_freq, final_gain, final_next;   /* loop states at the end (re-stitch / debugging) */
+    int32_t  prelocked;      /* stream segments only (pdt_demod_segments_device): 0 = the reference's acquisition sweep ran
+                                (`locked`/`lock_sample`/`lock_freq_hz` are a real latch of CarrierTrackingPLL.c:266-274);
+                                1 = started in TRACK mode from the FFT carrier estimate, no latch ever fired (`locked` is
+                                then 1 by construction and lock_freq_hz is the estimate); 2 = the estimate was rejected
+                                (spectral peak below PDT_PRELOCK_MIN_SNR times the mean) and the segment fell back to
+                                the reference's sweep from zero */
+    float    prelock_snr;    /* peak / mean of |DFT|^2 over the searched band of the carrier estimate (0 when not estimated) */
 } pdt_capture_stats;
+#define PDT_PRELOCK_MIN_SNR 16.0f
 
 /* Optional per-capture trace taps (device pointers, any may be NULL).  REAL = float in libpdt_f32, double in f64. */
 typedef struct pdt_traces {
@@ -194,6 +202,11 @@ typedef struct pdt_stream_plan {
     uint64_t total_samples, segment, lead, tail;
     uint32_t n_segments;
     uint32_t interp;             /* samples of pdt_frame.sample_index per input sample (max(params.interp, 1)) */
+    uint32_t seam_tol;           /* ownership tolerance in interpolated samples (two symbols): a sync position is not
+                                    bit-identical between neighbouring segments (own chunk grid, chunk-relative float
+                                    Gardner state), so a frame within seam_tol of a window edge is claimed by BOTH
+                                    neighbours and the later copy is dropped by position (see pdt_stream_stitch) */
+    uint32_t pad;
 } pdt_stream_plan;
 /* lead / tail 0 = defaults (0.3 s and 0.13 s + 4096 samples of signal).  Captures handed to pdt_demod_segments_device():
  * d_iq = stream base (+ first·segment), stride_samples = segment, n_samples[s] = pdt_stream_segment_length(plan, s). */
@@ -204,6 +217,13 @@ int         pdt_demod_segments_device(pdt_ctx *ctx, const void *d_iq, int pcm16,
 uint64_t    pdt_stream_segment_length(const pdt_stream_plan *plan, uint32_t s);
 /* Stitch the tables of segments [first, first + n) (stats[n], frames[n·max_frames]) into out[]: owned frames only, in
  * stream order, sample_index rewritten to the stream-global interpolated-sample index (bit_index is left segment-local).
+ * Ownership is robust against the +-1-symbol position jitter between neighbouring segments: segment s claims
+ * [lo - seam_tol, hi + seam_tol) and a frame whose global position lies within 2·seam_tol of the frame emitted just
+ * before it is the same minor frame seen twice and is skipped (minor frames are 1664 symbols apart).  The outer edges of
+ * the range [first, first + n) stay exact, so ranges stitched separately (one per rank) concatenate to a partition of the
+ * stream; stitching the gathered tables in ONE call (stream.gather_and_stitch) is the form that is jitter-proof at every seam.
+ * Equality with the serial chain holds from the point where the serial chain itself has locked: segments start in track
+ * mode whether or not the reference's sweep would have latched by then (pdt_capture_stats.prelocked).
  * Returns the number of frames written, or <0. */
 long        pdt_stream_stitch(const pdt_stream_plan *plan, uint32_t first, uint32_t n, const pdt_capture_stats *stats,
                               const pdt_frame *frames, uint32_t max_frames, pdt_frame *out, uint32_t out_cap);
@@ -227,6 +247,12 @@ long        pdt_format_frames(const pdt_ctx *ctx, const pdt_frame *frames, uint3
  *   out[0] PLL tiles re-run, out[1] AGC tiles re-run, out[2] acquisition restarts, out[3] PLL tiles per capture (max). */
 int         pdt_engine(const pdt_ctx *ctx);
 int         pdt_tiled_counters(pdt_ctx *ctx, uint32_t out[4], void *stream);
+
+/* Capture groups of the tiled engine: a batch is cut into up to `max_groups` groups of >= 64 captures that run the kernel
+ * sequence on internal streams (one group's latency-bound kernels overlap another's streaming kernels).  0 = default (3).
+ * Many small batches in flight (strong scaling: a fixed batch sharded over several GPUs) do better with 1: the overlap
+ * then comes from the other batches and the process stays within the hardware work queues. */
+int         pdt_set_groups(pdt_ctx *ctx, int max_groups);
 
 /* Per-kernel device times of the tiled engine: when enabled, a CUDA event is recorded on the launch stream after
  * every kernel of a batch; pdt_kernel_times() synchronises and returns how many kernels the last batch launched,

@@ -282,6 +282,37 @@ void pdto_agc_run(pdto_agc *s, pdto_real *x, unsigned long n, pdto_real initial,
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * AGC.c:164-200 NormalizingAGCC, AGC.c:6-20 FindSignalAmplitude (exported by the reference, not called by its drivers)
+ * ---------------------------------------------------------------------------------------------- */
+void pdto_agcc_run(pdto_agc *s, pdto_real *iq, unsigned long n, pdto_real initial, pdto_real loop_gain)
+{
+    const pdto_real desired = 5;
+    if (!s->init) { s->init = 1; s->gain = initial; }      /* :177-181 */
+    for (unsigned long i = 0; i < n; i++) {
+        iq[2 * i] *= s->gain; iq[2 * i + 1] *= s->gain;    /* complex *= real (:185) */
+#if PDT_USE_FLOATS
+        /* :188 calls fabsf() on a float complex: fabsf is NOT one of <tgmath.h>'s macros, so the argument converts to
+         * float by dropping the imaginary part - the float build measures |Re| */
+        pdto_real mag = fabsf(iq[2 * i]);
+#else
+        /* :190 calls fabs(), which <tgmath.h> dispatches to cabs() for a complex argument */
+        pdto_real mag = R_HYPOT(iq[2 * i], iq[2 * i + 1]);
+#endif
+        pdto_real err = desired - (s->gain * mag);
+        s->gain = s->gain + loop_gain * err;               /* :198 */
+    }
+}
+
+pdto_real pdto_amp_run(pdto_real *average, const pdto_real *x, unsigned long n, pdto_real alpha)
+{
+    pdto_real avg = *average;
+    for (unsigned long i = 0; i < n; i++)
+        avg = avg * (1.0 - alpha) + alpha * R_FABS(x[i]);  /* :14/:16, the 1.0 makes the first product double */
+    *average = avg;
+    return avg;
+}
+
+/* ------------------------------------------------------------------------------------------------
  * GardenerClockRecovery.c:5-114
  * ---------------------------------------------------------------------------------------------- */
 void pdto_gardner_reset(pdto_gardner *s) { memset(s, 0, sizeof *s); }

@@ -85,6 +85,9 @@ class Oracle:
         L.pdto_fir_run.argtypes = [C.c_void_p, C.c_void_p, C.c_ulong, C.c_void_p, C.c_int]
         L.pdto_agc_reset.argtypes = [C.c_void_p]
         L.pdto_agc_run.argtypes = [C.c_void_p, C.c_void_p, C.c_ulong, R, R, R, C.c_void_p]
+        L.pdto_agcc_run.argtypes = [C.c_void_p, C.c_void_p, C.c_ulong, R, R]
+        L.pdto_amp_run.restype = R
+        L.pdto_amp_run.argtypes = [C.c_void_p, C.c_void_p, C.c_ulong, R]
         L.pdto_gardner_reset.argtypes = [C.c_void_p]
         L.pdto_gardner_run.restype = C.c_ulong
         L.pdto_gardner_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_ulong, C.c_void_p, C.c_int, R, R, R,
@@ -154,6 +157,17 @@ class Oracle:
         tg = np.zeros(x.size, self.dt) if trace else None
         self.lib.pdto_agc_run(st.p, _ptr(x), x.size, initial, attack, decay, _ptr(tg))
         return x, tg
+
+    def agcc(self, st, iq, initial, loop_gain):
+        """NormalizingAGCC (AGC.c:164-200) on interleaved complex samples; `st` = new_state("agc")."""
+        iq = np.array(iq, self.dt)
+        self.lib.pdto_agcc_run(st.p, _ptr(iq), iq.size // 2, initial, loop_gain)
+        return iq
+
+    def signal_amplitude(self, avg_state, x, alpha):
+        """FindSignalAmplitude (AGC.c:6-20); `avg_state` = one-element array holding the running average (in/out)."""
+        x = np.ascontiguousarray(x, self.dt)
+        return float(self.lib.pdto_amp_run(_ptr(avg_state), _ptr(x), x.size, alpha))
 
     def squelch(self, x, lock, thresh):
         x = np.array(x, self.dt)
@@ -339,6 +353,9 @@ class RefLib:
         L.LowPassFilterInterp.argtypes = [C.c_void_p] * 4 + [C.c_ulong, C.c_void_p, C.c_int, C.c_int]
         L.LowPassFilter.argtypes = [C.c_void_p, C.c_ulong, C.c_void_p, C.c_int]
         L.NormalizingAGC.argtypes = [C.c_void_p, C.c_ulong, R, R, R]
+        L.NormalizingAGCC.argtypes = [C.c_void_p, C.c_ulong, R, R]
+        L.FindSignalAmplitude.restype = R
+        L.FindSignalAmplitude.argtypes = [C.c_void_p, C.c_ulong, R]
         L.GardenerClockRecovery.restype = C.c_ulong
         L.GardenerClockRecovery.argtypes = [C.c_void_p, C.c_void_p, C.c_ulong, C.c_void_p, C.c_int, R, R, R]
         L.MMClockRecovery.restype = C.c_ulong
@@ -396,6 +413,15 @@ class RefLib:
         x = np.array(x, self.dt)
         self.lib.NormalizingAGC(_ptr(x), x.size, initial, attack, decay)
         return x
+
+    def agcc(self, iq, initial, loop_gain):
+        iq = np.array(iq, self.dt)
+        self.lib.NormalizingAGCC(_ptr(iq), iq.size // 2, initial, loop_gain)
+        return iq
+
+    def signal_amplitude(self, x, alpha):
+        x = np.ascontiguousarray(x, self.dt)
+        return float(self.lib.FindSignalAmplitude(_ptr(x), x.size, alpha))
 
     def squelch(self, x, lock, thresh):
         x = np.array(x, self.dt)
@@ -461,9 +487,14 @@ def _quiet(fn):
         os.close(devnull)
 
 
-def run_ref_cli(app: str, wav_path: str, extra_args=()):
-    """Run oracle/_ref/demodPOES_ref or demodARGOS_ref on a WAV file; returns (stdout, output-text)."""
-    exe = os.path.join(REF_DIR, f"demod{app}_ref")
+def ref_l1_available() -> bool:
+    return os.path.exists(os.path.join(REF_DIR, "demodPOES_ref_L1"))
+
+
+def run_ref_cli(app: str, wav_path: str, extra_args=(), exe: str | None = None):
+    """Run oracle/_ref/demodPOES_ref or demodARGOS_ref (or the named binary of oracle/_ref) on a WAV file;
+    returns (stdout, output-text)."""
+    exe = os.path.join(REF_DIR, exe or f"demod{app}_ref")
     with tempfile.TemporaryDirectory() as d:
         p = subprocess.run([exe, *extra_args, os.path.abspath(wav_path)], cwd=d, capture_output=True, text=True,
                            errors="replace")
@@ -484,9 +515,10 @@ def read_wav_pcm16(path: str):
     return rate, data[: (data.size // 2) * 2]
 
 
-def ref_chain_poes(iq, fs, chunk=10000):
+def ref_chain_poes(iq, fs, chunk=10000, out_path=None):
     """The reference's POES per-chunk loop (POESTIPdemod/main.c:373-482) driven through the UNMODIFIED reference
-    library with preallocated buffers (bench.py's CPU arm).  Fresh static state per call.  Returns frames found."""
+    library with preallocated buffers (bench.py's CPU arm).  Fresh static state per call.  Returns frames found; the
+    minor-frame text the reference fprintf()s goes to `out_path` (default: /dev/null)."""
     r = RefLib("f32")
     lib = r.lib
     iq = np.ascontiguousarray(iq, np.float32)
@@ -505,7 +537,7 @@ def ref_chain_poes(iq, fs, chunk=10000):
     lpf_t = np.zeros(chunk * N, np.float32)
     sym = np.zeros(chunk * L, np.float32)
     bits = np.zeros(chunk * L, np.uint8)
-    fp = r.libc.fopen(b"/dev/null", b"w")
+    fp = r.libc.fopen((out_path or "/dev/null").encode(), b"w")
     FsL = np.float32(Fs * L)
     a_atk, a_dcy = 79.5775 * (TWO_PI / FsL), 159.1549 * (TWO_PI / FsL)
     frames = 0

@@ -53,7 +53,8 @@ class Stats(C.Structure):
     _fields_ = [("n_samples", C.c_uint64), ("n_symbols", C.c_uint64), ("n_bits", C.c_uint64), ("n_frames", C.c_uint32),
                 ("locked", C.c_int32), ("lock_sample", C.c_uint64), ("lock_freq_hz", C.c_double),
                 ("norm_factor", C.c_double), ("avg_phase", C.c_double), ("final_phase", C.c_double),
-                ("final_freq", C.c_double), ("final_gain", C.c_double), ("final_next", C.c_double)]
+                ("final_freq", C.c_double), ("final_gain", C.c_double), ("final_next", C.c_double),
+                ("prelocked", C.c_int32), ("prelock_snr", C.c_float)]
 
 
 class Traces(C.Structure):
@@ -71,7 +72,7 @@ assert QUALITY_DTYPE.itemsize == 8
 STATS_DTYPE = np.dtype([("n_samples", "<u8"), ("n_symbols", "<u8"), ("n_bits", "<u8"), ("n_frames", "<u4"),
                         ("locked", "<i4"), ("lock_sample", "<u8"), ("lock_freq_hz", "<f8"), ("norm_factor", "<f8"),
                         ("avg_phase", "<f8"), ("final_phase", "<f8"), ("final_freq", "<f8"), ("final_gain", "<f8"),
-                        ("final_next", "<f8")])
+                        ("final_next", "<f8"), ("prelocked", "<i4"), ("prelock_snr", "<f4")])
 assert STATS_DTYPE.itemsize == C.sizeof(Stats)
 
 
@@ -119,6 +120,7 @@ def load(prec: str = "f32"):
     L.pdt_format_frames.argtypes = [vp, vp, u32, C.c_char_p, C.c_size_t]
     L.pdt_launch_count.restype = u64
     L.pdt_set_profiling.argtypes = [vp, C.c_int]
+    L.pdt_set_groups.argtypes = [vp, C.c_int]
     L.pdt_kernel_times.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]
     L.pdt_timeline.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_int), C.POINTER(C.c_float), C.c_int]
     L.pdt_engine.argtypes = [vp]
@@ -166,7 +168,7 @@ EXPORTED_SYMBOLS = [
     "pdt_fetch",
     "pdt_result_tables", "pdt_format_frames", "pdt_launch_count", "pdt_synth_poes_device", "pdt_engine",
     "pdt_demod_segments_device", "pdt_stream_plan_make", "pdt_stream_segment_length", "pdt_stream_stitch", "pdt_stream_frame_checks", "pdt_synth_poes_stream_device",
-    "pdt_frame_checks", "pdt_tiled_counters", "pdt_set_profiling", "pdt_kernel_times", "pdt_timeline", "pdt_debug_acq_prof",
+    "pdt_frame_checks", "pdt_tiled_counters", "pdt_set_profiling", "pdt_set_groups", "pdt_kernel_times", "pdt_timeline", "pdt_debug_acq_prof",
     # include/pdt_legacy.h
     "FindSignalAmplitude", "Squelch", "StaticGain", "NormalizingAGC", "NormalizingAGCC", "CarrierTrackPLL", "arctan2",
     "Q_rsqrt", "LowPassFilter", "LowPassFilterInterp", "MakeLPFIR", "GardenerClockRecovery", "MMClockRecovery", "sign",
@@ -257,6 +259,9 @@ class Demod:
         out = (C.c_uint32 * 4)()
         _check(self.L, self.L.pdt_tiled_counters(self.ctx, C.byref(out), stream))
         return tuple(int(v) for v in out)
+
+    def set_groups(self, max_groups: int):
+        _check(self.L, self.L.pdt_set_groups(self.ctx, int(max_groups)))
 
     def set_profiling(self, on: bool = True):
         _check(self.L, self.L.pdt_set_profiling(self.ctx, int(on)))
@@ -360,6 +365,17 @@ class Legacy:
         x = np.array(x, self.dt)
         self.L.NormalizingAGC(_p(x), x.size, initial, attack, decay)
         return x
+
+    def NormalizingAGCC(self, iq, initial, loop_gain):
+        """AGC.c:164-200 on interleaved complex samples (returned copy is the in-place result)."""
+        iq = np.array(iq, self.dt)
+        self.L.NormalizingAGCC(_p(iq), iq.size // 2, initial, loop_gain)
+        return iq
+
+    def FindSignalAmplitude(self, x, alpha):
+        """AGC.c:6-20: running average of |x| carried across calls."""
+        x = np.ascontiguousarray(x, self.dt)
+        return float(self.L.FindSignalAmplitude(_p(x), x.size, alpha))
 
     def Squelch(self, x, lock, thresh):
         x = np.array(x, self.dt)

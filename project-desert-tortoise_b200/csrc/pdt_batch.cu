@@ -137,6 +137,7 @@ struct pdt_ctx {
     size_t      stage_bytes = 0;
     int         device = 0, sm_count = 0;
     int         engine = PDT_ENGINE_EXACT;
+    int         max_groups = 0;          // pdt_set_groups: 0 = default (PDT_MAX_GROUPS or 3)
     static constexpr int MAX_GROUPS = 5;      // upper bound; the default in use is 3 (group_plan): with 4 batches in flight, 4·(3 + slow) + callers stay within the 32 hardware queues
     cudaStream_t h2d_stream = nullptr;       // chunked staging of pdt_demod_host
     cudaEvent_t  ev_h2d[MAX_GROUPS] = {}, ev_done = nullptr;
@@ -156,13 +157,14 @@ struct pdt_ctx {
 };
 
 // how a batch is cut into capture groups (shared by the kernel launches and by the chunked host->device staging)
-static int group_plan(uint32_t n_captures, uint32_t &per)
+static int group_plan(const pdt_ctx *c, uint32_t n_captures, uint32_t &per)
 {
-    static int max_groups = 0;                        // PDT_MAX_GROUPS: experiment knob (default: pdt_ctx::MAX_GROUPS)
-    if (max_groups == 0) {
+    static int env_groups = 0;                        // PDT_MAX_GROUPS: experiment knob (default 3)
+    if (env_groups == 0) {
         const char *e = getenv("PDT_MAX_GROUPS");
-        max_groups = e ? std::max(1, std::min(atoi(e), (int)pdt_ctx::MAX_GROUPS)) : 3;
+        env_groups = e ? std::max(1, std::min(atoi(e), (int)pdt_ctx::MAX_GROUPS)) : 3;
     }
+    const int max_groups = c->max_groups > 0 ? std::min(c->max_groups, (int)pdt_ctx::MAX_GROUPS) : env_groups;
     const int groups = (int)std::min<uint32_t>((uint32_t)max_groups, (n_captures + 63) / 64);
     per = groups > 0 ? (n_captures + groups - 1) / groups : n_captures;
     return groups;
@@ -283,16 +285,18 @@ struct GroupLaunch {
         dim3 g(std::min<unsigned>(blocks(n_max, 1024), 4096), cnt);
         k_sp<<<g, 256, 0, s>>>(t);
         mark(s, "k_sp");
-        const uint32_t serial = std::min(cnt, t.prelock_from);        // captures that run the reference's acquisition
-        if (serial) k_acquire<<<serial, ACQ_THREADS, 0, s>>>(t, 0);
-        mark(s, "k_acquire");
+        // captures >= prelock_from start in track mode from a carrier estimate (k_prelock); one whose estimate is rejected falls
+        // back to the reference's acquisition sweep, so k_acquire covers every capture and skips the pre-locked ones
+        const uint32_t serial = std::min(cnt, t.prelock_from);
         if (serial < cnt) { k_prelock<<<blocks(cnt - serial, EST_WARPS), EST_WARPS * 32, 0, s>>>(t); mark(s, "k_prelock"); count_launch(1); }
-        count_launch(serial ? 3 : 2);
+        k_acquire<<<cnt, ACQ_THREADS, 0, s>>>(t, 0);
+        mark(s, "k_acquire");
+        count_launch(3);
     }
     void acquire_rest(cudaStream_t s)
     {
         using namespace tiled;
-        k_acquire<<<std::max(1u, std::min(cnt, t.prelock_from)), ACQ_THREADS_SLOW, 0, s>>>(t, 1);
+        k_acquire<<<std::max(1u, cnt), ACQ_THREADS_SLOW, 0, s>>>(t, 1);
         mark(s, "k_acquire");
         count_launch(1);
     }
@@ -397,7 +401,7 @@ static int tiled_run(pdt_ctx *c, const void *d_iq, int pcm16, uint32_t n_capture
     PDT_CUDA(cudaMemsetAsync(t.task_counts, 0, 2 * (pdt_ctx::MAX_GROUPS + 1) * 2 * sizeof(uint32_t), s));
     c->n_marks = 0;
     uint32_t per = 0;
-    const int groups = group_plan(n_captures, per);
+    const int groups = group_plan(c, n_captures, per);
     if (c->profiling == 1 || traces || groups < 2) {
         if (ready) for (int gi = 0; gi < groups; gi++) PDT_CUDA(cudaStreamWaitEvent(s, ready[gi], 0));
         GroupLaunch g = make_group(c, t, 0, n_captures, n_max, c->profiling != 0);
@@ -702,7 +706,7 @@ static int demod_device_impl(pdt_ctx *c, const void *d_iq, int pcm16, uint32_t n
         if (!needs_exact) return tiled_run(c, d_iq, pcm16, n_captures, stride_samples, n_samples, traces, s, ready);
     }
 #endif
-    if (ready) { uint32_t per = 0; const int groups = group_plan(n_captures, per); for (int gi = 0; gi < groups; gi++) PDT_CUDA(cudaStreamWaitEvent(s, ready[gi], 0)); }
+    if (ready) { uint32_t per = 0; const int groups = group_plan(c, n_captures, per); for (int gi = 0; gi < groups; gi++) PDT_CUDA(cudaStreamWaitEvent(s, ready[gi], 0)); }
     ChainArgs a;
     a.cc = c->cc; a.taps = c->d_taps; a.iq = d_iq; a.pcm16 = pcm16; a.stride = stride_samples;
     a.n_samples = n_samples ? c->d_nsamp : nullptr; a.n_uniform = stride_samples; a.n_captures = n_captures;
@@ -738,6 +742,13 @@ int pdt_tiled_counters(pdt_ctx *c, uint32_t out[4], void *stream)
         out[3] = c->ta.pll.max_tiles;
     }
 #endif
+    return PDT_OK;
+}
+
+int pdt_set_groups(pdt_ctx *c, int max_groups)
+{
+    if (!c || max_groups < 0) return fail(PDT_EINVAL, "bad arguments");
+    c->max_groups = max_groups;
     return PDT_OK;
 }
 
@@ -843,7 +854,7 @@ int pdt_demod_host_async(pdt_ctx *c, const void *h_iq, int pcm16, uint32_t n_cap
     // The samples go up one capture group at a time on a copy stream; every group starts its kernels as soon as its own
     // samples have landed, so all but the first group's transfer is hidden behind the kernels of the groups before it.
     uint32_t per = 0;
-    const int groups = group_plan(n_captures, per);
+    const int groups = group_plan(c, n_captures, per);
     if (!c->h2d_stream) PDT_CUDA(cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
     if (!c->ev_done) PDT_CUDA(cudaEventCreateWithFlags(&c->ev_done, cudaEventDisableTiming));
     else PDT_CUDA(cudaStreamWaitEvent(c->h2d_stream, c->ev_done, 0));      // the previous batch has finished reading the staging buffer
@@ -942,6 +953,11 @@ int pdt_stream_plan_make(pdt_stream_plan *plan, const pdt_params *p, uint64_t to
     plan->lead = lead ? lead : (uint64_t)std::ceil(0.3 * p->sample_rate);
     plan->tail = tail ? tail : (uint64_t)std::ceil(0.13 * p->sample_rate) + 4096;
     plan->interp = (uint32_t)std::max(p->interp, 1);
+    {   // two symbols, in interpolated samples (GardenerClockRecovery.c:20: step = Fs·L / baud)
+        const double sym = (double)plan->interp * p->sample_rate / (p->baud > 0 ? p->baud : 16640.3);
+        plan->seam_tol = (uint32_t)std::ceil(2.0 * sym);
+        plan->pad = 0;
+    }
     // the last segment owns everything from its window start to the end of the stream
     const uint64_t k = total_samples > plan->lead ? (total_samples - plan->lead + segment - 1) / segment : 1;
     if (k > 0xFFFFFFFFull) return fail(PDT_EINVAL, "too many segments");
@@ -960,23 +976,31 @@ long pdt_stream_stitch(const pdt_stream_plan *plan, uint32_t first, uint32_t n, 
                        const pdt_frame *frames, uint32_t max_frames, pdt_frame *out, uint32_t out_cap)
 {
     if (!plan || !stats || !frames || !out || (uint64_t)first + n > plan->n_segments) return fail(PDT_EINVAL, "bad arguments");
-    const uint64_t L = plan->interp;
+    const uint64_t L = plan->interp, tol = plan->seam_tol;
     uint32_t k = 0;
+    bool have_prev = false; uint64_t prev_g = 0;
     for (uint32_t i = 0; i < n; i++) {
         const uint32_t s = first + i;
         const uint64_t start = (uint64_t)s * plan->segment;
         const bool last = s + 1 == plan->n_segments;
-        const uint64_t lo = s == 0 ? 0 : (start + plan->lead) * L;
-        const uint64_t hi = last ? ~0ull : (start + plan->segment + plan->lead) * L;
+        // ownership window, widened by the seam tolerance on both sides: neighbouring segments see the same sync word up to
+        // a symbol apart, so a frame near an edge is claimed by both and de-duplicated by position below (never by neither)
+        // (The outer edges of the range being stitched stay exact, so that ranges stitched separately — one per rank — still
+        // concatenate to a partition of the stream; only a stitch over ALL segments is jitter-proof at every seam.)
+        const uint64_t lo_exact = s == 0 ? 0 : (start + plan->lead) * L;
+        const uint64_t lo = (i == 0) ? lo_exact : (lo_exact > tol ? lo_exact - tol : 0);
+        const uint64_t hi = last ? ~0ull : (start + plan->segment + plan->lead) * L + (i + 1 == n ? 0 : tol);
         const uint32_t nf = std::min(stats[i].n_frames, max_frames);
         for (uint32_t f = 0; f < nf; f++) {
             const pdt_frame &fr = frames[(size_t)i * max_frames + f];
             const uint64_t g = start * L + fr.sample_index;
             if (g < lo || g >= hi) continue;
             if (!fr.complete && !last) continue;            // cannot happen with tail > one frame; never emit a seam fragment
+            if (have_prev && g <= prev_g + 2 * tol) continue;               // the frame just emitted, seen again by this segment
             if (k >= out_cap) return fail(PDT_EINVAL, "stitched frame table too small");
             out[k] = fr;
             out[k].sample_index = g;
+            prev_g = g; have_prev = true;
             k++;
         }
     }

@@ -200,11 +200,15 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_chain_exact(const ChainArgs a
             __syncthreads();
             // slide the FIR history: keep the last K-1 inputs
             {
-                real_t keep = 0;
-                const bool mine = tid < cc.K - 1;
-                if (mine) keep = Rext[m + tid];
+                // K - 1 <= 1023 (build_chain_const) may exceed the CTA: every thread carries up to 4 elements through registers,
+                // all reads before all writes (source and destination overlap when the chunk is shorter than the history)
+                constexpr int SLIDE = (1024 + CHAIN_THREADS - 1) / CHAIN_THREADS;
+                real_t keep[SLIDE];
+#pragma unroll
+                for (int q = 0; q < SLIDE; q++) { const int i = (int)tid + q * CHAIN_THREADS; keep[q] = (i < cc.K - 1) ? Rext[m + i] : (real_t)0; }
                 __syncthreads();
-                if (mine) Rext[tid] = keep;
+#pragma unroll
+                for (int q = 0; q < SLIDE; q++) { const int i = (int)tid + q * CHAIN_THREADS; if (i < cc.K - 1) Rext[i] = keep[q]; }
             }
 
             // ---- AGC (+ squelch) then Gardner -> Manchester -> ByteSync on lane 0 ---------------------
@@ -241,6 +245,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_chain_exact(const ChainArgs a
             s.locked = (st.pll.stage == 2); s.lock_sample = st.pll.lock_sample; s.lock_freq_hz = st.pll.lock_freq_hz;
             s.norm_factor = st.norm; s.avg_phase = st.avg_phase;
             s.final_phase = st.pll.phase; s.final_freq = st.pll.freq; s.final_gain = st.agc.gain; s.final_next = st.gar.next;
+            s.prelocked = 0; s.prelock_snr = 0.0f;
             args.stats[cap] = s;
         }
     }

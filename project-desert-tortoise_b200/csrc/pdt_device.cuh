@@ -2,8 +2,8 @@
 //
 // Every function here reproduces the floating-point operation order of the reference stage it cites
 // (file:line relative to the reference repo), so that with -fmad=false the float build is bit-identical
-// to the reference compiled with -O2 -ffp-contract=off on x86-64.  The fast block-parallel
-// reformulations live in pdt_parallel.cuh and are validated against these.
+// to the reference compiled with -O2 -ffp-contract=off on x86-64.  The time-parallel reformulations of
+// the recurrences live in pdt_tiled.cuh / pdt_tiled_kernels.cuh and are validated against these.
 #pragma once
 
 #include <cstdint>

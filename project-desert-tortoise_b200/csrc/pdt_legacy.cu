@@ -161,7 +161,14 @@ __global__ void k_leg_agcc(LegacyState *s, real_t *iq, unsigned long long n, rea
     const real_t desired = 5;
     for (unsigned long long i = 0; i < n; i++) {
         iq[2 * i] *= gain; iq[2 * i + 1] *= gain;                     // complex *= real
-        real_t err = desired - (gain * hypot_exact(iq[2 * i], iq[2 * i + 1]));
+#if PDT_USE_FLOATS
+        // AGC.c:188 calls fabsf() on a float complex: not a <tgmath.h> macro, the argument converts to float by dropping the
+        // imaginary part — the float build measures |Re|
+        const real_t mag = fabsf(iq[2 * i]);
+#else
+        const real_t mag = hypot_exact(iq[2 * i], iq[2 * i + 1]);     // AGC.c:190: <tgmath.h> fabs() of a complex = cabs()
+#endif
+        real_t err = desired - (gain * mag);
         gain = gain + loop_gain * err;
     }
     s->agcc_init = 1; s->agcc_gain = gain;

@@ -89,8 +89,11 @@ struct AcqResult {
     float avg_phase, locksig;   // EMA states after sample track_begin-1
     float norm;                 // StaticGain (main.c:384-389) or the override
     float sweep;
-    float agc_gain_est, pad2;   // 1 / mean|FIR output| (k_agc_plan): where the AGC gain will settle
+    float agc_gain_est;         // 1 / mean|FIR output| (k_agc_plan): where the AGC gain will settle
+    float prelock_snr;          // peak / mean of the carrier estimate's spectrum (k_prelock)
     double lock_freq_hz;
+    int   prelocked, pad3;      // pdt_capture_stats.prelocked: 0 reference acquisition, 1 started in track mode from the estimate,
+                                // 2 estimate rejected -> reference acquisition from zero
 };
 
 struct LoopState2 { float a, b; };   // (phase, freq) for the PLL, (gain, init) for the AGC

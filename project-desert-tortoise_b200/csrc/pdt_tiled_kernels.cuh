@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(128) k_norm(const TiledArgs a)
     const int lane = threadIdx.x & 31;
     if (cap >= a.n_captures) return;
     AcqResult *r = &a.acq[cap];
+    if (lane == 0) { r->prelocked = 0; r->prelock_snr = 0.0f; }
     if (a.cc.norm_override != 0) { if (lane == 0) r->norm = a.cc.norm_override; return; }
     const u64 n = cap_len(a, cap), first = (u64)cap * a.stride;
     const u64 m = n < a.cc.chunk ? n : a.cc.chunk;
@@ -325,7 +326,7 @@ __global__ void __launch_bounds__(ACQ_THREADS) k_acquire(const TiledArgs a, cons
     AcqResult *res = &a.acq[cap];
     const u64 wfirst = (u64)cap * a.ws_stride;
     float *ph_out = a.ph + wfirst;
-    if (cap >= a.prelock_from) return;                       // k_prelock's captures
+    if (cap >= a.prelock_from && res->prelocked == 1) return;       // started in track mode by k_prelock (launched before this kernel)
 
     PllState ps;
     pll_reset(ps);
@@ -524,7 +525,8 @@ constexpr int EST_MAX_D = 24;          // staged (coalesced) decimation up to th
 
 // carrier frequency (rad/sample) and phase at sample `warm` of a capture, from the EST_FFT·D samples in front of it.
 // One warp; z / stg are its shared-memory scratch.  The result is valid on lane 0.
-__device__ __forceinline__ LoopState2 est_carrier(const TiledArgs &a, const u64 first, const u64 warm, float2 *z, float2 *stg, const int lane)
+__device__ __forceinline__ LoopState2 est_carrier(const TiledArgs &a, const u64 first, const u64 warm, float2 *z, float2 *stg, const int lane,
+                                                  float *snr_out = nullptr)
 {
     const int D = a.est_decim;
     const long long w0 = (long long)warm - (long long)EST_FFT * D;
@@ -572,16 +574,22 @@ __device__ __forceinline__ LoopState2 est_carrier(const TiledArgs &a, const u64 
     const float fs_d = a.cc.pll.Fs / (float)D, bin_hz = fs_d / (float)EST_FFT;
     int kmax = (int)(a.est_fmax / bin_hz) + 1;
     if (kmax > EST_FFT / 2 - 2) kmax = EST_FFT / 2 - 2;
-    float best = -1.f; int best_k = 0;
+    float best = -1.f, total = 0.f; int best_k = 0;
     for (int kk = -kmax + lane; kk <= kmax; kk += 32) {
         const float2 v = z[kk & (EST_FFT - 1)];
         const float m2 = v.x * v.x + v.y * v.y;
+        total += m2;
         if (m2 > best) { best = m2; best_k = kk; }
     }
     for (int o = 16; o; o >>= 1) {
         const float ob = __shfl_xor_sync(0xffffffffu, best, o);
         const int ok = __shfl_xor_sync(0xffffffffu, best_k, o);
+        total += __shfl_xor_sync(0xffffffffu, total, o);
         if (ob > best || (ob == best && ok < best_k)) { best = ob; best_k = ok; }
+    }
+    if (snr_out) {       // peak against the mean of the OTHER searched bins (noise only: max of n exponentials ~ ln n ~ 7)
+        const float rest = total - best;
+        *snr_out = (rest > 0.f) ? best * (float)(2 * kmax) / rest : ((best > 0.f) ? 1e30f : 0.f);
     }
     const float delta = est_peak_offset(z[(best_k - 1) & (EST_FFT - 1)], z[best_k & (EST_FFT - 1)], z[(best_k + 1) & (EST_FFT - 1)]);
     const float f_hz = ((float)best_k + delta) * bin_hz;
@@ -642,8 +650,15 @@ __global__ void __launch_bounds__(EST_WARPS * 32) k_prelock(const TiledArgs a)
     AcqResult *res = &a.acq[cap];
     u64 pre = prelock_span(a.est_decim);
     if (pre > n) pre = n;                                   // (the host refuses segments this short; keep the kernel safe)
-    LoopState2 g = est_carrier(a, first, pre, zs[wib], stage[wib], lane);
+    float snr = 0.f;
+    LoopState2 g = est_carrier(a, first, pre, zs[wib], stage[wib], lane, &snr);
     g.a = __shfl_sync(0xffffffffu, g.a, 0); g.b = __shfl_sync(0xffffffffu, g.b, 0);
+    if (!(snr >= PDT_PRELOCK_MIN_SNR)) {
+        // no carrier stands out of the searched band: do not pretend a lock — the segment runs the reference's acquisition
+        // sweep from zero like a recording that starts here (k_acquire picks it up), and says so in its stats
+        if (lane == 0) { res->prelocked = 2; res->prelock_snr = snr; }
+        return;
+    }
     PllState ps; pll_reset(ps); pll_begin(ps, a.cc.pll);
     if (g.b > ps.max_freq) g.b = ps.max_freq; else if (g.b < ps.min_freq) g.b = ps.min_freq;
     float *ph = a.ph + (u64)cap * a.ws_stride;
@@ -657,6 +672,7 @@ __global__ void __launch_bounds__(EST_WARPS * 32) k_prelock(const TiledArgs a)
         res->lock_sample = pre ? pre - 1 : 0; res->track_begin = pre;
         res->phase = g.a; res->freq = g.b; res->sweep = 0.0f;
         res->avg_phase = 0.0f; res->locksig = 1.0f;
+        res->prelocked = 1; res->prelock_snr = snr;
         res->lock_freq_hz = g.b * a.cc.pll.Fs / (2.0 * PDT_PI);
         const float bw = a.cc.pll.bw_track, damp = ps.damp;                                         // CarrierTrackingPLL.c:272-273
         res->alpha = (4.0 * damp * bw) / (1.0 + 2.0 * damp * bw + bw * bw);
@@ -1415,6 +1431,7 @@ __global__ void __launch_bounds__(BITS_WARPS * 32) k_bits(const TiledArgs a)
             }
         }
         s.final_next = gr.final_next;
+        s.prelocked = acq.prelocked; s.prelock_snr = acq.prelock_snr;
         a.stats[cap] = s;
     }
 }

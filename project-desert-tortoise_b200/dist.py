@@ -47,3 +47,47 @@ def frames_in_capture_order(stats: np.ndarray, frames: np.ndarray):
         for k in range(nf):
             out.append((c, frames[c, k]))
     return out
+
+
+def bind_to_gpu_numa(local_rank: int) -> dict:
+    """Pin this process (and therefore the pinned host buffers it allocates next: first-touch) to the CPUs of the NUMA node
+    its GPU hangs off, when the platform exposes more than one node to this process.  Returns what was found/done —
+    bench.py reports it.  Pure sysfs + sched_setaffinity; a container that shows a single node is left alone."""
+    import glob
+    import os
+    info = {"gpu_numa_node": None, "nodes_visible": 0, "bound": False}
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+    except Exception:
+        bdf = None
+    try:
+        if bdf is None:
+            import subprocess
+            out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local_rank)],
+                                 capture_output=True, text=True, timeout=20).stdout.strip()
+            bdf = out.splitlines()[0].strip() if out else None
+        nodes = sorted(glob.glob("/sys/devices/system/node/node[0-9]*"))
+        info["nodes_visible"] = len(nodes)
+        if not bdf or len(nodes) < 2:
+            return info
+        bdf = bdf.lower()
+        if len(bdf.split(":")[0]) == 8:            # nvidia-smi prints an 8-digit PCI domain, sysfs uses 4
+            bdf = bdf[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        info["gpu_numa_node"] = node
+        if node < 0:
+            return info
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            info["bound"] = True
+            info["cpus"] = len(allowed)
+    except Exception as e:       # diagnostics only: never fail the run over topology files
+        info["error"] = f"{type(e).__name__}: {e}"
+    return info

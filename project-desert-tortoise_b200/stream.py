@@ -22,7 +22,7 @@ _pkg = importlib.import_module(__name__.rsplit(".", 1)[0])
 
 class StreamPlan(C.Structure):
     _fields_ = [("total_samples", C.c_uint64), ("segment", C.c_uint64), ("lead", C.c_uint64), ("tail", C.c_uint64),
-                ("n_segments", C.c_uint32), ("interp", C.c_uint32)]
+                ("n_segments", C.c_uint32), ("interp", C.c_uint32), ("seam_tol", C.c_uint32), ("pad", C.c_uint32)]
 
 
 def _bind(L):

@@ -71,8 +71,9 @@ def parse_frames_text(text: str):
 def make_poes_capture(n_samples: int, fs: float, seed: int, esn0_db: float = 12.0, doppler_hz: float = 1000.0,
                       drift_hz_s: float = 20.0, amplitude: float = 0.25, theta0: float = 0.7,
                       lead_in_s: float = 0.0, spacecraft: int = 8, counter0: int | None = None,
-                      chip_rate: float = POES_CHIP_RATE):
-    """Returns (pcm int16 [2n] interleaved I,Q ; info dict)."""
+                      chip_rate: float = POES_CHIP_RATE, frames_hook=None):
+    """Returns (pcm int16 [2n] interleaved I,Q ; info dict).  `frames_hook(frames)` may edit the [n,104] frame table in place
+    before it is modulated (crafted payloads)."""
     rng = np.random.default_rng(seed)
     sps = fs / chip_rate
     n_chips = int(np.ceil(n_samples / sps)) + 4
@@ -80,6 +81,8 @@ def make_poes_capture(n_samples: int, fs: float, seed: int, esn0_db: float = 12.
     if counter0 is None:
         counter0 = int(rng.integers(0, 320))
     frames = tip_frames(n_frames, seed + 1000003, spacecraft, counter0)
+    if frames_hook is not None:
+        frames_hook(frames)
     bits = frames_to_bits(frames)
     # random frame phase so that captures do not all start on a frame boundary (counter stays continuous)
     start = int(rng.integers(0, 2 * 8 * FRAME_BYTES))

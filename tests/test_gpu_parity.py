@@ -420,6 +420,70 @@ def test_config4_stream_as_segments_matches_serial_capture(torch_cuda, fs, total
     assert np.array_equal(np.concatenate([part1, part2]), out)
 
 
+def test_config4_stream_2msps_locked_matches_serial_and_oracle(torch_cuda, oracle32):
+    """BASELINE configs[4]'s rate where the reference chain DOES lock (the synthetic device stream of the test above is too
+    noisy for the reference's own acquisition sweep at 2 Msps): a 12 M-sample 2 Msps recording — the very one
+    tests/test_prelock_model.py runs through the CPU model of the stream mode — demodulated (a) serially, compared byte for
+    byte with oracle.chain(force_min_L1), and (b) as six pre-locked segments stitched by ownership windows: the same list of
+    minor frames, every byte, positions within one symbol."""
+    torch = torch_cuda
+    stream_mod = importlib.import_module("project-desert-tortoise_b200.stream")
+    fs, total, segment = 2_000_000, 12_000_000, 2_000_000
+    pcm, _ = make_poes_capture(total, fs, 9, esn0_db=24.0, doppler_hz=1200.0, drift_hz_s=-150.0, amplitude=0.3)
+    iq = oracle32.pcm16_to_complex(pcm)
+    want = oracle32.chain(iq, fs, force_min_L1=True)
+    assert want["locked"] and want["total_frames"] >= 55
+    p = pdt.default_params("f32", pdt.PDT_MODE_POES, fs)
+    p.force_min_interp1 = 1
+    cs = torch.cuda.current_stream().cuda_stream
+    d_iq = torch.from_numpy(iq).cuda()
+    d = pdt.Demod("f32", p, 1, total, int(total / fs * 10) + 8)
+    d.demod_device(d_iq.data_ptr(), 1, total, stream=cs)
+    st, fr = d.fetch(1, cs)
+    assert (st[0]["n_symbols"], st[0]["n_bits"], st[0]["n_frames"]) == (want["total_symbols"], want["total_bits"], want["total_frames"])
+    assert st[0]["locked"] == 1 and st[0]["lock_sample"] == want["lock_sample"]
+    _frames_text_equal_bytes(d.format_frames(fr[0], int(st[0]["n_frames"])), want["text"])
+    serial = fr[0][: int(st[0]["n_frames"])]
+    serial_full = serial[serial["complete"] == 1]
+    plan = stream_mod.make_plan("f32", d.params, total, segment)
+    sd = stream_mod.StreamDemod("f32", p, plan, 0, plan.n_segments)
+    sd.run_device(d_iq.data_ptr(), stream=cs)
+    s_st, s_fr = sd.fetch(cs)
+    out = sd.stitch_local(s_st, s_fr)
+    out_full = out[out["complete"] == 1]
+    assert stream_mod.continuity(out)["counter_breaks"] == 0
+    assert out_full.size == serial_full.size and np.array_equal(out_full["bytes"], serial_full["bytes"])
+    assert np.abs(out_full["sample_index"].astype(np.int64) - serial_full["sample_index"].astype(np.int64)).max() <= fs / 16640.3
+
+
+def test_config4_serial_2msps_locked_bit_exact_all_stages(torch_cuda, oracle32):
+    """BASELINE configs[4]'s rate with oracle EQUALITY (not counts): 10 M samples @ 2 Msps that the serial chain does lock
+    on, through the tiled engine with the declared L = max(1, …) deviation, against oracle.chain(force_min_L1) — the mode
+    tests/test_oracle_vs_ref.py pins to the reference rebuilt with that one line patched.  PLL phase / output, FIR, AGC,
+    symbols, Gardner errors and pick indices, bits and frame bytes are all bit-exact."""
+    fs, n = 2_000_000, 10_000_000
+    pcm, _ = make_poes_capture(n, fs, 7, esn0_db=24.0, doppler_hz=900.0, amplitude=0.3)
+    iq = oracle32.pcm16_to_complex(pcm)
+    want = oracle32.chain(iq, fs, force_min_L1=True, trace=True)
+    assert want["locked"] and want["total_frames"] >= 45
+    d, st, fr, tr = _run_batch_with_traces(torch_cuda, "f32", pdt.PDT_MODE_POES, fs, iq, force_l1=True, engine="tiled")
+    assert d.params.interp == 1 and d.params.taps == 26
+    assert (st["n_symbols"], st["n_bits"], st["n_frames"]) == (want["total_symbols"], want["total_bits"], want["total_frames"])
+    assert st["locked"] == 1 and st["lock_sample"] == want["lock_sample"]
+    ns, nb = int(st["n_symbols"]), int(st["n_bits"])
+    for k_dev, k_or in (("pll_phase", "tr_phase"), ("pll_out", "tr_pll_out"), ("lpf", "tr_lpf"), ("agc", "tr_agc")):
+        assert np.array_equal(tr.host(k_dev), want[k_or]), k_dev
+    assert np.array_equal(tr.host("sym", ns), want["tr_sym"])
+    assert np.array_equal(tr.host("gardner_err", ns), want["tr_gerr"])
+    assert np.array_equal(tr.host("gardner_idx", ns).astype(np.uint64), want["tr_gidx"])
+    assert np.array_equal(tr.host("bits", nb), want["tr_bits"])
+    text = d.format_frames(fr, int(st["n_frames"]))
+    _frames_text_equal_bytes(text, want["text"])
+    full = [f for f in parse_frames_text(text) if f[2].size == 104]
+    cnt = [frame_counter(f[2]) for f in full]
+    assert len(full) >= 45 and all((b - a) % 320 == 1 for a, b in zip(cnt, cnt[1:]))
+
+
 def test_config2_argos_batch_of_bursts(torch_cuda, oracle64):
     """BASELINE configs[2] shape: 256 synthetic 401.65 MHz ARGOS bursts (128 captures x 2) as independent double-precision
     captures in one batch (exact engine): packets and counts of every capture equal to the CPU oracle."""
@@ -644,7 +708,30 @@ def test_legacy_bytesync_kat(torch_cuda, golden_dir, tmp_path, name):
     assert open(out).read() == kat["text"]
 
 
-def test_legacy_squelch_mm_agcc(torch_cuda, oracle64):
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_legacy_agcc_and_signal_amplitude(torch_cuda, prec):
+    """NormalizingAGCC (AGC.c:164-200) and FindSignalAmplitude (AGC.c:6-20) of the legacy ABI against the oracle restatement
+    (itself pinned to the unmodified reference in tests/test_oracle_vs_ref.py): state carried across calls; float build
+    bit-exact (including its |Re| quirk), double build within 1e-13 (hypot)."""
+    o = po.Oracle(prec)
+    lg = pdt.Legacy(prec)
+    lg.reset()
+    rng = np.random.default_rng(31)
+    ast = o.new_state("agc")
+    avg = np.zeros(1, o.dt)
+    for n in (1, 7, 2400, 10000, 3):
+        iq = (rng.standard_normal(2 * n) * rng.choice([0.05, 1.0, 4.0])).astype(o.dt)
+        want, got = o.agcc(ast, iq, 2.5, 1e-3), lg.NormalizingAGCC(iq, 2.5, 1e-3)
+        x = (rng.standard_normal(n) * 3.0).astype(o.dt)
+        wa, ga = o.signal_amplitude(avg, x, 0.01), lg.FindSignalAmplitude(x, 0.01)
+        if prec == "f32":
+            assert np.array_equal(want, got) and wa == ga
+        else:
+            np.testing.assert_allclose(got, want, rtol=1e-13, atol=0)
+            assert abs(ga / wa - 1) < 1e-14
+
+
+def test_legacy_squelch_mm(torch_cuda, oracle64):
     lg = pdt.Legacy("f64")
     lg.reset()
     rng = np.random.default_rng(23)

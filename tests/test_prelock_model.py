@@ -137,17 +137,34 @@ def _parse(text, t_offset):
     return out
 
 
-def test_stream_as_prelocked_segments_equals_serial_chain_cpu_model(oracle32):
-    """The stream mode of DESIGN §8 restated with the CPU oracle only: a 12 s stream cut into 2 s segments (+0.3 s lead,
-    +0.15 s tail), every segment behind the first started in TRACK mode from the FFT carrier guess, frames kept by ownership
-    windows — the stitched list must be the serial chain's list of minor frames, byte for byte."""
-    fs, total, segment = 250000, 3_000_000, 500_000
+def _time_axis(fs, n):
+    """wave.c:91-167 accumulates `time += Ts` in float once per sample; the column printed with a frame is that value.
+    Returns the accumulated axis so that a printed time can be mapped back to the sample it belongs to."""
+    return np.cumsum(np.full(n + 2, np.float32(1.0) / np.float32(fs), np.float32), dtype=np.float32)
+
+
+def _to_samples(frames, axis, first):
+    return [(first + int(np.searchsorted(axis, np.float32(t - 2e-5))), b) for t, b in frames]
+
+
+@pytest.mark.parametrize("fs,total,segment,esn0,amp,force_l1,min_frames",
+                         [(250000, 3_000_000, 500_000, 14.0, 0.2, False, 115),
+                          (2_000_000, 12_000_000, 2_000_000, 24.0, 0.3, True, 55)])
+def test_stream_as_prelocked_segments_equals_serial_chain_cpu_model(oracle32, fs, total, segment, esn0, amp, force_l1, min_frames):
+    """The stream mode of DESIGN §8 restated with the CPU oracle only: a stream cut into segments (+0.3 s lead, +0.13 s
+    tail), every segment behind the first started in TRACK mode from the FFT carrier guess, frames kept by ownership
+    windows — the stitched list must be the serial chain's list of minor frames, byte for byte.  Second case: BASELINE
+    configs[4]'s 2 Msps rate (declared L = max(1, …) deviation, pinned to the patched reference in test_oracle_vs_ref.py) on
+    a recording the serial chain locks on."""
     lead, tail = int(0.3 * fs), int(0.13 * fs) + 4096
-    pcm, _ = make_poes_capture(total, fs, 9, esn0_db=14.0, doppler_hz=1200.0, drift_hz_s=-150.0, amplitude=0.2)
+    pcm, _ = make_poes_capture(total, fs, 9, esn0_db=esn0, doppler_hz=1200.0, drift_hz_s=-150.0, amplitude=amp)
     iq = oracle32.pcm16_to_complex(pcm)
     iq_c = iq.astype(np.float64).view(np.complex128)
-    serial = _parse(oracle32.chain(iq, fs)["text"], 0.0)
-    assert len(serial) >= 115
+    axis = _time_axis(fs, total)
+    res = oracle32.chain(iq, fs, force_min_L1=force_l1)
+    assert res["locked"]
+    serial = _to_samples(_parse(res["text"], 0.0), axis, 0)
+    assert len(serial) >= min_frames
     CH = oracle32._chain_struct()
     D = max(int(fs / (2.5 * 5100.0)), 1)
     pre = 1024 * D
@@ -156,9 +173,9 @@ def test_stream_as_prelocked_segments_equals_serial_chain_cpu_model(oracle32):
     for s in range(n_seg):
         start = s * segment
         stop = min(start + lead + segment + tail, total)
-        lo = 0.0 if s == 0 else (start + lead) / fs
-        hi = np.inf if s == n_seg - 1 else (start + segment + lead) / fs
-        c = oracle32.lib.pdto_chain_new(0, float(fs), 10000, 0)
+        lo = 0 if s == 0 else start + lead
+        hi = total + 1 if s == n_seg - 1 else start + segment + lead
+        c = oracle32.lib.pdto_chain_new(0, float(fs), 10000, int(force_l1))
         try:
             first = start
             if s > 0:
@@ -177,9 +194,12 @@ def test_stream_as_prelocked_segments_equals_serial_chain_cpu_model(oracle32):
             text = C.string_at(oracle32.lib.pdto_chain_text(c, C.byref(ln)), ln.value).decode()
         finally:
             oracle32.lib.pdto_chain_free(c)
-        stitched += [(t, b) for t, b in _parse(text, first / fs) if lo <= t < hi]
+        stitched += [(g, b) for g, b in _to_samples(_parse(text, 0.0), axis, first) if lo <= g < hi]
     assert [b for _, b in stitched] == [b for _, b in serial]
-    # (the time columns themselves are not compared: the reference accumulates its time axis in float, wave.c:167, which
-    # drifts by several per cent within seconds — each segment restarts it, the serial chain does not)
-    ts = [t for t, _ in stitched]
-    assert all(0.07 < b - a < 0.13 for a, b in zip(ts, ts[1:]))                                # one frame per 0.1 s (float time axis), none twice
+    # positions: the same sync bit within one symbol (the printed time has 1e-5 s resolution; each segment restarts the
+    # reference's float time axis, which is why ownership is decided in samples, not in the drifting time column)
+    sps = max(round(150000.0 / fs), 1) * fs / 16640.3
+    tol = sps + 3e-5 * fs
+    assert all(abs(a - b) <= tol for (a, _), (b, _) in zip(stitched, serial))
+    gs = [g for g, _ in stitched]
+    assert all(0.09 * fs < b - a < 0.11 * fs for a, b in zip(gs, gs[1:]))                      # one frame per 0.1 s, none twice

@@ -89,7 +89,9 @@ def test_stitch_keeps_every_frame_exactly_once():
     stats2[4]["n_frames"] = 0
     out2 = stream.stitch("f32", plan, 0, plan.n_segments, stats2, frames)
     c2 = stream.continuity(out2)
-    assert c2["counter_breaks"] == 1 and c2["missing_frames"] == 40
+    # (39 of segment 4's 40 frames: its first one lies 7 samples behind the edge, inside the seam tolerance, and is kept
+    # from segment 3's copy)
+    assert c2["counter_breaks"] == 1 and c2["missing_frames"] == 39
     assert int((stream.frame_checks("f32", out2)["continuous"] == 0).sum()) == 1
     # stitching ranges separately and concatenating is the same as stitching everything (what the ranks do)
     a = stream.stitch("f32", plan, 0, 4, stats[:4], frames[:4])
@@ -167,3 +169,36 @@ def test_plan_edge_cases_and_stitch_capacity():
     assert rc < 0 and b"too small" in L.pdt_last_error()
     # a range that runs past the plan is refused
     assert L.pdt_stream_stitch(C.byref(plan), 1, plan.n_segments, pdt._p(stats), pdt._p(frames), frames.shape[1], pdt._p(out), out.size) < 0
+
+
+@pytest.mark.parametrize("jit_a,jit_b", [(0, 0), (-1, 0), (0, -1), (1, 0), (0, 1), (-9, 9), (9, -9), (-1, 1), (15, -14)])
+def test_stitch_frame_exactly_on_a_seam_with_position_jitter(jit_a, jit_b):
+    """neighbouring segments see the same sync word up to a symbol apart (own chunk grid, chunk-relative float
+    Gardner state).  A frame whose sync lands exactly on an ownership edge, seen by segment s at edge + jit_a and by segment
+    s+1 at edge + jit_b, must come out exactly once whatever the signs — never twice, never lost."""
+    plan = stream.make_plan("f32", _params(), 4_000_000, 1_000_000)
+    assert plan.seam_tol == int(np.ceil(2 * 250000 / 16640.3))                  # two symbols
+    k, period = plan.n_segments, 25000
+    edge = 2 * plan.segment + plan.lead                                         # ownership edge between segments 1 and 2
+    stats = np.zeros(k, pdt.STATS_DTYPE)
+    frames = np.zeros((k, 64), pdt.FRAME_DTYPE)
+    lens = stream.segment_lengths("f32", plan, 0, k)
+    for s in range(k):
+        start, end = s * plan.segment, s * plan.segment + int(lens[s])
+        n = 0
+        for num in range(-200, 400):
+            g = edge + num * period                                             # the global frame grid passes through the edge
+            if g < start + (0 if s == 0 else 1000) or g + period > end:
+                continue
+            jit = jit_a if s == 1 else (jit_b if s == 2 else 0)
+            f = frames[s, n]
+            f["sample_index"], f["n_bytes"], f["complete"] = g + (jit if num == 0 else 0) - start, 104, 1
+            f["bytes"][6:14] = np.frombuffer(np.int64(num).tobytes(), np.uint8)
+            n += 1
+        stats[s]["n_frames"] = n
+    out = stream.stitch("f32", plan, 0, k, stats, frames)
+    nums = np.array([int(np.frombuffer(f["bytes"][6:14].tobytes(), np.int64)[0]) for f in out])
+    assert np.array_equal(nums, np.arange(nums[0], nums[0] + nums.size)), nums   # every frame once, in stream order
+    assert nums[0] < 0 < nums[-1]
+    at = int(np.nonzero(nums == 0)[0][0])
+    assert int(out[at]["sample_index"]) in (edge + jit_a, edge + jit_b)
