@@ -55,18 +55,33 @@ FS = 250_000
 # ----------------------------------------------------------------------------------------------------
 # CPU reference arm (also used for cpu_baseline)
 # ----------------------------------------------------------------------------------------------------
-def _cpu_worker_init(kind):
-    global _W
+def _cpu_worker_init(kind, mode="poes", fs=None):
+    global _W, FS
     import pyoracle as po
     devnull = os.open(os.devnull, os.O_WRONLY)      # the reference printf()s " : PLL locked at …" per capture
     os.dup2(devnull, 1)
-    _W = {"kind": kind, "po": po}
+    if fs:
+        FS = fs
+    _W = {"kind": kind, "po": po, "mode": mode}
 
 
 def _cpu_worker_run(path):
     """One capture through the reference's per-chunk loop (POESTIPdemod/main.c:373-482), fresh state per capture."""
     po = _W["po"]
     iq = np.load(path, mmap_mode="r")
+    if _W["mode"] == "argos":                      # ARGOSdemod/main.c:250-300, double precision
+        iq = np.ascontiguousarray(iq, np.float64)
+        t0 = time.perf_counter()
+        if _W["kind"] == "reference":
+            frames = po.ref_chain_argos(iq, FS, out_path=path + ".txt")
+            dt = time.perf_counter() - t0
+            text = open(path + ".txt").read()
+            os.remove(path + ".txt")
+        else:
+            r = po.Oracle("f64").chain(iq, FS, argos=True)
+            dt = time.perf_counter() - t0
+            frames, text = r["total_frames"], r["text"]
+        return dt, int(frames), text
     iq = np.ascontiguousarray(iq, np.float32)
     t0 = time.perf_counter()
     if _W["kind"] == "reference":
@@ -81,23 +96,24 @@ def _cpu_worker_run(path):
     return dt, int(frames), text
 
 
-def cpu_arm(captures, steps, warmup, cores=None):
-    """captures: list of float32 [2n] arrays.  Returns dict(value Msamples/s, ms_per_step, cores, kind, frames)."""
+def cpu_arm(captures, steps, warmup, cores=None, mode="poes"):
+    """captures: list of float32 (POES) / float64 (ARGOS) [2n] arrays.  Returns dict(value Msamples/s, ms_per_step, cores,
+    kind, frames, texts)."""
     import multiprocessing as mp
     import pyoracle as po
-    kind = "reference" if po.ref_available("f32") else "port"
+    kind = "reference" if po.ref_available("f64" if mode == "argos" else "f32") else "port"
     cores = cores or len(os.sched_getaffinity(0))
     cores = max(1, min(cores, len(captures)))
     tmp = tempfile.mkdtemp(prefix="pdtbench_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
     paths = []
     for i, c in enumerate(captures):
         p = os.path.join(tmp, f"cap{i}.npy")
-        np.save(p, np.ascontiguousarray(c, np.float32))
+        np.save(p, np.ascontiguousarray(c, np.float64 if mode == "argos" else np.float32))
         paths.append(p)
     n_samples = sum(c.size // 2 for c in captures)
     ctx = mp.get_context("spawn")
     try:
-        with ctx.Pool(cores, initializer=_cpu_worker_init, initargs=(kind,)) as pool:
+        with ctx.Pool(cores, initializer=_cpu_worker_init, initargs=(kind, mode, FS)) as pool:
             pool.map(_cpu_worker_run, paths[:cores])          # start-up + page-in, untimed
             for _ in range(max(warmup - 1, 0)):
                 pool.map(_cpu_worker_run, paths)
@@ -328,6 +344,232 @@ def stream_bench(args):
     return 0
 
 
+# ----------------------------------------------------------------------------------------------------
+# --mode argos: BASELINE configs[2] — batches of synthetic 401.65 MHz ARGOS bursts, double precision
+# ----------------------------------------------------------------------------------------------------
+ARGOS_FS, ARGOS_N = 5000, 40_000
+
+
+def argos_captures(count):
+    """`count` float64 [2n] captures: 64 distinct seeded two-burst recordings (8 s @ 5 ksps each, SNR 14…25 dB, the set
+    tests/test_gpu_parity.py::test_config2 checks against the oracle), repeated with a constant carrier-phase rotation."""
+    import pyoracle as po
+    from tests.synth_ref import make_argos_capture
+    o = po.Oracle("f64")
+    base = []
+    for c in range(min(count, 64)):
+        pcm, _ = make_argos_capture(ARGOS_N, float(ARGOS_FS), seed=40 + c, n_bursts=2, snr_db=14.0 + (c % 12))
+        base.append(o.pcm16_to_complex(pcm).view(np.complex128))
+    out = np.empty((count, ARGOS_N), np.complex128)
+    for c in range(count):
+        out[c] = base[c % len(base)] * np.exp(1j * 0.37 * (c // len(base)))
+    return out.view(np.float64).reshape(count, 2 * ARGOS_N)
+
+
+def argos_reference_arm(args):
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    cores = len(os.sched_getaffinity(0))
+    n_caps = max(cores, 64)
+    caps = list(argos_captures(n_caps))
+    r = cpu_arm(caps, args.steps, args.warmup, cores, mode="argos")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"ARGOS chain (double), {n_caps} burst captures x {ARGOS_N} IQ samples @ {ARGOS_FS} sps per step on host "
+                               f"cores (bounded sample of the GPU arm's batch shape)", "sample_rate": ARGOS_FS,
+                   "captures_per_step": n_caps, "samples_per_capture": ARGOS_N},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                         "sample": f"{n_caps} captures x {ARGOS_N} samples per step, one process per capture"},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def argos_bench(args):
+    """configs[2]: ARGOSdemod's chain (ARGOSdemod/main.c:250-300: PLL with lock stream -> 50-tap LowPassFilter ->
+    NormalizingAGC -> Squelch -> Gardner -> Manchester -> FindSyncWords) in DOUBLE precision over a batch of burst
+    captures.  One kernel per batch (k_chain_exact: one CTA per capture, recurrences in reference order); 16 B per input
+    sample algorithmic (cf64 read once)."""
+    import torch
+    import torch.distributed as dist
+    global FS
+    FS = ARGOS_FS
+    pdt = importlib.import_module("project-desert-tortoise_b200")
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    L = pdt.load("f64")
+    if L.pdt_device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device - the product has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    L.pdt_set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    C_ = args.captures if args.captures != 1024 else 4096
+    n = ARGOS_N
+    host = argos_captures(C_)
+    if rank:
+        host = np.roll(host, rank, axis=0)
+    h_pin = torch.from_numpy(host).pin_memory()
+    d_iq = h_pin.cuda()
+    params = pdt.default_params("f64", pdt.PDT_MODE_ARGOS, ARGOS_FS)
+    max_frames = 16
+    inflight = max(1, min(args.inflight if args.inflight > 0 else 3, max(args.steps, 1)))
+    ctxs = [pdt.Demod("f64", params, C_, n, max_frames) for _ in range(inflight)]
+    side = [torch.cuda.Stream() for _ in range(inflight)]
+    row_bytes = max_frames * 120
+    tables = [torch.as_tensor(_Raw(c.result_tables()[1], C_ * row_bytes), device="cuda").view(C_, row_bytes) for c in ctxs]
+    gathered = torch.empty((world * C_, row_bytes), dtype=torch.uint8, device="cuda") if world > 1 else None
+    step_no = [0]
+
+    def step():
+        k = step_no[0] % inflight
+        step_no[0] += 1
+        with torch.cuda.stream(side[k]):
+            ctxs[k].demod_device(d_iq.data_ptr(), C_, n, stream=side[k].cuda_stream)
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, tables[k])
+
+    def run(k_steps):
+        for sk in side:
+            sk.wait_stream(torch.cuda.current_stream())
+        for _ in range(k_steps):
+            step()
+        for sk in side:
+            torch.cuda.current_stream().wait_stream(sk)
+
+    run(args.warmup)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+        time.sleep(0.3)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = L.pdt_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    run(args.steps)
+    e1.record()
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    launches = L.pdt_launch_count() - launches0
+    clocks = sampler.stop(t0, t1) if sampler else None
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms_step = ms / args.steps
+    value = C_ * n * world / (ms_step * 1e-3) / 1e6
+    # the one kernel of the step, alone
+    d = ctxs[0]
+    stream = torch.cuda.current_stream().cuda_stream
+    kt = []
+    for _ in range(3):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        d.demod_device(d_iq.data_ptr(), C_, n, stream=stream)
+        b.record()
+        torch.cuda.synchronize()
+        kt.append(a.elapsed_time(b))
+    k_ms = float(np.mean(kt))
+    stats, frames = d.fetch(C_, stream)
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    alg_bytes = C_ * n * 16
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"BASELINE configs[2] shape: batch of {C_} synthetic 401.65 MHz ARGOS burst captures x {n} IQ samples @ "
+                               f"{ARGOS_FS} sps per GPU (two bursts each, SNR 14-25 dB), double-precision chain PLL(+lock stream)->"
+                               f"LowPassFilter(50)->AGC->Squelch->Gardner->Manchester->FindSyncWords, exact engine (one CTA per capture)",
+                   "engine": "exact", "captures_per_gpu": C_, "samples_per_capture": n, "sample_rate": ARGOS_FS, "input": "cf64",
+                   "chunk": d.params.chunk, "batches_in_flight": inflight,
+                   "l2": f"inputs {C_ * n * 16 / 1e9:.2f} GB per GPU" + (" (larger than the 126 MB L2)" if C_ * n * 16 > 252e6 else "")},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                     "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / peak, "traffic": None, "kernel": "k_chain_exact", "kernel_ms": k_ms,
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_bytes_per_sample": 16,
+                     "note": "the only kernel of the step, one batch alone; it is bound by the per-sample dependent chains of the "
+                             "double-precision recurrences on one lane per capture, not by memory"},
+        "check": {"packets_decoded": int(stats["n_frames"].sum()), "captures_locked": int(stats["locked"].sum()),
+                  "symbols": int(stats["n_symbols"].sum())},
+    }
+    if clocks:
+        line["clocks"] = clocks
+    if not args.no_e2e:
+        m = min(inflight, 2)
+        e_streams = [torch.cuda.Stream() for _ in range(m)]
+        h_np = h_pin.numpy()
+        d2h = [0]
+
+        def e2e_run(steps):
+            pending = [False] * m
+            for i in range(steps):
+                k = i % m
+                if pending[k]:
+                    st_h, fr_h = ctxs[k].fetch(C_, e_streams[k].cuda_stream)
+                    d2h[0] = st_h.nbytes + fr_h.nbytes
+                ctxs[k].demod_host_async(h_np, C_, stream=e_streams[k].cuda_stream)
+                pending[k] = True
+            for k in range(m):
+                if pending[k]:
+                    st_h, fr_h = ctxs[k].fetch(C_, e_streams[k].cuda_stream)
+                    d2h[0] = st_h.nbytes + fr_h.nbytes
+            return st_h
+        e2e_run(m)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e2e_steps = max(4, min(args.steps, 8))
+        tt0 = time.perf_counter()
+        st_last = e2e_run(e2e_steps)
+        torch.cuda.synchronize()
+        tt = time.perf_counter() - tt0
+        if world > 1:
+            t = torch.tensor([tt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            tt = float(t.item())
+        assert int(st_last["n_frames"].sum()) == int(stats["n_frames"].sum())
+        line["e2e"] = {"value": C_ * n * world * e2e_steps / tt / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(C_ * n * 16),
+                       "d2h_bytes_per_step": int(d2h[0]), "steps": e2e_steps, "batches_in_flight": m, "input": "cf64",
+                       "api": "pdt_demod_host_async + pdt_fetch (pinned host IQ -> chunked H2D -> kernel -> D2H stats+packets)"}
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from tests.synth_ref import parse_frames_text
+        cores = len(os.sched_getaffinity(0))
+        k = min(C_, args.cpu_captures or max(4 * cores, 64))
+        caps = [host[c] for c in range(k)]
+        r = cpu_arm(caps, 1, 1, cores, mode="argos")
+        mismatched = rows = 0
+        for c in range(k):
+            want_rows = [(w[1], bytes(w[2])) for w in parse_frames_text(r["texts"][c])]
+            nf = min(int(stats["n_frames"][c]), max_frames)
+            got_rows = [(bool(f["inverse"]), bytes(f["bytes"][: f["n_bytes"]])) for f in frames[c][:nf]]
+            rows += len(want_rows)
+            mismatched += want_rows != got_rows
+        line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                                "sample": f"first {k} captures of the GPU batch ({k} x {n} samples), one process per capture",
+                                "packets": r["frames"], "gpu_packets_same_captures": int(stats["n_frames"][:k].sum()),
+                                "packet_bytes_check": {"captures": k, "rows": rows, "captures_with_any_difference": int(mismatched),
+                                                       "equal": mismatched == 0}}
+        assert mismatched == 0, "GPU packet bytes differ from the reference's on the ARGOS bench batch"
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     global FS
     ap = argparse.ArgumentParser()
@@ -356,9 +598,13 @@ def main():
     ap.add_argument("--cpu-captures", type=int, default=0)
     ap.add_argument("--ref-captures", type=int, default=0)
     ap.add_argument("--ref-samples", type=int, default=1_000_000)
+    ap.add_argument("--mode", default="poes", choices=["poes", "argos"],
+                    help="argos: BASELINE configs[2] — batches of double-precision ARGOS burst captures (own JSON line)")
     args = ap.parse_args()
     FS = args.fs
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    if args.mode == "argos":
+        return argos_reference_arm(args) if args.impl == "reference" else argos_bench(args)
     if args.impl == "reference":
         return reference_arm(args)
     if args.stream:

@@ -647,6 +647,13 @@ void pdto_pcm16_to_complex(const int16_t *pcm, uint64_t n, pdto_real *iq)
     for (uint64_t i = 0; i < 2 * n; i++) iq[i] = pcm[i] / maxsize;
 }
 
+/* libm's sinf/cosf over an array: the reference calls them once per sample (CarrierTrackingPLL.c:106-107); tests compare the
+ * kernels' restatement of glibc's algorithm against the real thing, float by float. */
+void pdto_sincosf_array(const float *y, uint64_t n, float *s, float *c)
+{
+    for (uint64_t i = 0; i < n; i++) { s[i] = sinf(y[i]); c[i] = cosf(y[i]); }
+}
+
 size_t pdto_sizeof(const char *what)
 {
     if (!strcmp(what, "pll")) return sizeof(pdto_pll);

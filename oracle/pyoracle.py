@@ -558,3 +558,45 @@ def ref_chain_poes(iq, fs, chunk=10000, out_path=None):
         pos += m
     r.libc.fclose(fp)
     return frames
+
+
+ARGOS_SYNC = b"0001011110000"
+
+
+def ref_chain_argos(iq, fs, chunk=2400, out_path=None):
+    """The reference's ARGOS per-chunk loop (ARGOSdemod/main.c:250-300) driven through the UNMODIFIED double-precision
+    reference library with preallocated buffers (bench.py --mode argos CPU arm).  Fresh static state per call.  Returns
+    packets found; the packet text goes to `out_path` (default /dev/null; FindSyncWords also echoes to stdout)."""
+    r = RefLib("f64")
+    lib = r.lib
+    iq = np.ascontiguousarray(iq, np.float64)
+    n = iq.size // 2
+    Fs = float(fs)
+    h = r.make_lpfir(50, 700.0, Fs, 1)
+    w = 2.0 * np.pi / Fs
+    tbuf = np.zeros(chunk + 2, np.float64)
+    real_s = np.zeros(chunk, np.float64)
+    lock = np.zeros(chunk, np.float64)
+    sym = np.zeros(chunk, np.float64)
+    bits = np.zeros(chunk, np.uint8)
+    fp = r.libc.fopen((out_path or "/dev/null").encode(), b"w")
+    packets, norm, pos, t = 0, 0.0, 0, 0.0
+    Ts = 1.0 / Fs
+    P = _ptr
+    while pos < n:
+        m = min(chunk, n - pos)
+        x = iq[2 * pos: 2 * (pos + m)]
+        tbuf[:m] = t + Ts * np.arange(1, m + 1)          # wave.c:167 accumulates time += Ts per sample (double build)
+        t = float(tbuf[m - 1])
+        if pos == 0:
+            norm = lib.StaticGain(P(x), m, 1.0)
+        lib.CarrierTrackPLL(P(x), P(real_s), P(lock), m, Fs, 550.0, 0.1, 3.1831 * w, 16.0 * w, 16.0 * w)
+        lib.LowPassFilter(P(real_s), m, P(h), 50)
+        lib.NormalizingAGC(P(real_s), m, norm, 79.5775 * w, 159.1549 * w)
+        lib.Squelch(P(real_s), P(lock), m, 0.15)
+        ns = lib.GardenerClockRecovery(P(real_s), P(tbuf), m, P(sym), int(Fs), 800.0, 0.1, 3.0)
+        nb = lib.ManchesterDecode(P(sym), P(tbuf), ns, P(bits), 0.5)
+        packets += r._bs(P(bits), P(tbuf), nb, ARGOS_SYNC, 13, fp)
+        pos += m
+    r.libc.fclose(fp)
+    return packets

@@ -145,6 +145,8 @@ struct pdt_ctx {
     uint32_t prelock_from = 0xFFFFFFFFu; // this call: captures >= this index start pre-locked (pdt_demod_segments_device)
     tiled::TiledArgs ta;                 // workspace pointers + plans of the tiled engine (engine == PDT_ENGINE_TILED)
     tiled::TapsRev   taps_rev;
+    tiled::TapsPair  taps_pair;          // L = 1: duplicated tap pairs of the packed front kernel (k_front1)
+    int         front_packed = 0;        // k_front1 in use (L = 1; PDT_FRONT_SCALAR=1 keeps the scalar k_front<1> for A/B runs)
     size_t      front_smem = 0;
     static constexpr int MAX_MARKS = 512;
     int         mark_group[MAX_MARKS] = {};
@@ -245,6 +247,12 @@ static int tiled_setup(pdt_ctx *c)
     }
 #undef TA
     for (int u = 0; u < cc.N; u++) c->taps_rev.hr[u] = c->taps_h[cc.N - 1 - u];
+    if (cc.L == 1) {
+        for (int u = 0; u < FIR_K; u++) c->taps_pair.hh[u] = make_float2(c->taps_rev.hr[u], c->taps_rev.hr[u]);
+        c->taps_pair.one = 1.0f; c->taps_pair.pad = 0.0f;
+        const char *e = getenv("PDT_FRONT_SCALAR");
+        c->front_packed = !(e && atoi(e) != 0);
+    }
     c->front_smem = front_smem_bytes(cc.L);
     if ((e = cudaFuncSetAttribute(front_kernel(cc.L), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->front_smem)) != cudaSuccess)
         return fail(PDT_ECUDA, "cudaFuncSetAttribute(k_front): %s", cudaGetErrorString(e));
@@ -327,7 +335,11 @@ struct GroupLaunch {
         mark(s, "k_pll_fix_par");
         k_pll_fix<<<blocks(cnt, 128), 128, 0, s>>>(q);
         mark(s, "k_pll_fix");
-        {
+        if (c->front_packed) {
+            dim3 g(blocks(n_max, F1_SPAN), cnt);
+            if (q.pcm16) k_front1<true><<<g, F1_THREADS, 0, s>>>(q, c->taps_pair);
+            else         k_front1<false><<<g, F1_THREADS, 0, s>>>(q, c->taps_pair);
+        } else {
             dim3 g(blocks(n_max, front_span(L)), cnt);
             front_kernel(L)<<<g, front_threads(L), c->front_smem, s>>>(q, c->taps_rev);
         }

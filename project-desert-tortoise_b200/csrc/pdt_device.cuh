@@ -109,25 +109,40 @@ PDT_DEV double sc_cos_poly(double x2)
 
 PDT_DEV uint32_t abstop12(float x) { return (pdt_f2u(x) >> 20) & 0x7ffu; }
 
-PDT_DEV void sincos_exact(float y, float &s, float &c)
+// the branch-free body, valid for |y| < 120 and y != -0 (sincos_in_core_range): what the hot loops call directly, so that
+// several evaluations interleave in one straight-line block (a per-sample range branch fences the scheduler off).
+//   * glibc's three ranges collapse into its general path: for |y| < π/4 the quadrant is n = 0 and the reduction x - 0·(π/2)
+//     is exact, which is its small-argument path; and for |y| < 2^-12, where glibc returns (y, 1) without evaluating
+//     anything, the polynomials round to exactly that: x·(1 - x²/6 …) is within 2^-26.5 of x, below half a float ulp, and
+//     1 - x²/2 … is less than 2^-25 below 1, half the float spacing there.  The one exception is y = -0 (the sine kernel
+//     gives +0), which the range predicate therefore excludes.  tests/test_sincos_exact.py checks a numpy restatement of
+//     this function against glibc over every float of [2^-13, 8] and samples below.
+//   * signs are applied AFTER the conversion to float (rounding to nearest is symmetric: (float)(-d) == -(float)d) as one
+//     XOR each with a mask taken straight from the quadrant bits — no double negations, no 64-bit selects.
+PDT_DEV bool sincos_in_core_range(float y) { return (r_fabs(y) < 120.0f) && (pdt_f2u(y) != 0x80000000u); }
+
+PDT_DEV void sincos_core(float y, float &s, float &c)
 {
-    if (abstop12(y) >= 0x42fu) { s = sinf(y); c = cosf(y); return; }      // |y| >= 120: never reached by the PLL (phase is wrapped to ±2π)
-    // glibc's three ranges collapse into its general path: for |y| < π/4 the quadrant is n = 0 and the reduction x - 0·(π/2)
-    // is exact, which is its small-argument path; its |y| < 2^-12 shortcut (s = y, c = 1) is applied as a select at the end.
     const double x = (double)y;
     const double hpi_inv = PDT_SC(7, 0x1.45F306DC9C883p+23), hpi = PDT_SC(8, 0x1.921FB54442D18p0);
     const double r = x * hpi_inv;
-    const int n = (pdt_d2i_rz(r) + 0x800000) >> 24;
+    const int t1 = pdt_d2i_rz(r) + 0x800000;                             // quadrant n = t1 >> 24 (arithmetic): bits 24, 25 = n & 3
+    const int n = t1 >> 24;
     const double xr = x - (double)n * hpi;
     const double x2 = xr * xr;
     const double sp = sc_sin_poly(xr, x2), cp = sc_cos_poly(x2);
-    const bool neg_sin = ((n & 3) == 1) || ((n & 3) == 2);               // sign of the sine-kernel argument (sgn in the table form)
-    const bool neg_cos = (n & 2) != 0;                                   // second coefficient table = negated cosine
-    const float sv = (float)(neg_sin ? -sp : sp), cv = (float)(neg_cos ? -cp : cp);
-    const bool odd = (n & 1) != 0;
-    float rs = odd ? cv : sv, rc = odd ? sv : cv;
-    if (abstop12(y) < 0x398u) { rs = y; rc = 1.0f; }                     // |y| < 2^-12
-    s = rs; c = rc;
+    // sine kernel negated for n & 3 in {1, 2}  <=>  bit 1 of n + 1;  cosine kernel negated (glibc's second table) for n & 2
+    const uint32_t ms = ((uint32_t)(t1 + 0x1000000) << 6) & 0x80000000u;
+    const uint32_t mc = ((uint32_t)t1 << 6) & 0x80000000u;
+    const float sv = pdt_u2f(pdt_f2u((float)sp) ^ ms), cv = pdt_u2f(pdt_f2u((float)cp) ^ mc);
+    const bool odd = (t1 & 0x1000000) != 0;
+    s = odd ? cv : sv; c = odd ? sv : cv;
+}
+
+PDT_DEV void sincos_exact(float y, float &s, float &c)
+{
+    if (!sincos_in_core_range(y)) { s = sinf(y); c = cosf(y); return; }   // |y| >= 120: never reached by the PLL (phase is wrapped to ±2π)
+    sincos_core(y, s, c);
 }
 PDT_DEV void sincos_exact(double y, double &s, double &c)
 {

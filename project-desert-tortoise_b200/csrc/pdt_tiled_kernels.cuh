@@ -923,6 +923,250 @@ __global__ void __launch_bounds__(front_threads(L)) k_front(const TiledArgs a, c
 }
 
 // ---------------------------------------------------------------------------------------------------
+// k_front1: the L = 1 front kernel (250 ksps and up: no interpolation, N = 26), rebuilt around Blackwell's PACKED fp32
+// pipe.  Same arithmetic as k_front<1> — out = Im(x·e^{-jφ}) with the glibc-exact sincos, then the 26-tap FIR in the
+// reference's rotating summation order, every product and every sum rounded separately (LowPassFilter.c:58-64) — but
+//   * a thread owns TWO aligned 26-sample blocks, 128 blocks apart (blocks t+1 and t+129 of the CTA's 257 staged blocks),
+//     and runs them as the two halves of f32x2 operands: per slot s one `mul.rn.f32x2` and one `fma.rn.f32x2(p, 1, acc)` for
+//     both blocks (the 1.0 comes from the parameter bank at run time — with a literal, or with add.rn.f32x2, ptxas folds
+//     the pair into a single-rounding FFMA2, tools/f32x2_test.cu).  Both blocks have the same position c in the ring, so
+//     they use the same tap for the same slot: the tap pairs (h,h) sit in UNIFORM registers, loaded once per thread from
+//     the parameter bank (SASS: FMUL2 R, R, UR / FFMA2 R, R, UR, R).  26 + 26 packed instructions per 2 outputs, against
+//     52 + 52 scalar ones;
+//   * the loop is slot-major: all 26 accumulator pairs stay in registers and each staged operand pair is loaded once
+//     (LDS.128 = two slots), ~70 registers instead of the 116 an output-major packed variant needed (profiles/README.md);
+//   * staging writes the derotated samples as (block j, block j+128) float2 pairs — exactly the operand layout — with one
+//     conflict-free STS.64 per two samples, no index division: thread q handles samples q and q + 3328 of the span;
+//   * the finished 6656-sample tile leaves through ONE bulk copy (cp.async.bulk shared -> global, SASS UBLKCP) issued by
+//     one thread, instead of a per-thread LDS/STG loop; the tile aliases the staging buffer (26.8 KB per CTA in total).
+// ---------------------------------------------------------------------------------------------------
+constexpr int F1_THREADS = 128;
+constexpr int F1_BLOCKS = 2 * F1_THREADS;                 // 26-sample blocks produced per CTA
+constexpr int F1_SPAN = F1_BLOCKS * FIR_K;                // 6656 input (= output) samples per CTA
+constexpr int F1_HALF = F1_THREADS * FIR_K;               // 3328: distance between the two samples of a staged pair
+constexpr int F1_PAIRS = (F1_THREADS + 1) * FIR_K;        // 3354 staged float2 pairs (one history block in front)
+struct TapsPair { float2 hh[FIR_K]; float one, pad; };    // hh[u] = (hr[u], hr[u]); one = 1.0f (run-time operand, see above)
+
+__device__ __forceinline__ u64 f1_pk(float lo, float hi) { return ((u64)__float_as_uint(hi) << 32) | (u64)__float_as_uint(lo); }
+__device__ __forceinline__ u64 f1_mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 f1_fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
+// Staging.  Pair q of the operand buffer is (sample i0+q, sample i0+q+3328), i0 = base-26.  A thread takes pairs 2t, 2t+1 of
+// every 256-pair round: its two "low" samples and its two "high" samples are adjacent in memory — one 16-byte IQ load and
+// one 8-byte phase load each — and the two finished pairs leave as one STS.128.  The loads of round r+1 are issued before
+// round r is computed (explicit register double-buffering): ncu on the first version showed half of the staging time
+// waiting for the global loads at their first use (profiles/README.md r02b).
+struct F1Raw { float4 iq_lo, iq_hi; float2 ph_lo, ph_hi; };      // two IQ samples + two phases, low and high half
+
+// checked loads (edge CTAs: capture start / end inside the span, and the last block's pairs): indices are clamped for the
+// loads, f1_derot4<true> selects 0 outside [0, n) — no branch.  PCM: int16 IQ (wave.c:141-166: /32768).
+template <bool PCM, bool CHECK>
+__device__ __forceinline__ void f1_load(F1Raw &r, const void *__restrict__ iq_cap, const float *__restrict__ ph, long long ilo, long long n)
+{
+    static_assert(CHECK, "interior CTAs stage through cp.async (f1_stage)");
+    auto two = [&](long long i, float4 &iq, float2 &p2) {
+        long long i0 = i, i1 = i + 1;
+        i0 = i0 < 0 ? 0 : (i0 >= n ? n - 1 : i0); i1 = i1 < 0 ? 0 : (i1 >= n ? n - 1 : i1);
+        float a0, b0, a1, b1;
+        load_iq1(iq_cap, PCM ? 1 : 0, (u64)i0, a0, b0); load_iq1(iq_cap, PCM ? 1 : 0, (u64)i1, a1, b1);
+        iq = make_float4(a0, b0, a1, b1);
+        p2 = make_float2(ph[i0], ph[i1]);
+    };
+    two(ilo, r.iq_lo, r.ph_lo);
+    two(ilo + F1_HALF, r.iq_hi, r.ph_hi);
+}
+
+template <bool CHECK>
+__device__ __forceinline__ float4 f1_derot4(const F1Raw &r, long long ilo, long long n, bool &big)
+{
+    auto one = [&](float p, float q, float phase, long long i) -> float {
+        big |= !sincos_in_core_range(phase);
+        float ti, tr;
+        sincos_core(phase, ti, tr);
+        const float nti = -ti;
+        const float o = p * nti + q * tr;                                           // CarrierTrackingPLL.c:110,:113
+        return (CHECK && (i < 0 || i >= n)) ? 0.0f : o;
+    };
+    float4 o;                                                                       // (lo q, hi q, lo q+1, hi q+1) = pairs q, q+1
+    o.x = one(r.iq_lo.x, r.iq_lo.y, r.ph_lo.x, ilo);
+    o.y = one(r.iq_hi.x, r.iq_hi.y, r.ph_hi.x, ilo + F1_HALF);
+    o.z = one(r.iq_lo.z, r.iq_lo.w, r.ph_lo.y, ilo + 1);
+    o.w = one(r.iq_hi.z, r.iq_hi.w, r.ph_hi.y, ilo + 1 + F1_HALF);
+    return o;
+}
+
+// 8-byte cp.async (LDGSTS): the NCO phases of the next round travel global -> shared memory without holding registers, so
+// nothing tempts ptxas into sinking the loads next to their first use (it did, under the 72-register budget: r02b)
+__device__ __forceinline__ void f1_cp8(uint32_t dst_smem, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ float2 f1_lds8(uint32_t src_smem)
+{
+    float2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(src_smem) : "memory");
+    return v;
+}
+
+template <bool PCM, bool CHECK>
+__device__ __forceinline__ void f1_stage(float2 *__restrict__ P, float2 (*__restrict__ RP)[F1_THREADS], const void *__restrict__ iq_cap,
+                                         const float *__restrict__ ph, const long long base, const long long n, const int tid,
+                                         float *__restrict__ trace_out)
+{
+    constexpr int ROUNDS = FIR_K / 2;                                               // 13 rounds of 256 pairs, then 26 pairs
+    const long long i0 = base - FIR_K;
+    bool big = false;
+    float4 *P4 = reinterpret_cast<float4 *>(P);
+    auto at = [&](int r) { return 2 * tid + r * 2 * F1_THREADS; };
+    F1Raw A;
+    if (!CHECK) {
+        // interior CTA.  Round r: the phases of round r arrive through the thread's own two shared-memory slots (requested a
+        // whole round earlier), the IQ samples through plain loads issued at the top of the round — they are only needed at
+        // the derotation, behind ~40 dependent double-precision operations.
+        // Two slot sets: round r first requests round r+1 into the other set and THEN waits for its own data
+        // (wait_group 1) — the request is ordered in front of the wait, the wait in front of the phase reads, the
+        // arithmetic depends on those: the copy has a whole round of arithmetic to land, whatever the scheduler does.
+        // (pointers and shared-memory offsets advance by constants: the round costs no address arithmetic to speak of)
+        const float *php = ph + (i0 + 2 * tid);                                   // phases of this thread's low pair, round r
+        const char *iqp = PCM ? (const char *)(reinterpret_cast<const short2 *>(iq_cap) + (i0 + 2 * tid))
+                              : (const char *)(reinterpret_cast<const float2 *>(iq_cap) + (i0 + 2 * tid));
+        constexpr int IQ_B = PCM ? 4 : 8;                                         // bytes per IQ sample
+        constexpr uint32_t HALF_B = F1_THREADS * sizeof(float2);                  // RP[k+1][tid] - RP[k][tid] in bytes
+        uint32_t slot = (uint32_t)__cvta_generic_to_shared(&RP[0][tid]);          // set 0: RP[0], RP[1]; set 1: RP[2], RP[3]
+        uint32_t other = slot + 2 * HALF_B;
+        float4 *dst = P4 + tid;
+        f1_cp8(slot, php); f1_cp8(slot + HALF_B, php + F1_HALF);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+#pragma unroll 1
+        for (int r = 0; r < ROUNDS; r++) {
+            if (r + 1 < ROUNDS) { f1_cp8(other, php + 2 * F1_THREADS); f1_cp8(other + HALF_B, php + 2 * F1_THREADS + F1_HALF); }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            if (PCM) {
+                const short4 lo = *reinterpret_cast<const short4 *>(iqp);
+                const short4 hi = *reinterpret_cast<const short4 *>(iqp + (size_t)F1_HALF * IQ_B);
+                A.iq_lo = make_float4(lo.x / 32768.0f, lo.y / 32768.0f, lo.z / 32768.0f, lo.w / 32768.0f);
+                A.iq_hi = make_float4(hi.x / 32768.0f, hi.y / 32768.0f, hi.z / 32768.0f, hi.w / 32768.0f);
+            } else {
+                A.iq_lo = *reinterpret_cast<const float4 *>(iqp);
+                A.iq_hi = *reinterpret_cast<const float4 *>(iqp + (size_t)F1_HALF * IQ_B);
+            }
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+            A.ph_lo = f1_lds8(slot); A.ph_hi = f1_lds8(slot + HALF_B);
+            *dst = f1_derot4<false>(A, 0, n, big);
+            php += 2 * F1_THREADS; iqp += (size_t)2 * F1_THREADS * IQ_B; dst += F1_THREADS;
+            const uint32_t t_ = slot; slot = other; other = t_;
+        }
+    } else {
+#pragma unroll 1
+        for (int r = 0; r < ROUNDS; r++) {
+            f1_load<PCM, true>(A, iq_cap, ph, i0 + at(r), n);
+            P4[at(r) >> 1] = f1_derot4<true>(A, i0 + at(r), n, big);
+        }
+    }
+    // the last block's 26 pairs go to threads 0…12 (checked loads: their high half may pass the end of the capture)
+    if (tid < FIR_K / 2) {
+        f1_load<PCM, true>(A, iq_cap, ph, i0 + F1_HALF + 2 * tid, n);
+        P4[(F1_HALF >> 1) + tid] = f1_derot4<true>(A, i0 + F1_HALF + 2 * tid, n, big);
+    }
+    if (big || trace_out) {
+        // never taken by PLL phases (wrapped to ±2π): phases beyond the branch-free sincos's range (a corrupted phase stream)
+        // go through the general routine; the rare trace tap is written here too, off the hot loop
+        for (int q = tid; q < F1_PAIRS; q += F1_THREADS) {
+            float2 v = P[q];
+            const long long idx[2] = {i0 + q, i0 + q + F1_HALF};
+            for (int h = 0; h < 2; h++) {
+                const long long i = idx[h];
+                if (i < 0 || i >= n) continue;
+                float p_, q_;
+                load_iq1(iq_cap, PCM ? 1 : 0, (u64)i, p_, q_);
+                float ti, tr_;
+                sincos_exact(ph[i], ti, tr_);
+                const float nti = -ti;
+                const float o = p_ * nti + q_ * tr_;
+                if (h) v.y = o; else v.x = o;
+                if (trace_out && i >= base && (h || q < F1_HALF + FIR_K)) trace_out[i] = o;
+            }
+            P[q] = v;
+        }
+    }
+}
+
+template <bool PCM>
+__global__ void __launch_bounds__(F1_THREADS, 7) k_front1(const TiledArgs a, const __grid_constant__ TapsPair taps)
+{
+    __shared__ __align__(128) float2 P[F1_PAIRS];          // staged operand pairs; re-used as the output tile (6656 floats)
+    __shared__ __align__(16) float2 RP[4][F1_THREADS];     // per-thread landing slots of the phase prefetch: two sets of (low, high half)
+    const uint32_t cap = blockIdx.y;
+    const int tid = threadIdx.x;
+    const long long n = (long long)cap_len(a, cap);
+    const long long base = (long long)blockIdx.x * F1_SPAN;
+    if (base >= n || !cap_selected(a, cap)) return;
+    const float *__restrict__ ph = a.ph + (u64)cap * a.ws_stride;
+    const void *__restrict__ iq_cap = PCM ? (const void *)(reinterpret_cast<const short2 *>(a.iq) + (u64)cap * a.stride)
+                                          : (const void *)(reinterpret_cast<const float2 *>(a.iq) + (u64)cap * a.stride);
+    const pdt_traces *tr = a.traces ? &a.traces[cap] : nullptr;
+    float *trace_out = (tr && tr->pll_out) ? reinterpret_cast<float *>(tr->pll_out) : nullptr;
+
+    // ---- staging: pair q = (sample base-26+q, sample base-26+q+3328) ------------------------------------------------
+    if (base >= FIR_K && base + F1_SPAN <= n) f1_stage<PCM, false>(P, RP, iq_cap, ph, base, n, tid, trace_out);    // interior CTA
+    else                                      f1_stage<PCM, true>(P, RP, iq_cap, ph, base, n, tid, trace_out);
+    __syncthreads();
+
+    // ---- FIR: blocks tid+1 (low halves) and tid+129 (high halves), slot-major --------------------------------------
+    u64 acc[FIR_K];
+    {
+        const u64 one2 = f1_pk(taps.one, taps.one);
+#pragma unroll
+        for (int c = 0; c < FIR_K; c++) acc[c] = 0ull;                              // +0.0f, +0.0f
+        const float4 *prev4 = reinterpret_cast<const float4 *>(P + tid * FIR_K);    // 208 B rows: 16-byte aligned, and the
+        const float4 *cur4 = reinterpret_cast<const float4 *>(P + (tid + 1) * FIR_K);   // 8 lanes of an LDS.128 phase hit 32 distinct banks
+#pragma unroll
+        for (int s2 = 0; s2 < FIR_K / 2; s2++) {
+            const float4 xc4 = cur4[s2], xp4 = prev4[s2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int s = 2 * s2 + h;
+                const u64 xc = h ? f1_pk(xc4.z, xc4.w) : f1_pk(xc4.x, xc4.y);
+                const u64 xp = h ? f1_pk(xp4.z, xp4.w) : f1_pk(xp4.x, xp4.y);
+#pragma unroll
+                for (int c = 0; c < FIR_K; c++) {
+                    // output c of a block sums ring slots s = 0…25 in this order; slot s holds the current block's sample
+                    // for s <= c and the previous block's otherwise, times hr[(c - s) mod 26]   (pdt_tiled.cuh::fir_block26)
+                    const u64 x = (s <= c) ? xc : xp;
+                    const float2 hh = taps.hh[(c - s + FIR_K) % FIR_K];
+                    acc[c] = f1_fma2(f1_mul2(x, f1_pk(hh.x, hh.y)), one2, acc[c]);
+                }
+            }
+        }
+    }
+    __syncthreads();                                       // every operand has been read: the buffer becomes the output tile
+    float *ys = reinterpret_cast<float *>(P);
+#pragma unroll
+    for (int c = 0; c < FIR_K; c++) {
+        ys[tid * FIR_K + c] = __uint_as_float((unsigned)acc[c]);
+        ys[tid * FIR_K + c + F1_HALF] = __uint_as_float((unsigned)(acc[c] >> 32));
+    }
+    const long long left = n - base;
+    const unsigned span = (unsigned)(left < F1_SPAN ? left : F1_SPAN);
+    float *y = a.y + (u64)cap * a.ws_stride + (u64)base;
+    const unsigned bytes = ((span + 3u) & ~3u) * 4u;       // rounded up into the row padding (ws_stride is a multiple of 4)
+    if ((reinterpret_cast<uintptr_t>(y) & 15) == 0) {
+        // generic-proxy writes of the tile -> visible to the async proxy, then one bulk copy shared -> global
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                         :: "l"(y), "r"((uint32_t)__cvta_generic_to_shared(ys)), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");       // the tile has been read: the CTA may retire
+        }
+    } else {
+        __syncthreads();
+        for (unsigned o = tid; o < span; o += F1_THREADS) y[o] = ys[o];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // AGC core: lane per (capture, tile)
 // ---------------------------------------------------------------------------------------------------
 PDT_DEV float agc_guess(const float *y, u64 at)
