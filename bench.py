@@ -588,6 +588,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-single", action="store_true")
+    ap.add_argument("--groups", type=int, default=-1, help="capture groups per context (pdt_set_groups; -1 = library default for 4 or fewer "
+                                                           "batches in flight, 1 beyond: every context then uses two internal streams and "
+                                                           "the process stays inside the 32 hardware work queues)")
     ap.add_argument("--no-gather", action="store_true", help="N > 1 diagnostic: skip the NCCL all-gather of the frame tables")
     ap.add_argument("--strong-shards", type=int, default=0,
                     help="N = 1 diagnostic: also run this GPU's share of an N-way strong-scaling step (--captures / N captures per step)")
@@ -743,7 +746,8 @@ def main():
     # batches in flight: context k (own workspaces, own internal streams) on side stream k; joined to the main stream at the end
     inflight = args.inflight if args.inflight > 0 else (4 if args.steps >= 8 else 3)
     inflight = max(1, min(inflight, max(args.steps, 1)))
-    rot = Rotation(C_, inflight)
+    groups = args.groups if args.groups >= 0 else (0 if inflight <= 4 else 1)
+    rot = Rotation(C_, inflight, groups=groups)
     d, ctxs = rot.ctxs[0], rot.ctxs
     ms_step, launches, clocks, per_rank = timed(rot, args.steps, args.warmup, ClockSampler(local))
     total_samples = C_ * n * world
@@ -855,7 +859,7 @@ def main():
                    "interp": d.params.interp, "taps": d.params.taps, "chunk": d.params.chunk,
                    "l2": f"inputs {C_ * n * bytes_per_sample / 1e9:.2f} GB per GPU, far larger than the 126 MB L2 (no flush needed)",
                    "parallelism": f"captures sharded over {world} GPU(s), frames all-gathered over NCCL" if world > 1 else "one GPU",
-                   "batches_in_flight": inflight, "numa": numa,
+                   "batches_in_flight": inflight, "capture_groups_per_batch": groups or "library default (3)", "numa": numa,
                    "gather": (None if world == 1 else ("off (--no-gather)" if args.no_gather else
                               "frame table copied to a staging ring, all-gathered on one communication stream"))},
         "gpu_launches": int(launches), "roofline": roofline, "kernels": ktable,

@@ -77,7 +77,8 @@ assert STATS_DTYPE.itemsize == C.sizeof(Stats)
 
 
 def lib_path(prec: str) -> str:
-    return os.path.join(HERE, f"libpdt_{prec}.so")
+    variant = os.environ.get("PDT_LIB_VARIANT", "")          # experiment builds (tools/): libpdt_f32<variant>.so
+    return os.path.join(HERE, f"libpdt_{prec}{variant if prec == 'f32' else ''}.so")
 
 
 def build(verbose: bool = False) -> None:

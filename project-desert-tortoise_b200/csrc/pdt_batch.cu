@@ -145,6 +145,8 @@ struct pdt_ctx {
     uint32_t prelock_from = 0xFFFFFFFFu; // this call: captures >= this index start pre-locked (pdt_demod_segments_device)
     tiled::TiledArgs ta;                 // workspace pointers + plans of the tiled engine (engine == PDT_ENGINE_TILED)
     tiled::TapsRev   taps_rev;
+    int         ws_aliased = 0;          // y/z share the rows of sp/ph (L = 1)
+    float      *y_sep = nullptr, *z_sep = nullptr;   // separate y/z of a traced call on an aliased context (allocated on demand)
     tiled::TapsPair  taps_pair;          // L = 1: duplicated tap pairs of the packed front kernel (k_front1)
     int         front_packed = 0;        // k_front1 in use (L = 1; PDT_FRONT_SCALAR=1 keeps the scalar k_front<1> for A/B runs)
     size_t      front_smem = 0;
@@ -225,7 +227,15 @@ static int tiled_setup(pdt_ctx *c)
     cudaError_t e;
 #define TA(ptr, bytes) if ((e = cudaMalloc((void **)&(ptr), (bytes))) != cudaSuccess) return fail(PDT_ENOMEM, "tiled workspace (%zu bytes): %s", (size_t)(bytes), cudaGetErrorString(e))
     TA(t.sp, nin * sizeof(float)); TA(t.ph, nin * sizeof(float));
-    TA(t.y, nout * sizeof(float)); TA(t.z, nout * sizeof(float));
+    // L = 1: the FIR output y re-uses the rows of sp and the AGC output z those of ph.  Row-wise this is safe by stream
+    // order: capture c's y is written by k_front after the last reader of sp[c] (its PLL kernels), and z[c] by the AGC
+    // after k_front has consumed ph[c]; kernels of the other pass only touch the rows of their own captures.  It halves
+    // the workspaces of a context (1024 x 1 M: 17 -> 9 GB), which is what lets more batches be in flight — the serial
+    // acquisition of a never-locking capture is 60 ms of latency that only other batches can hide.
+    // A call with trace taps needs ph and y beside z at the end: it gets separate buffers on demand (tiled_run).
+    c->ws_aliased = (cc.L == 1);
+    if (c->ws_aliased) { t.y = t.sp; t.z = t.ph; }
+    else { TA(t.y, nout * sizeof(float)); TA(t.z, nout * sizeof(float)); }
     TA(t.acq, sizeof(AcqResult) * c->max_captures);
     const size_t np = (size_t)c->max_captures * t.pll.max_tiles, na = (size_t)c->max_captures * t.agc_max_tiles;
     TA(t.guess, np * sizeof(LoopState2)); TA(t.pll_start, np * sizeof(LoopState2)); TA(t.pll_end, np * sizeof(LoopState2));
@@ -265,7 +275,9 @@ static int tiled_setup(pdt_ctx *c)
 static void tiled_free(pdt_ctx *c)
 {
     tiled::TiledArgs &t = c->ta;
-    cudaFree(t.sp); cudaFree(t.ph); cudaFree(t.y); cudaFree(t.z); cudaFree(t.acq); cudaFree(t.guess);
+    cudaFree(t.sp); cudaFree(t.ph); cudaFree(t.acq); cudaFree(t.guess);
+    if (!c->ws_aliased) { cudaFree(t.y); cudaFree(t.z); }
+    cudaFree(c->y_sep); cudaFree(c->z_sep);
     cudaFree(t.pll_start); cudaFree(t.pll_end); cudaFree(t.agc_start); cudaFree(t.agc_end); cudaFree(t.counters);
     cudaFree(t.sym); cudaFree(t.gidx); cudaFree(t.gar); cudaFree(t.pll_tasks); cudaFree(t.agc_tasks); cudaFree(t.task_counts);
 }
@@ -297,7 +309,12 @@ struct GroupLaunch {
         // back to the reference's acquisition sweep, so k_acquire covers every capture and skips the pre-locked ones
         const uint32_t serial = std::min(cnt, t.prelock_from);
         if (serial < cnt) { k_prelock<<<blocks(cnt - serial, EST_WARPS), EST_WARPS * 32, 0, s>>>(t); mark(s, "k_prelock"); count_launch(1); }
-        k_acquire<<<cnt, ACQ_THREADS, 0, s>>>(t, 0);
+        static int acq0_threads = 0;                      // PDT_ACQ0_THREADS: experiment knob (CTA width of the first acquisition pass)
+        if (acq0_threads == 0) {
+            const char *e = getenv("PDT_ACQ0_THREADS");
+            acq0_threads = e ? std::max(96, std::min((atoi(e) / 32) * 32, (int)ACQ_THREADS)) : ACQ_THREADS;
+        }
+        if (!dbg_skip("k_acquire0")) k_acquire<<<cnt, acq0_threads, 0, s>>>(t, 0);
         mark(s, "k_acquire");
         count_launch(3);
     }
@@ -307,6 +324,11 @@ struct GroupLaunch {
         k_acquire<<<std::max(1u, cnt), ACQ_THREADS_SLOW, 0, s>>>(t, 1);
         mark(s, "k_acquire");
         count_launch(1);
+    }
+    static bool dbg_skip(const char *name)                // PDT_DEBUG_SKIP=k_gardner,k_bits,…: TIMING EXPERIMENTS ONLY (results are garbage)
+    {
+        static const char *list = getenv("PDT_DEBUG_SKIP");
+        return list && strstr(list, name) != nullptr;
     }
     void pipeline(cudaStream_t s, int slow_pass)
     {
@@ -321,21 +343,26 @@ struct GroupLaunch {
             q.agc_tasks += (size_t)c->max_captures * q.agc_tasks_per_cap;
         }
         q.task_counts = c->ta.task_counts + 2 * (size_t)(slow_pass * (pdt_ctx::MAX_GROUPS + 1) + slot);
-        const unsigned ls_cap = 2u * (unsigned)std::max(c->sm_count, 1);          // resident CTAs of a persistent lane-stream launch
+        static unsigned ls_per_sm = 0;                    // PDT_LS_CAP: experiment knob (CTAs per SM of a persistent lane-stream launch)
+        if (ls_per_sm == 0) { const char *e = getenv("PDT_LS_CAP"); ls_per_sm = e ? (unsigned)std::max(1, std::min(atoi(e), 8)) : 2u; }
+        const unsigned ls_cap = ls_per_sm * (unsigned)std::max(c->sm_count, 1);    // resident CTAs of a persistent lane-stream launch
         const unsigned pll_grid = std::min(blocks((u64)cnt * q.pll_tasks_per_cap, LS_WARPS), ls_cap);
         const unsigned agc_grid = std::min(blocks((u64)cnt * q.agc_tasks_per_cap, LS_WARPS), ls_cap);
         k_pll_tasks<<<blocks(cnt, 128), 128, 0, s>>>(q);
         if (q.pll.max_tiles > 1)
             k_estimate<<<blocks((u64)cnt * (q.pll.max_tiles - 1), EST_WARPS), EST_WARPS * 32, 0, s>>>(q);
         mark(s, "k_estimate");
-        k_pll_core<<<pll_grid, LS_WARPS * 32, LS_SMEM, s>>>(q);
+        if (!dbg_skip("k_pll_core")) k_pll_core<<<pll_grid, LS_WARPS * 32, LS_SMEM, s>>>(q);
         mark(s, "k_pll_core");
-        k_pll_fix_par<<<pll_grid, LS_WARPS * 32, LS_SMEM, s>>>(q);
-        k_pll_fix_par<<<pll_grid, LS_WARPS * 32, LS_SMEM, s>>>(q);
+        if (!dbg_skip("k_pll_fix_par")) {
+            k_pll_fix_par<<<pll_grid, LS_WARPS * 32, LS_SMEM, s>>>(q);
+            k_pll_fix_par<<<pll_grid, LS_WARPS * 32, LS_SMEM, s>>>(q);
+        }
         mark(s, "k_pll_fix_par");
         k_pll_fix<<<blocks(cnt, 128), 128, 0, s>>>(q);
         mark(s, "k_pll_fix");
-        if (c->front_packed) {
+        if (dbg_skip("k_front")) {
+        } else if (c->front_packed) {
             dim3 g(blocks(n_max, F1_SPAN), cnt);
             if (q.pcm16) k_front1<true><<<g, F1_THREADS, 0, s>>>(q, c->taps_pair);
             else         k_front1<false><<<g, F1_THREADS, 0, s>>>(q, c->taps_pair);
@@ -346,15 +373,15 @@ struct GroupLaunch {
         mark(s, "k_front");
         k_agc_plan<<<blocks((u64)cnt * 32, 128), 128, 0, s>>>(q);
         mark(s, "k_agc_plan");
-        k_agc_core<<<agc_grid, LS_WARPS * 32, LS_SMEM, s>>>(q);
+        if (!dbg_skip("k_agc_core")) k_agc_core<<<agc_grid, LS_WARPS * 32, LS_SMEM, s>>>(q);
         mark(s, "k_agc_core");
         k_agc_fix_par<<<agc_grid, LS_WARPS * 32, LS_SMEM, s>>>(q);
         mark(s, "k_agc_fix_par");
         k_agc_fix<<<blocks(cnt, 128), 128, 0, s>>>(q);
         mark(s, "k_agc_fix");
-        k_gardner<<<blocks(cnt, GAR_WARPS), GAR_WARPS * 32, 0, s>>>(q);
+        if (!dbg_skip("k_gardner")) k_gardner<<<blocks(cnt, GAR_WARPS), GAR_CTA_THREADS, 0, s>>>(q);
         mark(s, "k_gardner");
-        k_bits<<<blocks(cnt, BITS_WARPS), BITS_WARPS * 32, 0, s>>>(q);
+        if (!dbg_skip("k_bits")) k_bits<<<blocks(cnt, BITS_WARPS), BITS_WARPS * 32, 0, s>>>(q);
         mark(s, "k_bits");
         count_launch(q.pll.max_tiles > 1 ? 13 : 12);
     }
@@ -395,6 +422,12 @@ static int tiled_run(pdt_ctx *c, const void *d_iq, int pcm16, uint32_t n_capture
 {
     using namespace tiled;
     TiledArgs t = c->ta;
+    if (traces && c->ws_aliased) {       // trace taps read ph / y / z after the run: give this call its own y and z
+        const size_t nout = (size_t)c->max_captures * t.ws_stride * c->cc.L;
+        if (!c->y_sep) PDT_CUDA(cudaMalloc((void **)&c->y_sep, nout * sizeof(float)));
+        if (!c->z_sep) PDT_CUDA(cudaMalloc((void **)&c->z_sep, nout * sizeof(float)));
+        t.y = c->y_sep; t.z = c->z_sep;
+    }
     t.iq = d_iq; t.pcm16 = pcm16; t.stride = stride; t.n_captures = n_captures;
     t.n_samples = n_samples ? c->d_nsamp : nullptr; t.n_uniform = stride;
     t.stats = c->d_stats; t.frames = c->d_frames; t.traces = traces ? c->d_traces : nullptr;
@@ -414,7 +447,7 @@ static int tiled_run(pdt_ctx *c, const void *d_iq, int pcm16, uint32_t n_capture
     c->n_marks = 0;
     uint32_t per = 0;
     const int groups = group_plan(c, n_captures, per);
-    if (c->profiling == 1 || traces || groups < 2) {
+    if (c->profiling == 1 || traces || (groups < 2 && !two_pass)) {
         if (ready) for (int gi = 0; gi < groups; gi++) PDT_CUDA(cudaStreamWaitEvent(s, ready[gi], 0));
         GroupLaunch g = make_group(c, t, 0, n_captures, n_max, c->profiling != 0);
         g.head(s);
@@ -446,7 +479,9 @@ static int tiled_run(pdt_ctx *c, const void *d_iq, int pcm16, uint32_t n_capture
             PDT_CUDA(cudaStreamWaitEvent(s, c->ev_join[gi], 0));
             used = gi + 1;
         }
-        if (two_pass) {
+        static int dbg_skip_slow = -1;                    // PDT_DEBUG_SKIP_SLOW=1: TIMING EXPERIMENTS ONLY — the slow captures are left undone
+        if (dbg_skip_slow < 0) { const char *e = getenv("PDT_DEBUG_SKIP_SLOW"); dbg_skip_slow = e ? atoi(e) : 0; }
+        if (two_pass && dbg_skip_slow != 1) {
             // ONE slow-capture stream for the whole batch (streams beyond the device's 8 hardware queues alias, and a
             // launch waiting behind the long second acquisition pass would block every stream sharing its queue)
             if (!c->sstream) {
@@ -459,8 +494,8 @@ static int tiled_run(pdt_ctx *c, const void *d_iq, int pcm16, uint32_t n_capture
             GroupLaunch whole = make_group(c, t, 0, n_captures, n_max, tl);
             whole.gid = 99;
             whole.mark(c->sstream, "begin");
-            whole.acquire_rest(c->sstream);
-            whole.pipeline(c->sstream, 1);
+            if (dbg_skip_slow != 3) whole.acquire_rest(c->sstream);       // (2: second acquisition pass only, 3: slow pipeline only)
+            if (dbg_skip_slow != 2) whole.pipeline(c->sstream, 1);
             PDT_CUDA(cudaEventRecord(c->ev_sjoin, c->sstream));
             PDT_CUDA(cudaStreamWaitEvent(s, c->ev_sjoin, 0));
         }

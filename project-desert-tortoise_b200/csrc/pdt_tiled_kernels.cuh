@@ -202,12 +202,18 @@ __global__ void __launch_bounds__(256) k_sp(const TiledArgs a)
 // the booleans are compared; on the first difference the block restarts from that sample with the corrected
 // flag.  The committed trajectory is exactly the serial one.
 // ---------------------------------------------------------------------------------------------------
-constexpr int ACQ_B = 256;            // samples per pipeline block
+#ifndef PDT_ACQ_B
+#define PDT_ACQ_B 256
+#endif
+#ifndef PDT_ACQ_THREADS
+#define PDT_ACQ_THREADS 224
+#endif
+constexpr int ACQ_B = PDT_ACQ_B;      // samples per pipeline block
 constexpr int ACQ_RING = 4;           // blocks in flight: core | terms | EMAs | decisions
 constexpr int ACQ_SERIAL = 64;        // warp 0: the core lane; warp 1: the two EMA lanes (same code, own data)
-constexpr int ACQ_THREADS = 224;      // 2 serial warps + 5 helper warps
-constexpr int ACQ_THREADS_SLOW = 96;  // second pass: the few slow captures hold their CTA for tens of ms — a thinner CTA (one helper warp) halves the
-                                      // registers they pin down while several batches are in flight
+constexpr int ACQ_THREADS = PDT_ACQ_THREADS;   // 2 serial warps + the helper warps (first pass)
+constexpr int ACQ_THREADS_SLOW = 128; // second pass: the few slow captures hold their CTA for tens of ms — a thinner CTA (two helper warps; four warps so
+                                      // that the rotated roles reach all four sub-cores) pins fewer registers while several batches are in flight
 
 struct __align__(16) AcqSmem {
     float sp[ACQ_RING][ACQ_B], a[ACQ_RING][ACQ_B], b[ACQ_RING][ACQ_B];               // inputs
@@ -320,7 +326,12 @@ __global__ void __launch_bounds__(ACQ_THREADS) k_acquire(const TiledArgs a, cons
     __shared__ AcqSmem s;
     const int n_threads = (int)blockDim.x, n_helpers = n_threads - ACQ_SERIAL;     // 2 serial warps + the helper warps
     const uint32_t cap = blockIdx.x;
-    const int tid = threadIdx.x;
+    // Roles are assigned by a VIRTUAL thread index that rotates the warps from CTA to CTA.  A warp's scheduler (SM sub-core) is
+    // its warp index modulo 4: with fixed roles the core lane of every CTA on an SM — the one warp that decides how long a
+    // step takes, issuing one instruction every ~4 cycles — sits on sub-core 0, and four or five co-resident CTAs (several
+    // batches in flight) ask that one scheduler for more than one instruction per cycle while the other three idle.
+    const int n_warps_cta = (int)blockDim.x >> 5;
+    const int tid = ((((int)threadIdx.x >> 5) + n_warps_cta - (int)(blockIdx.x % (unsigned)n_warps_cta)) % n_warps_cta) * 32 + ((int)threadIdx.x & 31);
     const u64 n = cap_len(a, cap), first = (u64)cap * a.stride;
     const PllParams &pp = a.cc.pll;
     AcqResult *res = &a.acq[cap];
@@ -683,7 +694,10 @@ __global__ void __launch_bounds__(EST_WARPS * 32) k_prelock(const TiledArgs a)
 // ---------------------------------------------------------------------------------------------------
 // PLL track core: lane per (capture, tile), a warp = 32 consecutive tiles of one capture, streams moved by the TMA
 // ---------------------------------------------------------------------------------------------------
-constexpr int LS_WARPS = 2;                               // warps per CTA of the lane-stream kernels
+#ifndef PDT_LS_WARPS
+#define PDT_LS_WARPS 2
+#endif
+constexpr int LS_WARPS = PDT_LS_WARPS;                    // warps per CTA of the lane-stream kernels
 constexpr size_t LS_SMEM = LS_WARPS * sizeof(LaneStreamSmem);
 
 struct PllLaneStep {
@@ -1108,8 +1122,12 @@ __global__ void __launch_bounds__(F1_THREADS, 7) k_front1(const TiledArgs a, con
     float *trace_out = (tr && tr->pll_out) ? reinterpret_cast<float *>(tr->pll_out) : nullptr;
 
     // ---- staging: pair q = (sample base-26+q, sample base-26+q+3328) ------------------------------------------------
-    if (base >= FIR_K && base + F1_SPAN <= n) f1_stage<PCM, false>(P, RP, iq_cap, ph, base, n, tid, trace_out);    // interior CTA
-    else                                      f1_stage<PCM, true>(P, RP, iq_cap, ph, base, n, tid, trace_out);
+    // interior CTA whose sample pairs are naturally aligned (the vector loads take two IQ samples at once: a capture that
+    // starts at an odd sample offset — odd stride, odd capture index — stages through the scalar, checked path instead)
+    const uintptr_t pair_mask = PCM ? 7u : 15u;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(iq_cap) + (uintptr_t)(base - FIR_K) * (PCM ? 4u : 8u)) & pair_mask) == 0;
+    if (aligned && base >= FIR_K && base + F1_SPAN <= n) f1_stage<PCM, false>(P, RP, iq_cap, ph, base, n, tid, trace_out);
+    else                                                 f1_stage<PCM, true>(P, RP, iq_cap, ph, base, n, tid, trace_out);
     __syncthreads();
 
     // ---- FIR: blocks tid+1 (low halves) and tid+129 (high halves), slot-major --------------------------------------
@@ -1346,7 +1364,10 @@ __global__ void __launch_bounds__(128) k_agc_fix(const TiledArgs a)
 //   k_bits     ManchesterDecode.c:27-97 + ByteSync.c:42-148 over the symbol stream, lane per capture.
 // ---------------------------------------------------------------------------------------------------
 constexpr int GAR_WIN = 4096;
-constexpr int GAR_WARPS = 2;
+#ifndef PDT_GAR_WARPS
+#define PDT_GAR_WARPS 2
+#endif
+constexpr int GAR_WARPS = PDT_GAR_WARPS;
 constexpr int GAR_STAGE = 512;          // symbols staged per flush (a window yields window/step of them; a full stage just flushes early)
 
 
@@ -1520,12 +1541,24 @@ __device__ __forceinline__ void gardner_capture(const TiledArgs &a, const uint32
     if (lane == 0) { GarRecord r; r.n_sym = n_sym; r.final_next = gs.next; r.pad = 0.f; a.gar[cap] = r; }
 }
 
-__global__ void __launch_bounds__(GAR_WARPS * 32) k_gardner(const TiledArgs a)
+// GAR_SPREAD: the CTA is launched with 4 warps of which 2 work — warps {0,1} in even CTAs, {2,3} in odd ones; the other two
+// retire at once.  A warp's scheduler is its index modulo 4: with plain 2-warp CTAs every capture's serial lane would sit
+// on sub-cores 0 and 1 of its SM and the other two schedulers would never see this kernel.
+#ifndef PDT_GAR_SPREAD
+#define PDT_GAR_SPREAD 0
+#endif
+constexpr int GAR_CTA_THREADS = PDT_GAR_SPREAD ? 128 : GAR_WARPS * 32;
+__global__ void __launch_bounds__(GAR_CTA_THREADS) k_gardner(const TiledArgs a)
 {
     __shared__ __align__(16) float wins[GAR_WARPS][GAR_WIN];
     __shared__ float ssym[GAR_WARPS][GAR_STAGE], serr[GAR_WARPS][GAR_STAGE];
     __shared__ unsigned sidx[GAR_WARPS][GAR_STAGE];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    int wib = threadIdx.x >> 5;
+    if (PDT_GAR_SPREAD) {
+        wib -= 2 * (int)(blockIdx.x & 1u);
+        if (wib < 0 || wib >= GAR_WARPS) return;
+    }
     const uint32_t cap = blockIdx.x * GAR_WARPS + wib;
     if (cap >= a.n_captures || !cap_selected(a, cap)) return;
     const bool fast = (double)a.cc.chunk * a.cc.L + 64.0 < 4.0e6;

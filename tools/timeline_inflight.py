@@ -29,7 +29,7 @@ tl = ctxs[a.inflight // 2].timeline()
 by = {}
 for name, g, t in tl:
     by.setdefault(g, []).append((name, t))
-for g in (0, 99):
+for g in sorted(by):
     prev = by[g][0][1] if by.get(g) else 0.0
     print(f"stream {g}:")
     for name, t in by.get(g, []):
