@@ -597,7 +597,7 @@ def main():
     ap.add_argument("--inflight", type=int, default=0,
                     help="batches in flight: consecutive steps alternate between this many contexts/streams, so the serial "
                          "acquisition tail of one batch overlaps the bulk kernels of the next (1 = strictly one batch at a time; "
-                         "0 = 4, or 3 for runs of fewer than 8 steps where the ramp-up of a fourth batch costs more than it brings)")
+                         "0 = 8 for runs of 16 steps or more, 4 from 8 steps, else 3: ramp-up and drain are inside the timed region)")
     ap.add_argument("--cpu-captures", type=int, default=0)
     ap.add_argument("--ref-captures", type=int, default=0)
     ap.add_argument("--ref-samples", type=int, default=1_000_000)
@@ -744,7 +744,9 @@ def main():
         return ms / steps, launches, clocks, per_rank
 
     # batches in flight: context k (own workspaces, own internal streams) on side stream k; joined to the main stream at the end
-    inflight = args.inflight if args.inflight > 0 else (4 if args.steps >= 8 else 3)
+    # default 8 contexts with ONE capture group each (two internal streams per context: 8 x 3 streams stay inside the 32
+    # hardware work queues): r02l — 4 x 3 groups 33.0 ms/step, 8 x 1 group 30.6 ms/step
+    inflight = args.inflight if args.inflight > 0 else (8 if args.steps >= 16 else (4 if args.steps >= 8 else 3))
     inflight = max(1, min(inflight, max(args.steps, 1)))
     groups = args.groups if args.groups >= 0 else (0 if inflight <= 4 else 1)
     rot = Rotation(C_, inflight, groups=groups)

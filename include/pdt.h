@@ -74,7 +74,18 @@ typedef struct pdt_params {
     uint32_t agc_min_tile;       /* tiled engine: smallest AGC tile in interpolated samples (0 = default) */
     uint32_t acq_first;          /* tiled engine: samples covered by the first acquisition pass; captures that have not
                                     latched by then continue on a second stream (0 = default 131072) */
+    /* stages the reference exports next to the path but calls from neither driver */
+    int      sync_generic;       /* 1: the parameterised sync of common/ByteSync.c:16-144 instead of the application copy:
+                                    a frame ends when its byte index exceeds sync_frame_len, bitIdx = sync_start_bit after a
+                                    sync word ("3 for POES, 0 for ARGOS", :135), inverse search on, literal ED E2 in front */
+    int      sync_frame_len, sync_start_bit;   /* frameLength (<= 103), startBit (0…7) */
+    int      clock_recovery;     /* PDT_CLOCK_GARDNER (default) | PDT_CLOCK_MM: common/MMClockRecovery.c:5-84 in place of the
+                                    Gardner loop (the call both drivers keep commented out: POESTIPdemod/main.c:435,
+                                    ARGOSdemod/main.c:277).  Runs on the exact engine. */
+    double   mm_step_range, mm_gain;           /* stepRange, kp of MMClockRecovery (the commented call sites pass 3, 0.15) */
 } pdt_params;
+#define PDT_CLOCK_GARDNER 0
+#define PDT_CLOCK_MM      1
 
 /* One decoded minor frame (POES, 104 bytes incl. the literal ED E2) or packet (ARGOS, 7 bytes). */
 typedef struct pdt_frame {

@@ -441,11 +441,14 @@ void pdto_bytesync_free(pdto_bytesync *s) { free(s->text); s->text = NULL; s->te
 
 /* frame_last_idx: 103 for the 104-byte TIP minor frame, 8 for ARGOS; poes selects the literal ED E2
  * prefix, the 3-bit carry-in (19-bit sync = 2 bytes + 3 bits) and the enabled inverse search. */
-static int bytesync_core(pdto_bytesync *s, const unsigned char *bits, const pdto_real *time, unsigned long n,
-                         const char *sync, unsigned int len, int poes)
+/* `poes`: 1 = POESTIPdemod/ByteSync.c, 0 = ARGOSdemod/ByteSync.c, 2 = the parameterised common/ByteSync.c:16-144
+ * (frame ends when frameByteIdx > frameLength, bitIdx = startBit after a sync word, inverse search on, literal ED E2). */
+static int bytesync_core_ex(pdto_bytesync *s, const unsigned char *bits, const pdto_real *time, unsigned long n,
+                            const char *sync, unsigned int len, int poes, int frame_len, int start_bit)
 {
     int found = 0;
-    const int last_idx = poes ? 103 : 8;
+    const int last_idx = poes == 2 ? frame_len : (poes ? 103 : 8);
+    const int carry = poes == 2 ? start_bit : (poes ? 3 : 0);
     if (!s->init) { s->init = 1; memset(s->hist, 48, len); }
     for (unsigned long i = 0; i < n; i++) {
         if (s->in_frame == 1) {                               /* shift payload bits into bytes (:45-72) */
@@ -470,18 +473,26 @@ static int bytesync_core(pdto_bytesync *s, const unsigned char *bits, const pdto
             sink_printf(s, "%.5f ", t, 0);
             if (poes) { sink_printf(s, "%.2X ", 0xED, 1); sink_printf(s, "%.2X ", 0xE2, 1); }
             s->frame_byte_idx = 2; s->in_frame = 1; found++;
-            s->bit_idx = poes ? 3 : 0; s->byte = 0; s->zero = 0; s->one = 1;
+            s->bit_idx = carry; s->byte = 0; s->zero = 0; s->one = 1;
         }
         if (hit_inv && s->in_frame == 0) {                    /* :127-144 */
             sink_printf(s, "%.5fi ", t, 0);
             if (poes) { sink_printf(s, "%.2X ", 0xED, 1); sink_printf(s, "%.2X ", 0xE2, 1); }
             s->frame_byte_idx = 2; s->in_frame = 1; found++;
-            s->bit_idx = poes ? 3 : 0; s->byte = 0; s->zero = 1; s->one = 0;
+            s->bit_idx = carry; s->byte = 0; s->zero = 1; s->one = 0;
         }
         s->oldest = (s->oldest + 1) % (int)len;
     }
     return found;
 }
+
+static int bytesync_core(pdto_bytesync *s, const unsigned char *bits, const pdto_real *time, unsigned long n,
+                         const char *sync, unsigned int len, int poes)
+{ return bytesync_core_ex(s, bits, time, n, sync, len, poes, 0, 0); }
+
+int pdto_bytesync_generic_run(pdto_bytesync *s, const unsigned char *bits, const pdto_real *time, unsigned long n,
+                              const char *sync, unsigned int len, int frame_len, int start_bit)
+{ return bytesync_core_ex(s, bits, time, n, sync, len, 2, frame_len, start_bit); }
 
 int pdto_bytesync_poes_run(pdto_bytesync *s, const unsigned char *bits, const pdto_real *time, unsigned long n,
                            const char *sync, unsigned int len)

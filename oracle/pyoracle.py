@@ -100,6 +100,8 @@ class Oracle:
         L.pdto_manchester_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_ulong, C.c_void_p, R]
         L.pdto_bytesync_reset.argtypes = [C.c_void_p]
         L.pdto_bytesync_free.argtypes = [C.c_void_p]
+        L.pdto_bytesync_generic_run.restype = C.c_int
+        L.pdto_bytesync_generic_run.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_ulong, C.c_char_p, C.c_uint, C.c_int, C.c_int]
         for f in (L.pdto_bytesync_poes_run, L.pdto_bytesync_argos_run):
             f.restype = C.c_int
             f.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_ulong, C.c_char_p, C.c_uint]
@@ -201,6 +203,12 @@ class Oracle:
         f = self.lib.pdto_bytesync_poes_run if kind == "poes" else self.lib.pdto_bytesync_argos_run
         sync = POES_SYNC if kind == "poes" else ARGOS_SYNC
         return f(st.p, _ptr(bits), _ptr(time), bits.size, sync, len(sync))
+
+    def bytesync_generic(self, st, bits, sync: bytes, frame_len: int, start_bit: int, time=None):
+        """common/ByteSync.c:16-144 — the parameterised variant (frameLength / startBit)."""
+        bits = np.ascontiguousarray(bits, np.uint8)
+        t = None if time is None else np.ascontiguousarray(time, self.dt)
+        return self.lib.pdto_bytesync_generic_run(st.p, _ptr(bits), _ptr(t), bits.size, sync, len(sync), frame_len, start_bit)
 
     def bytesync_text(self, st) -> str:
         # layout-independent accessor: text pointer/len live at the tail of pdto_bytesync; use the chain
@@ -560,9 +568,6 @@ def ref_chain_poes(iq, fs, chunk=10000, out_path=None):
     return frames
 
 
-ARGOS_SYNC = b"0001011110000"
-
-
 def ref_chain_argos(iq, fs, chunk=2400, out_path=None):
     """The reference's ARGOS per-chunk loop (ARGOSdemod/main.c:250-300) driven through the UNMODIFIED double-precision
     reference library with preallocated buffers (bench.py --mode argos CPU arm).  Fresh static state per call.  Returns
@@ -600,3 +605,30 @@ def ref_chain_argos(iq, fs, chunk=2400, out_path=None):
         pos += m
     r.libc.fclose(fp)
     return packets
+
+
+def ref_bytesync_generic(chunks, sync: bytes, frame_len: int, start_bit: int) -> str:
+    """common/ByteSync.c:16-144 compiled alone (oracle/_ref/libref_bytesync_generic.so; neither application links it): feed
+    the bit chunks [(bits uint8, time float64), …] through a private copy and return the text it wrote."""
+    src = os.path.join(REF_DIR, "libref_bytesync_generic.so")
+    tmp = tempfile.mkdtemp(prefix="pdtbsg_")
+    try:
+        path = os.path.join(tmp, "bsg.so")
+        shutil.copy(src, path)
+        lib = C.CDLL(path)
+        libc = C.CDLL(None)
+        libc.fopen.restype = C.c_void_p
+        libc.fopen.argtypes = [C.c_char_p, C.c_char_p]
+        libc.fclose.argtypes = [C.c_void_p]
+        lib.ByteSyncOnSyncword.restype = C.c_int
+        lib.ByteSyncOnSyncword.argtypes = [C.c_void_p, C.c_void_p, C.c_ulong, C.c_char_p, C.c_uint, C.c_int, C.c_int, C.c_void_p]
+        out = os.path.join(tmp, "out.txt")
+        fp = libc.fopen(out.encode(), b"w")
+        for bits, time in chunks:
+            bits = np.ascontiguousarray(bits, np.uint8)
+            time = np.ascontiguousarray(time, np.float64)
+            lib.ByteSyncOnSyncword(_ptr(bits), _ptr(time), bits.size, sync, len(sync), frame_len, start_bit, fp)
+        libc.fclose(fp)
+        return open(out).read()
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)

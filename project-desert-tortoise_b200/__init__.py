@@ -25,6 +25,7 @@ ROOT = os.path.dirname(HERE)
 
 PDT_MODE_POES, PDT_MODE_ARGOS = 0, 1
 PDT_ENGINE_AUTO, PDT_ENGINE_EXACT, PDT_ENGINE_TILED = 0, 1, 2
+PDT_CLOCK_GARDNER, PDT_CLOCK_MM = 0, 1
 FRAME_MAX = 104
 
 
@@ -41,7 +42,8 @@ class Params(C.Structure):
                 ("gardner_gain", C.c_double), ("manchester_resync", C.c_double), ("squelch_thresh", C.c_double),
                 ("norm_factor", C.c_double), ("sync_word", C.c_char * 32), ("sync_len", C.c_int),
                 ("engine", C.c_int), ("pll_warm", C.c_uint32), ("pll_tile", C.c_uint32), ("agc_min_tile", C.c_uint32),
-                ("acq_first", C.c_uint32)]
+                ("acq_first", C.c_uint32), ("sync_generic", C.c_int), ("sync_frame_len", C.c_int), ("sync_start_bit", C.c_int),
+                ("clock_recovery", C.c_int), ("mm_step_range", C.c_double), ("mm_gain", C.c_double)]
 
 
 class Frame(C.Structure):

@@ -108,6 +108,15 @@ int build_chain_const(const pdt_params &p, ChainConst &cc)
     cc.sync.carry_bits = cc.argos ? 0 : 3;
     cc.sync.inverse_enabled = cc.argos ? 0 : 1;
     cc.prefix_bytes = cc.argos ? 0 : 2;
+    if (p.sync_generic) {                                            // common/ByteSync.c:16-144
+        if (p.sync_frame_len < 2 || p.sync_frame_len > PDT_FRAME_MAX_BYTES - 1 || p.sync_start_bit < 0 || p.sync_start_bit > 7)
+            return fail(PDT_EINVAL, "generic sync: frame length %d / start bit %d out of range", p.sync_frame_len, p.sync_start_bit);
+        cc.sync.last_idx = p.sync_frame_len; cc.sync.carry_bits = p.sync_start_bit;
+        cc.sync.inverse_enabled = 1; cc.prefix_bytes = 2;
+    }
+    cc.use_mm = (p.clock_recovery == PDT_CLOCK_MM);
+    cc.mm_range = p.mm_step_range; cc.mm_kp = p.mm_gain;
+    if (cc.use_mm && !(p.baud - p.mm_step_range > 0)) return fail(PDT_EINVAL, "M&M step range %g >= baud", p.mm_step_range);
     cc.ypad = 16 + 4 * (int)((double)cc.gardner_fs / p.baud / 4.0 + 1.0);
     return PDT_OK;
 }
@@ -187,6 +196,7 @@ static FrontKernel front_kernel(int L)          // one instantiation per interpo
 static bool tiled_applicable(const pdt_params &p, const ChainConst &cc, uint32_t max_captures)
 {
     if (cc.argos || cc.L < 1 || cc.L > tiled::FIR_MAX_L || cc.N != tiled::FIR_K * cc.L) return false;
+    if (cc.use_mm) return false;                                         // the M&M loop lives in the exact engine
     if (max_captures > 65535u) return false;
     if ((double)cc.chunk * cc.L > 1e9) return false;
     // one 2π wrap per sample must suffice (pdt_tiled.cuh::pll_track_step): |Δphase| <= max_freq + (alpha+beta)·3π < 2π
@@ -598,6 +608,8 @@ int pdt_params_default(pdt_params *p, int mode, double sample_rate)
         p->gardner_err_lim = 0.1; p->gardner_gain = 3.0;
         p->manchester_resync = 1.0;                   // main.c:445 passes the literal, not DSP_MCHSTR_RESYNC_LVL
         strcpy(p->sync_word, "1110110111100010000"); p->sync_len = 19;
+        p->sync_frame_len = 103; p->sync_start_bit = 3;   // what sync_generic = 1 would need to equal the application copy
+        p->mm_step_range = 3; p->mm_gain = 0.15;          // main.c:435 (commented call)
     } else if (mode == PDT_MODE_ARGOS) {              // ARGOSdemod/main.c:27-65
         p->chunk = 2400;
         p->interp = 1; p->taps = 50;
@@ -611,6 +623,8 @@ int pdt_params_default(pdt_params *p, int mode, double sample_rate)
         p->manchester_resync = 0.5;
         p->squelch_thresh = 0.15;
         strcpy(p->sync_word, "0001011110000"); p->sync_len = 13;
+        p->sync_frame_len = 8; p->sync_start_bit = 0;
+        p->mm_step_range = 3; p->mm_gain = 0.15;          // ARGOSdemod/main.c:277 (commented call)
     } else return fail(PDT_EINVAL, "unknown mode %d", mode);
     return PDT_OK;
 }

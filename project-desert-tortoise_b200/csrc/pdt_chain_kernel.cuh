@@ -17,6 +17,7 @@ struct ChainState {
     PllState        pll;
     AgcState        agc;
     GardnerState    gar;
+    MMState         mm;
     ManchesterState man;
     SyncState       sync;
     real_t          norm;
@@ -223,6 +224,22 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_chain_exact(const ChainArgs a
                 }
                 gardner_begin(st.gar, cc.gardner_fs, cc.baud);
                 const unsigned long long ibase = base * (unsigned long long)cc.L;
+                if (cc.use_mm) {
+                    // MMClockRecovery.c:5-84 in the Gardner loop's place (the call the drivers keep commented out)
+                    mm_begin(st.mm, cc.gardner_fs, cc.baud);
+                    const real_t step_max = cc.gardner_fs / (cc.baud - cc.mm_range), step_min = cc.gardner_fs / (cc.baud + cc.mm_range);
+                    while (mm_rint(st.mm.next) < n_out) {
+                        real_t sym;
+                        const unsigned at = mm_step(st.mm, Y, step_min, step_max, cc.mm_kp, sym);
+                        if (tr && st.n_sym < tr->cap) {
+                            if (tr->sym)         reinterpret_cast<real_t *>(tr->sym)[st.n_sym] = sym;
+                            if (tr->gardner_idx) tr->gardner_idx[st.n_sym] = ibase + at;
+                        }
+                        st.n_sym++;
+                        consume_symbol(st, cc, sym, ibase + at, frames, tr);
+                    }
+                    st.mm.next = st.mm.next - n_out;                             // :80
+                } else
                 while (r_rint(st.gar.next) < n_out) {
                     real_t sym, err;
                     const unsigned at = gardner_step(st.gar, Y, cc.g_range, cc.g_kp, sym, err);
@@ -234,7 +251,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_chain_exact(const ChainArgs a
                     st.n_sym++;
                     consume_symbol(st, cc, sym, ibase + at, frames, tr);
                 }
-                st.gar.next = st.gar.next - n_out;                               // :111
+                if (!cc.use_mm) st.gar.next = st.gar.next - n_out;               // :111
             }
             __syncthreads();
         }

@@ -364,6 +364,33 @@ PDT_DEV unsigned gardner_step(GardnerState &s, const real_t *x, real_t range, re
     return at;
 }
 
+// Mueller & Müller — MMClockRecovery.c:5-84 (exported by the reference; its call is commented out in both drivers)
+struct MMState { int init; real_t step, next, last; };
+
+PDT_DEV real_t mm_rint(real_t v)
+{
+#if PDT_USE_FLOATS
+    return rintf(v);                       // <tgmath.h> rint() of a float (:23,:26)
+#else
+    return (real_t)rintf((float)v);        // the double build rounds through rintf (:53,:56) — kept
+#endif
+}
+PDT_DEV void mm_begin(MMState &s, int Fs, real_t baud) { if (!s.init) { s.step = Fs / (baud); s.init = 1; } }
+// one symbol at the current position (the caller checks mm_rint(next) < n first); returns the picked index
+PDT_DEV unsigned mm_step(MMState &s, const real_t *x, real_t step_min, real_t step_max, real_t kp, real_t &sym)
+{
+    const unsigned at = (unsigned)(mm_rint(s.next));
+    const real_t cur = x[at];
+    const real_t err = sign_of(s.last) * cur - sign_of(cur) * s.last;          // :35
+    s.step = s.step + kp * err;
+    if (s.step > step_max) s.step = step_max;
+    if (s.step < step_min) s.step = step_min;
+    s.next = s.next + s.step;
+    s.last = cur;
+    sym = cur;
+    return at;
+}
+
 // one symbol; returns 1 and sets `bit` ('0'/'1') when a bit is produced
 PDT_DEV int manchester_step(ManchesterState &s, real_t v, real_t thresh, unsigned char &bit)
 {

@@ -17,8 +17,6 @@ using namespace pdt;
 
 namespace {
 
-struct MMState { int init; real_t step, next, last; };
-
 struct LegacyState {
     PllState pll; AgcState agc; GardnerState gar; MMState mm; ManchesterState man; SyncState sync;
     int agcc_init; real_t agcc_gain; real_t amp_avg;
@@ -210,25 +208,13 @@ __global__ void k_leg_mm(LegacyState *s, const real_t *x, unsigned long long n, 
     // MMClockRecovery.c:5-84 (exported, not called by the drivers)
     MMState st = s->mm;
     const real_t step_max = Fs / (baud - range), step_min = Fs / (baud + range);
-    if (!st.init) { st.step = Fs / (baud); st.init = 1; }
+    mm_begin(st, Fs, baud);
     unsigned long long count = 0;
-#if PDT_USE_FLOATS
-#define MM_RINT(v) rintf(v)
-#else
-#define MM_RINT(v) rintf((float)(v))      // the double build rounds through rintf (:55) — kept
-#endif
-    while (MM_RINT(st.next) < n) {
-        const unsigned at = (unsigned)(MM_RINT(st.next));
-        const real_t cur = x[at];
-        out[count] = cur; idx[count] = at; count++;
-        real_t err = sign_of(st.last) * cur - sign_of(cur) * st.last;
-        st.step = st.step + kp * err;
-        if (st.step > step_max) st.step = step_max;
-        if (st.step < step_min) st.step = step_min;
-        st.next = st.next + st.step;
-        st.last = cur;
+    while (mm_rint(st.next) < n) {
+        real_t sym;
+        const unsigned at = mm_step(st, x, step_min, step_max, kp, sym);
+        out[count] = sym; idx[count] = at; count++;
     }
-#undef MM_RINT
     st.next = st.next - n;
     s->mm = st; s->count = count;
 }

@@ -202,11 +202,15 @@ __global__ void __launch_bounds__(256) k_sp(const TiledArgs a)
 // the booleans are compared; on the first difference the block restarts from that sample with the corrected
 // flag.  The committed trajectory is exactly the serial one.
 // ---------------------------------------------------------------------------------------------------
+// Geometry (r02i/r02l measurements, profiles/README.md): 128-sample blocks and 128-thread CTAs in both passes.  The step's
+// fixed cost weighs a little more than with 256-sample blocks, but a CTA holds 21 KB of shared memory and 7 K registers
+// instead of 44 KB / 12.5 K — acquisition CTAs sit on their SM for milliseconds (the slow ones for 60 ms), and what they
+// hold is what the other batches in flight cannot use.
 #ifndef PDT_ACQ_B
-#define PDT_ACQ_B 256
+#define PDT_ACQ_B 128
 #endif
 #ifndef PDT_ACQ_THREADS
-#define PDT_ACQ_THREADS 224
+#define PDT_ACQ_THREADS 128
 #endif
 constexpr int ACQ_B = PDT_ACQ_B;      // samples per pipeline block
 constexpr int ACQ_RING = 4;           // blocks in flight: core | terms | EMAs | decisions
@@ -695,7 +699,7 @@ __global__ void __launch_bounds__(EST_WARPS * 32) k_prelock(const TiledArgs a)
 // PLL track core: lane per (capture, tile), a warp = 32 consecutive tiles of one capture, streams moved by the TMA
 // ---------------------------------------------------------------------------------------------------
 #ifndef PDT_LS_WARPS
-#define PDT_LS_WARPS 2
+#define PDT_LS_WARPS 4                                    // (2 -> 4: k_pll_core 13.8 -> 9.9 ms on the whole batch, r02h)
 #endif
 constexpr int LS_WARPS = PDT_LS_WARPS;                    // warps per CTA of the lane-stream kernels
 constexpr size_t LS_SMEM = LS_WARPS * sizeof(LaneStreamSmem);

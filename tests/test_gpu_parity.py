@@ -626,6 +626,72 @@ def test_l0_reference_emits_nothing_and_declared_deviation(torch_cuda, oracle32)
     assert (st[0]["n_symbols"], st[0]["n_bits"], st[0]["n_frames"]) == (want["total_symbols"], want["total_bits"], want["total_frames"])
 
 
+@pytest.mark.parametrize("engine", ["exact", "tiled"])
+@pytest.mark.parametrize("frame_len,start_bit", [(103, 3), (40, 5), (8, 0)])
+def test_generic_bytesync_on_the_batch_api(torch_cuda, oracle32, engine, frame_len, start_bit):
+    """the parameterised sync of common/ByteSync.c:16-144 (frameLength / startBit) as batch parameters, both
+    engines, against its restatement (pinned to the reference file in tests/test_oracle_vs_ref.py) fed with the oracle's bits."""
+    fs = 250000
+    pcm, _ = make_poes_capture(600_000, fs, 71, esn0_db=15.0, doppler_hz=-1200.0, amplitude=0.25)
+    want = oracle32.chain(oracle32.pcm16_to_complex(pcm), fs, trace=True)
+    st_o = oracle32.new_state("bytesync")
+    n_sync = oracle32.bytesync_generic(st_o, want["tr_bits"], b"1110110111100010000", frame_len, start_bit)
+    rows = [(r[1], bytes(r[2])) for r in parse_frames_text(oracle32.bytesync_text(st_o))]
+    assert n_sync >= 20
+    p = pdt.default_params("f32", pdt.PDT_MODE_POES, fs)
+    p.engine = ENGINES[engine]
+    p.sync_generic, p.sync_frame_len, p.sync_start_bit = 1, frame_len, start_bit
+    d = pdt.Demod("f32", p, 1, pcm.size // 2, 256)
+    st, fr = d.demod_host(pcm, 1, pcm16=True)
+    assert int(st[0]["n_frames"]) == n_sync and int(st[0]["n_bits"]) == want["total_bits"]
+    got = [(bool(f["inverse"]), bytes(f["bytes"][: f["n_bytes"]])) for f in fr[0][:n_sync]]
+    assert got == rows
+    assert all(len(b) == frame_len + 1 for _, b in got[:-1])
+
+
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+def test_mm_clock_recovery_on_the_batch_api(torch_cuda, prec):
+    """MMClockRecovery (common/MMClockRecovery.c:5-84 — the call both drivers keep commented out,
+    POESTIPdemod/main.c:435 / ARGOSdemod/main.c:277) selected on the batch API, against the oracle's stages composed in the
+    driver's order: AGC (+squelch) output of the oracle chain -> mm per chunk -> Manchester -> ByteSync."""
+    o = po.Oracle(prec)
+    if prec == "f32":
+        fs, mode, argos, thr = 250000, pdt.PDT_MODE_POES, False, 1.0
+        pcm, _ = make_poes_capture(400_000, fs, 72, esn0_db=16.0, doppler_hz=600.0, amplitude=0.25)
+        iq = o.pcm16_to_complex(pcm)
+        baud, chunk = 8320 * 2 + 0.3, 10000
+    else:
+        fs, mode, argos, thr = 5000, pdt.PDT_MODE_ARGOS, True, 0.5
+        pcm, _ = make_argos_capture(60000, 5000.0, seed=9, n_bursts=3, snr_db=20.0)
+        iq = o.pcm16_to_complex(pcm)
+        baud, chunk = 800.0, 2400
+    want = o.chain(iq, fs, argos=argos, trace=True)
+    L = max(want["L"], 1)
+    z = want["tr_agc"]                                                    # AGC (ARGOS: + squelch) output, per interpolated sample
+    mst, manst, bst = o.new_state("mm"), o.new_state("manchester"), o.new_state("bytesync")
+    syms, n_frames = [], 0
+    for base in range(0, z.size, chunk * L):
+        m = min(chunk * L, z.size - base)
+        buf = np.zeros(m + 16, o.dt)
+        buf[:m] = z[base: base + m]
+        s_ = o.mm(mst, buf, m, int(np.float32(fs) * L) if prec == "f32" else int(fs), baud, 3.0, 0.15)
+        syms.append(s_)
+        bits = o.manchester(manst, s_, thr)
+        n_frames += o.bytesync(bst, bits, kind="argos" if argos else "poes")
+    syms = np.concatenate(syms)
+    rows = [(r[1], bytes(r[2])) for r in parse_frames_text(o.bytesync_text(bst))]
+    p = pdt.default_params(prec, mode, fs)
+    p.clock_recovery = pdt.PDT_CLOCK_MM
+    d = pdt.Demod(prec, p, 1, iq.size // 2, 64)
+    assert d.engine == pdt.PDT_ENGINE_EXACT
+    st, fr = d.demod_host(iq, 1)
+    assert int(st[0]["n_symbols"]) == syms.size and int(st[0]["n_frames"]) == n_frames
+    got = [(bool(f["inverse"]), bytes(f["bytes"][: f["n_bytes"]])) for f in fr[0][: min(n_frames, 64)]]
+    assert got == rows[: len(got)]
+    if prec == "f32":
+        assert n_frames >= 10
+
+
 def test_argos_synthetic_bursts(torch_cuda, oracle64):
     pcm, info = make_argos_capture(120000, 5000.0, seed=5, n_bursts=6, snr_db=18.0)
     iq = oracle64.pcm16_to_complex(pcm)

@@ -3,6 +3,8 @@
 Runs only where oracle/_ref exists (the build container, or the GPU box when the prebuilt files travelled).
 Every comparison is bit-exact: same inputs, same chunking, np.array_equal on the outputs.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -184,3 +186,25 @@ def test_declared_deviation_oracle_equals_patched_reference(tmp_path):
     assert res["locked"] and res["total_frames"] >= 45
     assert res["text"] == txt
     assert f"PLL locked at {res['lock_freq_hz']:.2f}Hz" in so.replace(" Hz", "Hz") or "PLL locked" in so
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(po.REF_DIR, "libref_bytesync_generic.so")), reason="oracle/_ref not built")
+@pytest.mark.parametrize("frame_len,start_bit,sync", [(103, 3, b"1110110111100010000"), (8, 0, b"0001011110000"), (20, 5, b"11100010010")])
+def test_generic_bytesync_vs_common_bytesync_c(frame_len, start_bit, sync):
+    """The parameterised sync of common/ByteSync.c:16-144 (frameLength / startBit; the README's "unify POES and ARGOS"
+    TODO — compiled by neither application) against its restatement, on a random bit stream with planted upright and
+    inverted sync words, fed in ragged chunks."""
+    rng = np.random.default_rng(frame_len)
+    bits = rng.integers(0, 2, 60000).astype(np.uint8) + 48
+    word = np.frombuffer(sync, np.uint8)
+    for k, at in enumerate(range(500, 59000, 1700)):
+        bits[at: at + word.size] = word if k % 3 else (97 - word)          # every third one inverted ('0' <-> '1')
+    time = np.arange(bits.size, dtype=np.float64) * 1e-3
+    cuts = [0, 1, 700, 701, 20000, 20013, bits.size]
+    chunks = [(bits[a:b], time[a:b]) for a, b in zip(cuts, cuts[1:])]
+    want = po.ref_bytesync_generic(chunks, sync, frame_len, start_bit)
+    o = po.Oracle("f64")
+    st = o.new_state("bytesync")
+    n = sum(o.bytesync_generic(st, b, sync, frame_len, start_bit, time=t) for b, t in chunks)
+    got = o.bytesync_text(st)
+    assert got == want and n == want.count(".") and n > 20 and "i " in want

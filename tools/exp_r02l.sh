@@ -1,4 +1,5 @@
 mkdir -p gpurun_out
+python -m pytest tests -m gpu -q 2>&1 | tail -6
 B="python bench.py --no-e2e --no-cpu --no-single --steps 20"
 run() { name=$1; shift; env $ENVV $B "$@" > gpurun_out/r02l_$name.json 2> gpurun_out/r02l_$name.err; python - <<PY
 import json
