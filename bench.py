@@ -41,6 +41,12 @@ import numpy as np
 # Each batch in flight uses up to 7 internal streams; beyond the default 8 hardware work queues streams alias and a launch
 # waiting behind a long kernel blocks unrelated streams.  Must be set before CUDA initialises.
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+# The only collective is the all-gather of a few MB of decoded frames per step.  NCCL's default 16+ channels put as many
+# 512-thread CTAs on the SMs of every rank, and a fast rank's gather kernel spins there until the slowest rank arrives:
+# measured on 8 GPUs (profiles/r02m_n8_*), the default cost 3.2 ms of a 32.5 ms step.  One channel moves the 47 MB in a
+# millisecond, off the critical path (the gather runs on its own stream).
+os.environ.setdefault("NCCL_MAX_NCHANNELS", "1")
+os.environ.setdefault("NCCL_MIN_NCHANNELS", "1")
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 for _p in (ROOT, os.path.join(ROOT, "oracle")):
@@ -235,6 +241,9 @@ def stream_bench(args):
     params = pdt.default_params("f32", pdt.PDT_MODE_POES, FS)
     if FS > 300000:
         params.force_min_interp1 = 1          # declared deviation: the reference rule gives L = 0 there and emits nothing
+    if args.pll_tile_frac > 0:                # shorter PLL tiles: more lanes and a shorter serial chain per tile, more warm-up work
+        w = 17.0 / (params.pll_track_gain * 2.0 * np.pi / FS)
+        params.pll_tile = max(1024, int(w * args.pll_tile_frac) // 4 * 4)
     segment = args.segment if args.segment else int(2.0 * FS)
     plan = sm.make_plan("f32", params, total, segment)
     first, cnt = pdist.shard_range(plan.n_segments, rank, world)
@@ -329,6 +338,7 @@ def stream_bench(args):
                                f"value counts STREAM samples (the {processed / total:.2f}x overlap is overhead, not throughput)",
                    "sample_rate": FS, "interp": sds[0].demod.params.interp, "input": "pcm16" if args.pcm16 else "cf32",
                    "segments_per_gpu": cnt, "samples_processed_incl_overlap": processed, "batches_in_flight": inflight,
+                   "pll_tile": int(params.pll_tile) or "W",
                    "l2": f"stream slice {sd.n_slice * bytes_per_sample / 1e9:.2f} GB per GPU, far larger than the 126 MB L2"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": chain_gbps, "peak": peak, "unit": "GB/s", "frac": chain_gbps / peak, "traffic": None,
@@ -585,6 +595,8 @@ def main():
                                                           "overlapping segments over the GPUs (strong scaling); not the default bench")
     ap.add_argument("--segment", type=int, default=0, help="--stream: samples owned per segment (default 2 s of signal)")
     ap.add_argument("--pcm16", action="store_true", help="feed int16 PCM (4 B/sample) instead of cf32")
+    ap.add_argument("--pll-tile-frac", type=float, default=0.0, help="--stream: PLL tile length as a fraction of the warm-up length "
+                                                                     "(default 1: T = W)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-single", action="store_true")
@@ -792,6 +804,10 @@ def main():
         d.set_profiling(False)
         kernels = sorted(acc.items(), key=lambda kv: -kv[1])
         counters = d.tiled_counters(stream)
+        if not kernels:        # timing-experiment knobs (PDT_DEBUG_*) can leave a batch without profiled kernels
+            print(json.dumps({"experiment": True, "value": value, "ms_per_step": ms_step, "batches_in_flight": inflight,
+                              "check": {"frames_decoded": None}}))
+            return 0
     else:
         kt = []
         for _ in range(min(args.steps, 5)):

@@ -61,7 +61,9 @@ __device__ __forceinline__ u64 ls_shfl64(u64 v, int src)
 // All 32 lanes of the warp must call this together; s1 - s0 < 2^32.
 //   Step:  void quad(const float4 &v, float4 &o);   float one(float v);
 // STORE = false: a pure warm-up (sb == s1), no output row is written at all.
-template <bool STORE, class Step>
+// HOOK = true: after every COMPLETE 64-sample round c of this lane, step.round_done(c) is called (checkpoints of the loop
+// state at fixed positions of the tile, see k_pll_core) — no extra pass, no pipeline drain.
+template <bool STORE, class Step, bool HOOK = false>
 __device__ __forceinline__ void lane_stream(LaneStream &h, const int lane, const float *__restrict__ in, float *__restrict__ out,
                                             const u64 s0, const u64 sb, const u64 s1, Step &step)
 {
@@ -120,6 +122,7 @@ __device__ __forceinline__ void lane_stream(LaneStream &h, const int lane, const
                     if (STORE) st4(orow + j, o);
                     v = vn;
                 }
+                if constexpr (HOOK) step.round_done(c);
             } else {
                 for (; j + 4 <= cnt; j += 4) { const float4 v = ld4(ir + j); float4 o; step.quad(v, o); if (STORE) st4(orow + j, o); }
                 for (; j < cnt; j++) { const float o = step.one(ir[j]); if (STORE) orow[j] = o; }

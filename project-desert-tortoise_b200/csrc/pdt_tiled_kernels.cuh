@@ -34,6 +34,8 @@ struct TiledArgs {
     float      *z;           // [captures][stride·L]    AGC output
     AcqResult  *acq;         // [captures]
     LoopState2 *guess, *pll_start, *pll_end;     // [captures][pll.max_tiles]
+    LoopState2 *pll_ckpt;    // [captures][pll.max_tiles][pll_nck]  PLL state at tile begin + j·PLL_CK (j >= 1) of the stored run
+    unsigned    pll_nck;
     LoopState2 *agc_start, *agc_end;             // [captures][agc_max_tiles]
     uint32_t   *counters;    // [0] PLL tiles re-run, [1] AGC tiles re-run, [2] acquisition flag restarts
     TilePlan    pll;         // in input samples
@@ -44,6 +46,7 @@ struct TiledArgs {
     int         slow_pass;   // 0: kernels process the captures that latched in the first pass, 1: the slow ones
     uint32_t    prelock_from;// captures >= this index skip the acquisition sweep and start in track mode from a carrier
                              // estimate (k_prelock): segments of one stream behind the first (pdt_demod_segments_device)
+    uint32_t   *slow_list, *slow_count;  // captures the second acquisition pass continues (k_slow_list -> k_acquire_packed)
     LaneTask   *pll_tasks, *agc_tasks;   // compact work lists of the persistent lane-stream kernels (built on the device)
     uint32_t   *task_counts; // [0] PLL tasks, [1] AGC tasks
     unsigned    pll_tasks_per_cap, agc_tasks_per_cap;
@@ -533,6 +536,345 @@ __global__ void __launch_bounds__(ACQ_THREADS) k_acquire(const TiledArgs a, cons
 }
 
 // ---------------------------------------------------------------------------------------------------
+// k_acquire_packed — the same acquisition (same arithmetic, same speculation, same committed trajectory) with the serial
+// chains of 32 captures packed into the lanes of ONE warp each.
+//
+// k_acquire gives every capture a CTA in which three lanes do serial work (the core recurrence and the two EMAs): a warp
+// instruction is issued for one useful lane, 5.4 G warp instructions per 1024 x 1 M batch, and 1024 (first pass) or ~90
+// long-lived (second pass, 55 ms) CTAs hold registers and shared memory that the other kernels in flight cannot use —
+// together ~15 ms of every 31 ms step (profiles/README.md, r02e-r02p).  Here a CTA serves AQ = 32 captures:
+//     warp 0   lane q = core recurrence [B]+[C] of capture q          (sweep flag by select: the lanes stay in lock-step)
+//     warp 1   lane q = EMA of |output phase| of capture q   (:124)
+//     warp 2   lane q = EMA of the lock detector of capture q (:220)
+//     warps 3+ helpers: feed-forward terms (sincos, derotation, approx-atan2, Q_rsqrt), decisions, loads, commits — a warp
+//              takes one capture's block at a time (lane = sample), so shared and global accesses are contiguous
+// over AB = 32-sample blocks in a three-stage pipeline (core | terms | EMAs + decisions: the EMA lanes leave every sample's
+// sweep / latch decision as a bit, the verdict on a block is integer work for one control warp in the same step), every
+// capture with its own epoch origin and step counter: a wrong sweep flag restarts THAT capture at the offending sample
+// while the others go on.
+// Rows of different captures are 129 / 133 floats apart, so the 32 serial lanes hit 32 different banks.
+// The first pass needs ceil(captures / 32) CTAs (32 SMs for a 1024-capture batch), the second pass three.
+// ---------------------------------------------------------------------------------------------------
+constexpr int AQ = 32;                  // captures per CTA
+constexpr int AB = 32;                  // samples per block
+constexpr int AR = 4;                   // ring slots (blocks in flight per capture)
+constexpr int AP_SERIAL = 96;           // three serial warps
+constexpr int AP_THREADS = 512;         // + thirteen helper warps (a helper warp serves at most AP_HCAPS captures per step)
+constexpr int AP_HCAPS = (AQ + (AP_THREADS - AP_SERIAL) / 32 - 1) / ((AP_THREADS - AP_SERIAL) / 32);
+constexpr int AP_RS = AR * AB + 1;      // row stride of the [slot][sample] arrays (129: one bank further per capture)
+constexpr int AP_RS1 = AR * (AB + 1) + 1;   // row stride of the [slot][sample + 1] arrays (133 = 5 mod 32)
+
+struct AcqCap {                         // control block of one capture slot (shared memory)
+    u64   x0, i_stop, n, first, wfirst; // epoch origin; end of this pass; capture length; sample offsets of the capture's rows
+    int   cap;                          // capture index (-1: empty slot)
+    int   st;                           // steps since the epoch started
+    int   active;
+    int   flag, spec_n;                 // speculated flag behind the per-sample predicted prefix (spec_n <= 2·AB samples of the epoch)
+    uint32_t specmask[2];               // predicted flags of the epoch's first 64 samples (bit i of word b = sample 32·b + i)
+    uint32_t amask[AR], lmask[AR];      // per ring slot, written by the EMA lanes: bit i = sweep flag the reference takes at sample i
+                                        // (:232), bit i = lock detector above its threshold after sample i (:266)
+    float e_phase, e_freq, e_sweep, e_avg, e_lks;   // loop state at the epoch origin
+    uint32_t restarts;
+};
+
+struct AcqPackSmem {
+    float sp[AQ][AP_RS], a[AQ][AP_RS], b[AQ][AP_RS], aterm[AQ][AP_RS], lterm[AQ][AP_RS];
+    float ph[AQ][AP_RS1], fr[AQ][AP_RS1], sw[AQ][AP_RS1];      // [slot][i] = state BEFORE sample i, [slot][cnt] = after the block
+    float avg[AQ][AP_RS1], lks[AQ][AP_RS1];                    // [slot][0] = before the block, [slot][i + 1] = after sample i
+    AcqCap c[AQ];
+    int   n_active;
+    float noise_lo, noise_hi;           // acq_noise_like(avg) <=> noise_lo <= avg <= noise_hi (found by bisection at kernel start)
+};
+
+// compact list of the captures the second acquisition pass has to continue (one thread per capture, whole batch)
+__global__ void __launch_bounds__(128) k_slow_list(const TiledArgs a, uint32_t *__restrict__ list, uint32_t *__restrict__ count)
+{
+    const uint32_t cap = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cap >= a.n_captures) return;
+    const AcqResult &r = a.acq[cap];
+    if (r.slow && r.resume_at < cap_len(a, cap)) list[atomicAdd(count, 1u)] = cap;
+}
+
+__device__ __forceinline__ void acq_step_sel(float &phase, float &freq, float &sweep, float sp, const TrackConst &k, bool on)
+{
+    pll_track_step(phase, freq, sp, k);
+    const float f2 = freq + sweep;                                              // CarrierTrackingPLL.c:232-246, taken or not by select
+    float s2 = (f2 >= 0) ? fabsf(sweep) : -fabsf(sweep);
+    s2 = (f2 <= k.min_freq) ? -sweep : s2;
+    s2 = (f2 >= k.max_freq) ? -sweep : s2;
+    freq = on ? f2 : freq; sweep = on ? s2 : sweep;
+}
+
+__global__ void __launch_bounds__(AP_THREADS, 1) k_acquire_packed(const TiledArgs a, const int pass, const uint32_t *__restrict__ slow_list,
+                                                                  const uint32_t *__restrict__ slow_count)
+{
+    extern __shared__ __align__(16) unsigned char ap_raw[];
+    AcqPackSmem &s = *reinterpret_cast<AcqPackSmem *>(ap_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int hid = tid - AP_SERIAL, n_helpers = AP_THREADS - AP_SERIAL, n_hwarps = n_helpers / 32, hwarp = warp - 3;
+    const PllParams &pp = a.cc.pll;
+    PllState ps0; pll_reset(ps0); pll_begin(ps0, pp);
+    TrackConst kacq; kacq.alpha = ps0.alpha; kacq.beta = ps0.beta; kacq.max_freq = ps0.max_freq; kacq.min_freq = ps0.min_freq;
+    const float avg_alpha = 0.00005f;
+    const double c_avg = 1.0 - avg_alpha, c_lks = 1.0 - pp.lock_alpha;
+
+    // ---- slot set-up: capture q of this CTA ---------------------------------------------------------------------
+    if (tid < AQ) {
+        AcqCap &c = s.c[tid];
+        const u64 idx = (u64)blockIdx.x * AQ + tid;
+        long long cap = -1;
+        if (pass == 0) { if (idx < a.n_captures) cap = (long long)idx; }
+        else if (idx < *slow_count) cap = (long long)slow_list[idx];
+        c.cap = (int)cap; c.active = 0; c.st = -1; c.restarts = 0; c.spec_n = 0;   // st = -1: the first step only loads block 0
+        if (cap >= 0) {
+            AcqResult *res = &a.acq[cap];
+            const u64 n = cap_len(a, (uint32_t)cap);
+            c.n = n; c.first = (u64)cap * a.stride; c.wfirst = (u64)cap * a.ws_stride;
+            bool run = true;
+            if (pass == 0) {
+                if ((uint32_t)cap >= a.prelock_from && res->prelocked == 1) run = false;      // started in track mode by k_prelock
+                c.x0 = 0; c.i_stop = (a.acq_first && a.acq_first < n) ? a.acq_first : n;
+                c.e_phase = ps0.phase; c.e_freq = ps0.freq; c.e_sweep = ps0.sweep; c.e_avg = ps0.avg_phase; c.e_lks = ps0.locksig;
+                if (run && n == 0) {
+                    res->locked = 0; res->slow = 0; res->resume_at = 0; res->lock_sample = 0; res->track_begin = 0;
+                    res->phase = ps0.phase; res->freq = ps0.freq; res->sweep = ps0.sweep; res->avg_phase = ps0.avg_phase;
+                    res->locksig = ps0.locksig; res->lock_freq_hz = 0; res->alpha = kacq.alpha; res->beta = kacq.beta;
+                    run = false;
+                }
+            } else {
+                c.x0 = res->resume_at; c.i_stop = n;
+                c.e_phase = res->phase; c.e_freq = res->freq; c.e_sweep = res->sweep; c.e_avg = res->avg_phase; c.e_lks = res->locksig;
+                if (!res->slow || res->resume_at >= n) run = false;
+            }
+            c.flag = acq_noise_like(c.e_avg) != 0;
+            c.active = run ? 1 : 0;
+        }
+    }
+    __syncthreads();
+
+    auto blk_cnt = [&](const AcqCap &c, int j) -> int {                 // samples in block j of the capture's current epoch
+        if (!c.active || j < 0) return 0;
+        const u64 b0 = c.x0 + (u64)j * AB;
+        if (b0 >= c.i_stop) return 0;
+        return (int)((c.i_stop - b0 < (u64)AB) ? (c.i_stop - b0) : (u64)AB);
+    };
+    // speculated sweep flags of block j, one bit per sample: the predicted prefix of the epoch, the epoch's flag behind it
+    auto blk_flags = [&](const AcqCap &c, int j) -> uint32_t {
+        const uint32_t tail = c.flag ? 0xffffffffu : 0u;
+        if (j < 0 || j > 1) return tail;
+        const int left = c.spec_n - j * AB;                       // predicted samples inside this block
+        if (left <= 0) return tail;
+        const uint32_t valid = left >= 32 ? 0xffffffffu : ((1u << left) - 1u);
+        return (c.specmask[j] & valid) | (tail & ~valid);
+    };
+    if (tid == 0) { int na = 0; for (int q = 0; q < AQ; q++) na += s.c[q].active; s.n_active = na; }
+    if (tid == AP_SERIAL) {
+        // CarrierTrackingPLL.c:232 compares |π/2 - averagePhase| with 0.05 through a double difference narrowed to float; the
+        // narrowing is monotonic, so the samples that satisfy it are exactly the floats of one interval around π/2.  Its two
+        // ends are found once, by bisection over the (ordered) bit patterns of positive floats with the reference's own
+        // expression — the 32 EMA lanes then decide with two float compares per sample instead of five double/convert ops.
+        const uint32_t mid = pdt_f2u((float)(PDT_PI / 2.0));                 // inside the interval
+        uint32_t a0 = 0u, a1 = mid;                                         // lo: smallest pattern that satisfies it
+        while (a0 < a1) { const uint32_t m = a0 + (a1 - a0) / 2; if (acq_noise_like(pdt_u2f(m))) a1 = m; else a0 = m + 1; }
+        uint32_t b0_ = mid, b1 = 0x7f7fffffu;                               // hi: largest pattern that satisfies it
+        while (b0_ < b1) { const uint32_t m = b0_ + (b1 - b0_ + 1) / 2; if (acq_noise_like(pdt_u2f(m))) b0_ = m; else b1 = m - 1; }
+        s.noise_lo = pdt_u2f(a0); s.noise_hi = pdt_u2f(b0_);
+    }
+    __syncthreads();
+    int any_active = s.n_active;
+    const float noise_lo = s.noise_lo, noise_hi = s.noise_hi;
+
+    unsigned long long pf_steps = 0, pf_a = 0, pf_wait = 0, pf_c = 0;     // cycle accounting (pdt_debug_acq_prof): phase A busy / barrier wait / phase C
+    while (any_active) {
+        const long long t0 = clock64();
+        // ================= phase A: the four pipeline stages, each on its own threads =================
+        if (warp == 0) {
+            // core recurrence of block st (CarrierTrackingPLL.c:128-188 + sweep :232-246), lane = capture
+            const AcqCap &c = s.c[lane];
+            const int j = c.st, cnt = blk_cnt(c, j);
+            const int slot = j & (AR - 1), prev = (j + AR - 1) & (AR - 1);
+            float phase = c.e_phase, freq = c.e_freq, sweep = c.e_sweep;
+            if (cnt && j > 0) { const int pc = blk_cnt(c, j - 1); phase = s.ph[lane][prev * (AB + 1) + pc]; freq = s.fr[lane][prev * (AB + 1) + pc]; sweep = s.sw[lane][prev * (AB + 1) + pc]; }
+            const uint32_t fm = blk_flags(c, j);
+            const float *spr = &s.sp[lane][slot * AB];
+            float *php = &s.ph[lane][slot * (AB + 1)], *frp = &s.fr[lane][slot * (AB + 1)], *swp = &s.sw[lane][slot * (AB + 1)];
+            const unsigned FULL = 0xffffffffu;
+            const bool all_on = __all_sync(FULL, cnt == 0 || fm == 0xffffffffu);
+            const bool all_off = __all_sync(FULL, cnt == 0 || fm == 0u);
+            // All 32 samples of the slot are run unconditionally, four per trip with their inputs fetched ahead of the
+            // dependent chain: entry [i] is the state BEFORE sample i, so for a block of cnt < 32 samples (end of a pass)
+            // entry [cnt] is its end state and whatever lies behind it is never read.  Idle lanes chew on stale rows.
+            auto run = [&](auto step) {
+#pragma unroll 2
+                for (int i = 0; i < AB; i += 4) {
+                    float x[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) x[u] = spr[i + u];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) { php[i + u] = phase; frp[i + u] = freq; swp[i + u] = sweep; step(x[u], i + u); }
+                }
+                php[AB] = phase; frp[AB] = freq; swp[AB] = sweep;
+            };
+            if (__any_sync(FULL, cnt != 0)) {
+                if (all_on)       run([&](float x, int) { acq_step<true>(phase, freq, sweep, x, kacq); });
+                else if (all_off) run([&](float x, int) { acq_step<false>(phase, freq, sweep, x, kacq); });
+                else              run([&](float x, int i) { acq_step_sel(phase, freq, sweep, x, kacq, ((fm >> i) & 1u) != 0); });
+            }
+        } else if (warp == 1 || warp == 2) {
+            // EMA chains of block st-2: x <- (float)((double)x·c + (double)term) (:124 / :220), lane = capture
+            const AcqCap &c = s.c[lane];
+            const int j = c.st - 2, cnt = blk_cnt(c, j);
+            const int slot = j & (AR - 1), prev = (j + AR - 1) & (AR - 1);
+            const bool is_avg = warp == 1;
+            float (*row)[AP_RS1] = is_avg ? s.avg : s.lks;
+            const float *term = is_avg ? &s.aterm[lane][slot * AB] : &s.lterm[lane][slot * AB];
+            const double cc_ = is_avg ? c_avg : c_lks;
+            float x = is_avg ? c.e_avg : c.e_lks;
+            if (cnt && j > 0) x = row[lane][prev * (AB + 1) + blk_cnt(c, j - 1)];
+            float *out = &row[lane][slot * (AB + 1)];
+            if (__any_sync(0xffffffffu, cnt != 0)) {
+                out[0] = x;
+                uint32_t m = 0;                                       // the decision each sample implies, one bit per sample
+#pragma unroll 2
+                for (int i = 0; i < AB; i += 4) {                     // all 32 entries, like the core: [cnt] is the block's end value
+                    double t4[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) t4[u] = (double)term[i + u];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        x = (float)((double)x * cc_ + t4[u]); out[i + u + 1] = x;
+                        const bool bit = is_avg ? (x >= noise_lo && x <= noise_hi) : (x > pp.lock_thresh);   // :232 / :266 (off the chain)
+                        m |= (bit ? 1u : 0u) << (i + u);
+                    }
+                }
+                if (is_avg) s.c[lane].amask[slot] = m; else s.c[lane].lmask[slot] = m;
+            }
+        } else {
+            // helpers: feed-forward terms of block st-1 ([A] derotate + |phase|, [D] lock-detector input), inputs of block st+1
+            // the loads of block st+1 are issued first and land while the terms are computed; they go to shared memory last
+            float lp[AP_HCAPS], lq[AP_HCAPS], ls[AP_HCAPS];
+#pragma unroll
+            for (int u = 0; u < AP_HCAPS; u++) {
+                const int q = hwarp + u * n_hwarps;
+                lp[u] = lq[u] = ls[u] = 0.0f;
+                if (q < AQ) {
+                    const AcqCap &c = s.c[q];
+                    const int jn = c.st + 1;
+                    if (lane < blk_cnt(c, jn)) {
+                        const u64 i = c.x0 + (u64)jn * AB + lane;
+                        load_iq1(a.iq, a.pcm16, c.first + i, lp[u], lq[u]);
+                        ls[u] = a.sp[c.wfirst + i];
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < AP_HCAPS; u++) {
+                const int q = hwarp + u * n_hwarps;
+                if (q >= AQ) break;
+                const AcqCap &c = s.c[q];
+                const int j = c.st - 1, cnt = blk_cnt(c, j);
+                if (lane < cnt) {
+                    const int slot = j & (AR - 1), o = slot * AB + lane;
+                    const float phase_i = s.ph[q][slot * (AB + 1) + lane];
+                    // the phase stream leaves here, speculatively: a restart at an earlier sample recomputes and overwrites it,
+                    // and behind a lock latch the track tiles write their own phases from track_begin on
+                    a.ph[c.wfirst + c.x0 + (u64)j * AB + lane] = phase_i;
+                    float ti, tr;
+                    sincos_exact(phase_i, ti, tr);                                          // :106-107
+                    const float p = s.a[q][o], qq = s.b[q][o], nti = -ti;
+                    const float mre = p * tr - qq * nti, mim = p * nti + qq * tr;             // :110
+                    s.aterm[q][o] = avg_alpha * fabsf(arctan2_approx(mim, mre));              // :117,:124
+                    const float mag2 = p * p + qq * qq;                                       // :193-220
+                    const float inv = q_rsqrt(mag2);
+                    const float nre = p * inv, nim = qq * inv;
+                    s.lterm[q][o] = pp.lock_alpha * (nre * tr + nim * ti);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < AP_HCAPS; u++) {
+                const int q = hwarp + u * n_hwarps;
+                if (q < AQ) {
+                    const AcqCap &c = s.c[q];
+                    const int jn = c.st + 1;
+                    if (lane < blk_cnt(c, jn)) { const int o = (jn & (AR - 1)) * AB + lane; s.a[q][o] = lp[u]; s.b[q][o] = lq[u]; s.sp[q][o] = ls[u]; }
+                }
+            }
+        }
+        const long long t1 = clock64();
+        __syncthreads();
+        const long long t2 = clock64();
+        // ================= phase C: decisions of block st-2 and control, ONE warp, lane = capture — the EMA lanes left the
+        // per-sample decisions as bit masks, so a capture's verdict is a few integer operations =========
+        int my_active = 0;
+        if (warp == 3) {
+            AcqCap &c = s.c[lane];
+            if (c.active) {
+                my_active = 1;
+                const int j = c.st - 2, cnt = blk_cnt(c, j);
+                if (cnt == 0) c.st++;                                                // pipeline still filling for this capture
+                else {
+                    const int slot = j & (AR - 1);
+                    const u64 b0 = c.x0 + (u64)j * AB;
+                    const float *php = &s.ph[lane][slot * (AB + 1)], *frp = &s.fr[lane][slot * (AB + 1)], *swp = &s.sw[lane][slot * (AB + 1)];
+                    const float *avp = &s.avg[lane][slot * (AB + 1)], *lkp = &s.lks[lane][slot * (AB + 1)];
+                    const uint32_t valid = cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u);
+                    const uint32_t actual = c.amask[slot];
+                    const uint32_t diff = (actual ^ blk_flags(c, j)) & valid, lat = c.lmask[slot] & valid;
+                    const int mism = diff ? (__ffs((int)diff) - 1) : cnt, latch = lat ? (__ffs((int)lat) - 1) : cnt;
+                    AcqResult *res = &a.acq[c.cap];
+                    if (latch < cnt && latch < mism) {
+                        // every flag up to and including the latch sample was right: leave acquisition
+                        const int k = latch + 1;
+                        const float freq = frp[k];
+                        res->locked = 1; res->lock_sample = b0 + latch; res->track_begin = b0 + k; res->resume_at = c.n;
+                        if (pass == 0) res->slow = 0;
+                        res->phase = php[k]; res->freq = freq; res->sweep = swp[k];
+                        res->avg_phase = avp[k]; res->locksig = lkp[k];
+                        res->lock_freq_hz = freq * pp.Fs / (2.0 * PDT_PI);                              // :269
+                        const float bw = pp.bw_track, damp = ps0.damp;                                  // :272-273
+                        res->alpha = (4.0 * damp * bw) / (1.0 + 2.0 * damp * bw + bw * bw);
+                        res->beta  = (4.0 * bw * bw) / (1.0 + 2.0 * damp * bw + bw * bw);
+                        if (c.restarts) atomicAdd(&a.counters[2], c.restarts);
+                        c.active = 0; my_active = 0;
+                    } else if (mism < cnt) {
+                        // the flag flips at sample `mism`: new epoch there, from the exact state in front of that sample.  The
+                        // decisions the EMA just produced for the rest of this block become the per-sample prediction of the
+                        // new epoch (avg_phase moves by < 2e-4 per sample whatever the phase is), the last one its flag.
+                        const int n0 = cnt - mism;
+                        const float np_ = php[mism], nf = frp[mism], nw = swp[mism], na = avp[mism], nl = lkp[mism];
+                        c.x0 = b0 + (u64)mism; c.e_phase = np_; c.e_freq = nf; c.e_sweep = nw; c.e_avg = na; c.e_lks = nl;
+                        c.specmask[0] = actual >> mism; c.specmask[1] = 0u;
+                        c.spec_n = n0; c.flag = (int)((actual >> (cnt - 1)) & 1u); c.restarts++;
+                        c.st = -1;                                                   // next step only loads the new epoch's first block
+                    } else if (b0 + (u64)cnt >= c.i_stop) {
+                        // reached the end of this pass without a latch
+                        const bool done = (c.i_stop == c.n);
+                        res->locked = 0; res->lock_sample = 0; res->track_begin = c.n;
+                        res->resume_at = c.i_stop;
+                        if (pass == 0) res->slow = done ? 0 : 1;
+                        res->phase = php[cnt]; res->freq = frp[cnt]; res->sweep = swp[cnt];
+                        res->avg_phase = avp[cnt]; res->locksig = lkp[cnt];
+                        res->lock_freq_hz = 0; res->alpha = kacq.alpha; res->beta = kacq.beta;
+                        if (c.restarts) atomicAdd(&a.counters[2], c.restarts);
+                        c.active = 0; my_active = 0;
+                    } else c.st++;
+                }
+            }
+        }
+        const long long t3 = clock64();
+        any_active = __syncthreads_or(my_active);
+        pf_steps++; pf_a += (unsigned long long)(t1 - t0); pf_wait += (unsigned long long)(t2 - t1); pf_c += (unsigned long long)(t3 - t2);
+    }
+    if (pass == 1 && lane == 0 && (warp == 0 || warp == 1 || warp == 3)) {
+        // [0] steps, [1] core-warp phase A cycles, [2] its barrier wait, [3] EMA-warp phase A, [4] helper-warp phase A, [5] helper barrier wait, [6] phase C (warp 15), [7] phase C (warp 0)
+        if (warp == 0)  { atomicAdd(&g_acq_prof[0], pf_steps); atomicAdd(&g_acq_prof[1], pf_a); atomicAdd(&g_acq_prof[2], pf_wait); atomicAdd(&g_acq_prof[7], pf_c); }
+        if (warp == 1)  atomicAdd(&g_acq_prof[3], pf_a);
+        if (warp == 3)  { atomicAdd(&g_acq_prof[4], pf_a); atomicAdd(&g_acq_prof[5], pf_wait); }
+        if (warp == 3)  atomicAdd(&g_acq_prof[6], pf_c);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // carrier guess per tile: warp per (capture, tile >= 1)
 // ---------------------------------------------------------------------------------------------------
 constexpr int EST_WARPS = 2;
@@ -704,8 +1046,24 @@ __global__ void __launch_bounds__(EST_WARPS * 32) k_prelock(const TiledArgs a)
 constexpr int LS_WARPS = PDT_LS_WARPS;                    // warps per CTA of the lane-stream kernels
 constexpr size_t LS_SMEM = LS_WARPS * sizeof(LaneStreamSmem);
 
+// Checkpoints.  While a tile's samples are stored, the loop state (phase, frequency) is also recorded every PLL_CK samples.
+// A tile whose speculated start state turns out wrong is re-run from the true state — but only until its state at a
+// checkpoint is bit-identical to the recorded one: from there on the two runs are the same run, sample for sample, and the
+// phases already stored are the true ones (k_pll_fix_par).  A failed tile is typically off by a few ulps at its first
+// sample and merges within the first pieces; without the checkpoints each repair cost a whole tile of serial recurrence
+// (65 k samples = 2.3 ms at 250 ksps, 523 k samples = 18 ms at 2 Msps) on the critical path of every batch.
+constexpr unsigned PLL_CK = 1024;                         // samples between checkpoints (16 lane-stream rounds)
+static_assert(PLL_CK % LS_R == 0, "checkpoints fall on lane-stream round boundaries");
+
 struct PllLaneStep {
     float phase, freq; TrackConst k;
+    LoopState2 *ck = nullptr;                             // this tile's checkpoint row (nullptr: none recorded)
+    unsigned n_ck = 0;
+    __device__ __forceinline__ void round_done(unsigned c)
+    {
+        const unsigned done = (c + 1) * (unsigned)LS_R;   // samples of this pass behind us
+        if (ck && (done % PLL_CK) == 0 && done / PLL_CK < n_ck) ck[done / PLL_CK] = LoopState2{phase, freq};
+    }
     __device__ __forceinline__ void quad(const float4 &v, float4 &o)
     {
         o.x = phase; pll_track_step(phase, freq, v.x, k); o.y = phase; pll_track_step(phase, freq, v.y, k);
@@ -749,8 +1107,11 @@ __device__ __forceinline__ void k_pll_core_task(const TiledArgs &a, LaneStream &
     if (!active) warm = mid = keep = end = 0;
     const u64 cb = active ? (u64)cap * a.ws_stride : 0;              // lane streams index the whole workspace arrays
     lane_stream<true>(sm, lane, a.sp, a.ph, cb + warm, cb + keep, cb + mid, st);   // warm-up (nothing kept) / first W samples of tile 0
-    if (active && k != 0) a.pll_start[slot] = LoopState2{st.phase, st.freq};
-    lane_stream<true>(sm, lane, a.sp, a.ph, cb + mid, cb + mid, cb + end, st);
+    if (active && k != 0) {
+        a.pll_start[slot] = LoopState2{st.phase, st.freq};
+        st.ck = a.pll_ckpt + slot * a.pll_nck; st.n_ck = a.pll_nck;               // checkpoints of the stored pass (mid == begin)
+    }
+    lane_stream<true, PllLaneStep, true>(sm, lane, a.sp, a.ph, cb + mid, cb + mid, cb + end, st);
     if (active) a.pll_end[slot] = LoopState2{st.phase, st.freq};
 }
 
@@ -805,10 +1166,28 @@ __device__ __forceinline__ void k_pll_fix_par_task(const TiledArgs &a, LaneStrea
     if (!__any_sync(0xffffffffu, active)) return;
     if (!active) begin = end = 0;
     const u64 off = (u64)(active ? cap : 0) * a.ws_stride;
-    lane_stream<true>(sm, lane, a.sp, a.ph, off + begin, off + begin, off + end, st);
+    // re-run piece by piece (PLL_CK samples) and stop at the first checkpoint where the state is bit-identical to the one
+    // the stored run recorded there: everything behind it, including the tile's end state, is already the true trajectory
+    LoopState2 *ck = a.pll_ckpt + slot * a.pll_nck;
+    bool running = active, merged = false;
+    u64 at = begin;
+    for (unsigned j = 1; __any_sync(0xffffffffu, running); j++) {
+        u64 stop = at + PLL_CK; if (stop > end) stop = end;
+        const u64 p0 = running ? off + at : 0, p1 = running ? off + stop : 0;
+        lane_stream<true>(sm, lane, a.sp, a.ph, p0, p0, p1, st);
+        if (running) {
+            at = stop;
+            if (at >= end) running = false;                               // ran to the end of the tile: new end state below
+            else if (j < a.pll_nck) {
+                const LoopState2 now{st.phase, st.freq};
+                if (same_bits(ld_state(&ck[j]), now)) { running = false; merged = true; }
+                else st_state(&ck[j], now);
+            }
+        }
+    }
     if (active) {
         st_state(&a.pll_start[slot], truth);
-        st_state(&a.pll_end[slot], LoopState2{st.phase, st.freq});
+        if (!merged) st_state(&a.pll_end[slot], LoopState2{st.phase, st.freq});
         atomicAdd(&a.counters[0], 1u);
     }
 }

@@ -65,3 +65,23 @@ def test_float_sum_equals_double_sum_for_gardner_midpoint():
     nxt = nxt[(np.abs(nxt) >= np.float32(2.0 ** -20)) | (nxt == 0)]
     want = (nxt.astype(np.float64) + np.float64(step) / 2.0).astype(np.float32)
     assert np.array_equal(want, nxt + half)
+
+
+def test_sweep_decision_is_an_interval_of_floats():
+    """k_acquire_packed: CarrierTrackingPLL.c:232 — fabsf((float)(M_PI/2 - averagePhase)) < 0.05 with averagePhase a float,
+    the difference taken in double and narrowed — holds exactly for the floats of ONE interval [lo, hi] (the narrowing is
+    monotonic), so the kernel finds lo / hi once by bisection and decides with two float compares.  Checked for every float
+    of [1.0, 2.2] and a spread of others."""
+    def noise_like(avg):
+        d = (np.float64(np.pi / 2.0) - avg.astype(np.float64)).astype(np.float32)
+        return np.abs(d).astype(np.float64) < 0.05
+    x = _all_floats(1.0, 2.2)
+    t = noise_like(x)
+    idx = np.nonzero(t)[0]
+    assert idx.size > 800_000 and np.array_equal(idx, np.arange(idx[0], idx[-1] + 1))       # one contiguous run of bit patterns
+    lo, hi = x[idx[0]], x[idx[-1]]
+    assert np.array_equal(t, (x >= lo) & (x <= hi))
+    rng = np.random.default_rng(4)
+    y = np.concatenate([rng.uniform(-10, 10, 1_000_000).astype(np.float32), np.float32([0.0, -0.0, np.inf, -np.inf, np.nan, 1e-30, 3e38])])
+    with np.errstate(invalid="ignore"):
+        assert np.array_equal(noise_like(y), (y >= lo) & (y <= hi))
