@@ -772,9 +772,9 @@ def main():
     shards = world if world > 1 else args.strong_shards
     if shards > 1:
         cs = pdist.shard_range(C_, rank if world > 1 else 0, shards)[1]
-        m_s = max(1, min(16, 4 * shards, 2048 // max(cs, 1)))
-        rot.close(keep=2)                              # two contexts stay for the e2e leg; the rest make room
-        rs = Rotation(cs, m_s, groups=1 if cs <= 256 else 0)
+        m_s = max(1, min(16, 8192 // max(cs, 1)))       # the acquisition tail of a batch is ~100 ms of latency whatever its size
+        rot.close(keep=3)                              # three contexts stay for the e2e leg; the rest make room
+        rs = Rotation(cs, m_s, groups=1)
         k_s = max(args.steps, 3 * m_s)
         ms_s, _, _, pr_s = timed(rs, k_s, max(args.warmup, m_s))
         strong = {"scaling": "strong", "value": C_ * n / (ms_s * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms_s, "steps": k_s, "captures_total": C_, "captures_per_gpu": cs, "shards": shards,
@@ -902,7 +902,9 @@ def main():
     # pinned host memory (chunked, overlapped with the kernels) and reads the stats + frame tables back to the host.
     if not args.no_e2e:
         e2e_caps = C_
-        m = min(inflight, 2)                      # two staging buffers are enough to keep the PCIe link busy
+        m = min(inflight, 3)                      # three contexts in rotation keep the PCIe link busy (a batch alone takes ~100 ms
+        for c_ in ctxs[:m]:                       # from its last byte to its frames; the int16 batch arrives in 80 ms)
+            c_.set_groups(3)                      # chunked staging: a capture group starts as soon as ITS samples have landed
         e_streams = [torch.cuda.Stream() for _ in range(m)]
 
         def e2e_measure(pcm, d_src):
