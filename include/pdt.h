@@ -246,6 +246,26 @@ int         pdt_stream_frame_checks(const pdt_frame *frames, uint32_t n_frames, 
 int         pdt_synth_poes_stream_device(void *d_iq, int pcm16, uint64_t start_sample, uint64_t n_samples,
                                          uint64_t total_samples, double sample_rate, uint64_t seed, void *stream);
 
+/* ---- live mode: bounded-latency streaming ---------------------------------------------------------
+ * The reference's sound-card drivers (POESTIPdemodPortAudio/main.c:324-401, ARGOSdemodPortAudio/main.c:290-329) read a
+ * chunk from the audio device and run the stage functions on it, for ever; the stages carry their state in statics.  Live
+ * mode is that loop for up to `max_captures` streams at once: every push hands the NEXT `n` samples of every stream to the
+ * chain, which continues exactly where the previous push stopped — PLL, FIR history, AGC gain, Gardner position (and the
+ * chunk buffer it looks back into), Manchester phase, the frame being shifted in.  A push is what one iteration of the
+ * reference's loop is: the result equals the reference fed with the same sequence of chunk lengths (pushes longer than
+ * params.chunk are cut into chunks of that length).  Latency of a push = one chunk through the serial chain (a few ms).
+ *   pdt_live_begin        (re)start: all streams back to the reference's initial state
+ *   pdt_live_push_device  enqueue one push (d_iq: stream s at d_iq + 2·s·stride_samples, n <= stride_samples samples each)
+ *   pdt_live_push_host    same from host buffers, then pdt_fetch: synchronous
+ * Results: pdt_capture_stats are running totals (n_samples, n_symbols, n_bits, n_frames since pdt_live_begin); the frame
+ * table is a RING — frame number k of a stream (0-based, in order of its sync word) is slot k mod max_frames; a frame whose
+ * `complete` is 0 is still being shifted in and will be finished by a later push.  sample_index is absolute in the stream. */
+int         pdt_live_begin(pdt_ctx *ctx);
+int         pdt_live_push_device(pdt_ctx *ctx, const void *d_iq, int pcm16, uint32_t n_streams, uint64_t stride_samples,
+                                 uint64_t n, void *stream);
+int         pdt_live_push_host(pdt_ctx *ctx, const void *h_iq, int pcm16, uint32_t n_streams, uint64_t stride_samples,
+                               uint64_t n, pdt_capture_stats *stats_out, pdt_frame *frames_out);
+
 /* Device addresses of the result tables of the last batch (for NCCL gathers without a host bounce). */
 int         pdt_result_tables(pdt_ctx *ctx, void **d_stats, void **d_frames, uint32_t *max_frames);
 

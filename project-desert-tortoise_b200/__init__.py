@@ -124,6 +124,9 @@ def load(prec: str = "f32"):
     L.pdt_launch_count.restype = u64
     L.pdt_set_profiling.argtypes = [vp, C.c_int]
     L.pdt_set_groups.argtypes = [vp, C.c_int]
+    L.pdt_live_begin.argtypes = [vp]
+    L.pdt_live_push_device.argtypes = [vp, vp, C.c_int, u32, u64, u64, vp]
+    L.pdt_live_push_host.argtypes = [vp, vp, C.c_int, u32, u64, u64, vp, vp]
     L.pdt_kernel_times.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]
     L.pdt_timeline.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_int), C.POINTER(C.c_float), C.c_int]
     L.pdt_engine.argtypes = [vp]
@@ -171,7 +174,7 @@ EXPORTED_SYMBOLS = [
     "pdt_fetch",
     "pdt_result_tables", "pdt_format_frames", "pdt_launch_count", "pdt_synth_poes_device", "pdt_engine",
     "pdt_demod_segments_device", "pdt_stream_plan_make", "pdt_stream_segment_length", "pdt_stream_stitch", "pdt_stream_frame_checks", "pdt_synth_poes_stream_device",
-    "pdt_frame_checks", "pdt_tiled_counters", "pdt_set_profiling", "pdt_set_groups", "pdt_kernel_times", "pdt_timeline", "pdt_debug_acq_prof",
+    "pdt_frame_checks", "pdt_tiled_counters", "pdt_set_profiling", "pdt_set_groups", "pdt_live_begin", "pdt_live_push_device", "pdt_live_push_host", "pdt_kernel_times", "pdt_timeline", "pdt_debug_acq_prof",
     # include/pdt_legacy.h
     "FindSignalAmplitude", "Squelch", "StaticGain", "NormalizingAGC", "NormalizingAGCC", "CarrierTrackPLL", "arctan2",
     "Q_rsqrt", "LowPassFilter", "LowPassFilterInterp", "MakeLPFIR", "GardenerClockRecovery", "MMClockRecovery", "sign",
@@ -315,6 +318,47 @@ def frames_to_text_rows(frames_1d: np.ndarray, n_frames: int):
     for f in frames_1d[:n_frames]:
         rows.append((bool(f["inverse"]), np.array(f["bytes"][: f["n_bytes"]], np.uint8), bool(f["complete"])))
     return rows
+
+
+class Live:
+    """Bounded-latency streaming (include/pdt.h pdt_live_*): the reference's sound-card loop
+    (POESTIPdemodPortAudio/main.c:324-401) for `n_streams` streams at once.  push() hands the next chunk of every stream to the
+    chain and returns, per stream, the frames COMPLETED since the previous push, in order."""
+
+    def __init__(self, prec: str, params: Params, n_streams: int, max_chunk: int, max_frames: int = 64):
+        self.d = Demod(prec, params, n_streams, max_chunk, max_frames)
+        self.n_streams, self.max_chunk, self.max_frames = n_streams, max_chunk, max_frames
+        _check(self.d.L, self.d.L.pdt_live_begin(self.d.ctx))
+        self.reported = [0] * n_streams
+        self.stats = None
+
+    def push(self, iq: np.ndarray, pcm16: bool = False):
+        """iq: [n_streams, n, 2] (or [n_streams, 2n]) — the next n <= max_chunk samples of every stream."""
+        iq = np.ascontiguousarray(iq, np.int16 if pcm16 else self.d.dt).reshape(self.n_streams, -1)
+        n = iq.shape[1] // 2
+        assert n <= self.max_chunk
+        stats = np.zeros(self.n_streams, STATS_DTYPE)
+        frames = np.zeros((self.n_streams, self.max_frames), FRAME_DTYPE)
+        _check(self.d.L, self.d.L.pdt_live_push_host(self.d.ctx, _p(iq), int(pcm16), self.n_streams, n, n, _p(stats), _p(frames)))
+        self.stats = stats
+        out = []
+        for s in range(self.n_streams):
+            done = []
+            while self.reported[s] < int(stats[s]["n_frames"]):
+                f = frames[s, self.reported[s] % self.max_frames]
+                if not f["complete"]:
+                    break                                   # still being shifted in: a later push finishes it
+                done.append(f.copy())
+                self.reported[s] += 1
+            out.append(done)
+        return out
+
+    def pending(self):
+        """Frames started but not complete (e.g. at the end of the input), per stream."""
+        return [int(self.stats[s]["n_frames"]) - self.reported[s] if self.stats is not None else 0 for s in range(self.n_streams)]
+
+    def close(self):
+        self.d.close()
 
 
 class Legacy:

@@ -142,6 +142,9 @@ struct pdt_ctx {
     unsigned long long *d_nsamp = nullptr;
     pdt_traces *d_traces = nullptr;
     pdt_frame_quality *d_quality = nullptr;
+    ChainState *d_live = nullptr;        // live mode (pdt_live_*): per-stream chain state carried from push to push
+    real_t     *d_live_ws = nullptr;     //   and per-stream workspaces (FIR history, chunk buffer)
+    size_t      live_ws_stride = 0;
     void       *d_stage = nullptr;       // staging for pdt_demod_host
     size_t      stage_bytes = 0;
     int         device = 0, sm_count = 0;
@@ -751,6 +754,7 @@ void pdt_destroy(pdt_ctx *c)
     if (!c) return;
     cudaFree(c->d_taps); cudaFree(c->d_ws); cudaFree(c->d_stats); cudaFree(c->d_frames);
     cudaFree(c->d_nsamp); cudaFree(c->d_traces); cudaFree(c->d_stage); cudaFree(c->d_quality);
+    cudaFree(c->d_live); cudaFree(c->d_live_ws);
 #if PDT_USE_FLOATS
     if (c->engine == PDT_ENGINE_TILED) tiled_free(c);
     for (cudaEvent_t e : c->marks) if (e) cudaEventDestroy(e);
@@ -820,12 +824,67 @@ static int demod_device_impl(pdt_ctx *c, const void *d_iq, int pcm16, uint32_t n
     a.cc = c->cc; a.taps = c->d_taps; a.iq = d_iq; a.pcm16 = pcm16; a.stride = stride_samples;
     a.n_samples = n_samples ? c->d_nsamp : nullptr; a.n_uniform = stride_samples; a.n_captures = n_captures;
     a.workspace = c->d_ws; a.ws_stride = c->ws_stride; a.use_smem = c->use_smem;
-    a.stats = c->d_stats; a.frames = c->d_frames; a.traces = traces ? c->d_traces : nullptr;
+    a.stats = c->d_stats; a.frames = c->d_frames; a.traces = traces ? c->d_traces : nullptr; a.persist = nullptr;
     const int grid = (int)std::min<uint32_t>(n_captures, (uint32_t)c->grid);
     k_chain_exact<<<grid, CHAIN_THREADS, c->smem_bytes, s>>>(a);
     count_launch();
     PDT_CUDA(cudaGetLastError());
     return PDT_OK;
+}
+
+// ---- live mode: bounded-latency streaming with carried state (POESTIPdemodPortAudio/main.c:324-401) ----------------
+int pdt_live_begin(pdt_ctx *c)
+{
+    if (!c) return fail(PDT_EINVAL, "bad arguments");
+    if (!device_ok()) return PDT_ENODEV;
+    if (c->cc.L <= 0) return fail(PDT_EINVAL, "live mode needs interp >= 1 (set force_min_interp1 above 300 ksps)");
+    if (!c->d_live) {
+        c->live_ws_stride = (chain_ws_reals(c->cc) + 31) & ~(size_t)31;
+        PDT_CUDA(cudaMalloc((void **)&c->d_live, sizeof(ChainState) * c->max_captures));
+        PDT_CUDA(cudaMalloc((void **)&c->d_live_ws, sizeof(real_t) * c->live_ws_stride * c->max_captures));
+    }
+    PDT_CUDA(cudaMemset(c->d_live, 0, sizeof(ChainState) * c->max_captures));
+    PDT_CUDA(cudaMemset(c->d_live_ws, 0, sizeof(real_t) * c->live_ws_stride * c->max_captures));
+    PDT_CUDA(cudaMemset(c->d_stats, 0, sizeof(pdt_capture_stats) * c->max_captures));
+    PDT_CUDA(cudaMemset(c->d_frames, 0, sizeof(pdt_frame) * (size_t)c->max_captures * c->max_frames));
+    return PDT_OK;
+}
+
+int pdt_live_push_device(pdt_ctx *c, const void *d_iq, int pcm16, uint32_t n_streams, uint64_t stride_samples, uint64_t n, void *stream)
+{
+    if (!c || !d_iq || !n_streams || n_streams > c->max_captures || n > stride_samples) return fail(PDT_EINVAL, "bad arguments");
+    if (!c->d_live) return fail(PDT_EINVAL, "pdt_live_begin first");
+    if (n == 0) return PDT_OK;
+    ChainArgs a;
+    a.cc = c->cc; a.cc.ring_frames = 1;
+    a.taps = c->d_taps; a.iq = d_iq; a.pcm16 = pcm16; a.stride = stride_samples;
+    a.n_samples = nullptr; a.n_uniform = n; a.n_captures = n_streams;
+    a.workspace = c->d_live_ws; a.ws_stride = c->live_ws_stride; a.use_smem = 0;
+    a.stats = c->d_stats; a.frames = c->d_frames; a.traces = nullptr; a.persist = c->d_live;
+    const int grid = (int)std::min<uint32_t>(n_streams, (uint32_t)std::max(c->sm_count, 1) * 4u);
+    k_chain_exact<<<grid, CHAIN_THREADS, 0, (cudaStream_t)stream>>>(a);
+    count_launch();
+    PDT_CUDA(cudaGetLastError());
+    return PDT_OK;
+}
+
+int pdt_live_push_host(pdt_ctx *c, const void *h_iq, int pcm16, uint32_t n_streams, uint64_t stride_samples, uint64_t n,
+                       pdt_capture_stats *stats_out, pdt_frame *frames_out)
+{
+    if (!c || !h_iq) return fail(PDT_EINVAL, "bad arguments");
+    if (!device_ok()) return PDT_ENODEV;
+    const size_t elem = pcm16 ? 2 * sizeof(int16_t) : 2 * sizeof(real_t);
+    const size_t bytes = elem * stride_samples * n_streams;
+    if (bytes > c->stage_bytes) {
+        PDT_CUDA(cudaDeviceSynchronize());
+        cudaFree(c->d_stage); c->d_stage = nullptr; c->stage_bytes = 0;
+        PDT_CUDA(cudaMalloc(&c->d_stage, bytes));
+        c->stage_bytes = bytes;
+    }
+    PDT_CUDA(cudaMemcpyAsync(c->d_stage, h_iq, bytes, cudaMemcpyHostToDevice, nullptr));
+    const int rc = pdt_live_push_device(c, c->d_stage, pcm16, n_streams, stride_samples, n, nullptr);
+    if (rc != PDT_OK) return rc;
+    return pdt_fetch(c, n_streams, stats_out, frames_out, nullptr);
 }
 
 int pdt_fetch(pdt_ctx *c, uint32_t n_captures, pdt_capture_stats *stats_out, pdt_frame *frames_out, void *stream)

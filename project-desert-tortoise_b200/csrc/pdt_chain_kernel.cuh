@@ -25,6 +25,8 @@ struct ChainState {
     uint32_t        n_frames;
     int             cur_frame;                 // slot being filled (-1 none / overflow)
     real_t          avg_phase;
+    unsigned long long in0;                    // live mode: input samples consumed by earlier pushes (absolute index of this push's sample 0)
+    int             live_init;                 // live mode: this state has been initialised (the stream is running)
 };
 
 struct ChainArgs {
@@ -42,6 +44,9 @@ struct ChainArgs {
     pdt_capture_stats *stats;       // [n_captures]
     pdt_frame      *frames;         // [n_captures][max_frames]
     const pdt_traces *traces;       // device [n_captures] or nullptr
+    ChainState     *persist;        // live mode (pdt_live_*): per-stream state carried from push to push, else nullptr.  The
+                                    // workspace is then per STREAM (FIR history and the chunk buffer Gardner looks back into
+                                    // survive between pushes like the reference's static buffers do) and the frame table a ring.
 };
 
 constexpr int CHAIN_THREADS = 256;
@@ -80,8 +85,8 @@ PDT_DEV void consume_symbol(ChainState &st, const ChainConst &cc, real_t sym, un
         if (eol) { f.complete = 1; st.cur_frame = -1; }
     } else if (eol) st.cur_frame = -1;
     if (ev != EV_NONE) {
-        if (st.n_frames < cc.max_frames) {
-            st.cur_frame = (int)st.n_frames;
+        if (st.n_frames < cc.max_frames || cc.ring_frames) {
+            st.cur_frame = (int)(st.n_frames % cc.max_frames);          // live mode: frame k of a stream sits in slot k mod max_frames
             pdt_frame &f = frames[st.cur_frame];
             f.sample_index = abs_interp_idx; f.bit_index = (uint32_t)st.n_bits;
             f.inverse = (ev == EV_SYNC_INV); f.complete = 0; f.pad = 0;
@@ -104,39 +109,48 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_chain_exact(const ChainArgs a
 
     const ChainConst &cc = args.cc;
     const int tid = threadIdx.x;
-    real_t *ws = args.use_smem ? reinterpret_cast<real_t *>(smem_raw) : args.workspace + (size_t)blockIdx.x * args.ws_stride;
-    real_t *Rext = ws;                                   // [K-1 + chunk]
-    real_t *LOCK = Rext + (cc.K - 1 + cc.chunk);         // [chunk] (ARGOS)
-    real_t *Y    = LOCK + (cc.argos ? cc.chunk : 0);     // [chunk*L + ypad]
-    real_t *IQT  = Y + (size_t)cc.chunk * cc.L + cc.ypad;     // [2*IQ_TILE]
     const size_t y_cap = (size_t)cc.chunk * cc.L + cc.ypad;
 
     for (int i = tid; i < cc.N; i += CHAIN_THREADS) taps_s[i] = args.taps[i];
 
     for (uint32_t cap = blockIdx.x; cap < args.n_captures; cap += gridDim.x) {
+        real_t *ws = args.use_smem ? reinterpret_cast<real_t *>(smem_raw)
+                                   : args.workspace + (size_t)(args.persist ? cap : blockIdx.x) * args.ws_stride;
+        real_t *Rext = ws;                                   // [K-1 + chunk]
+        real_t *LOCK = Rext + (cc.K - 1 + cc.chunk);         // [chunk] (ARGOS)
+        real_t *Y    = LOCK + (cc.argos ? cc.chunk : 0);     // [chunk*L + ypad]
+        real_t *IQT  = Y + (size_t)cc.chunk * cc.L + cc.ypad;     // [2*IQ_TILE]
         const unsigned long long n = args.n_samples ? args.n_samples[cap] : args.n_uniform;
         const unsigned long long first = (unsigned long long)cap * args.stride;
         pdt_frame *frames = args.frames + (size_t)cap * cc.max_frames;
         const pdt_traces *tr = args.traces ? &args.traces[cap] : nullptr;
 
         __syncthreads();
+        const bool resume = args.persist && args.persist[cap].live_init;    // live mode, second push onwards: carry on
         if (tid == 0) {
-            st = ChainState();
-            pll_reset(st.pll);
-            st.agc.gain = 1;
-            st.sync.one = 1;
-            st.cur_frame = -1;
-            st.norm = cc.norm_override;
+            if (resume) st = args.persist[cap];
+            else {
+                st = ChainState();
+                pll_reset(st.pll);
+                st.agc.gain = 1;
+                st.sync.one = 1;
+                st.cur_frame = -1;
+                st.norm = cc.norm_override;
+                st.live_init = 1;
+            }
         }
-        for (size_t i = tid; i < (size_t)cc.K - 1; i += CHAIN_THREADS) Rext[i] = 0;
-        for (size_t i = tid; i < y_cap; i += CHAIN_THREADS) Y[i] = 0;        // fresh zeroed buffer, like the malloc'd one
+        if (!resume) {
+            for (size_t i = tid; i < (size_t)cc.K - 1; i += CHAIN_THREADS) Rext[i] = 0;
+            for (size_t i = tid; i < y_cap; i += CHAIN_THREADS) Y[i] = 0;    // fresh zeroed buffer, like the malloc'd one
+        }
         __syncthreads();
+        const unsigned long long in0 = st.in0;                              // absolute index of this call's first sample (0 outside live mode)
 
         for (unsigned long long base = 0; base < n; base += cc.chunk) {
             const uint32_t m = (uint32_t)((n - base < cc.chunk) ? (n - base) : cc.chunk);
 
             // ---- StaticGain on the first chunk (main.c:384-389) --------------------------------------
-            if (base == 0 && tid == 0 && st.norm == 0) {
+            if (base == 0 && in0 == 0 && tid == 0 && st.norm == 0) {
                 real_t level; real_t a, b;
                 load_iq(args.iq, args.pcm16, first, a, b);
                 level = hypot_exact(a, b);
@@ -161,7 +175,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_chain_exact(const ChainArgs a
                 __syncthreads();
                 if (tid == 0) {
                     for (uint32_t i = 0; i < tn; i++) {
-                        const unsigned long long g = base + t0 + i;
+                        const unsigned long long g = in0 + base + t0 + i;
                         if (tr) {
                             if (tr->pll_phase) reinterpret_cast<real_t *>(tr->pll_phase)[g] = st.pll.phase;
                             if (tr->pll_freq)  reinterpret_cast<real_t *>(tr->pll_freq)[g]  = st.pll.freq;
@@ -223,7 +237,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_chain_exact(const ChainArgs a
                     if (tr && tr->agc) reinterpret_cast<real_t *>(tr->agc)[base * cc.L + o] = v;
                 }
                 gardner_begin(st.gar, cc.gardner_fs, cc.baud);
-                const unsigned long long ibase = base * (unsigned long long)cc.L;
+                const unsigned long long ibase = (in0 + base) * (unsigned long long)cc.L;
                 if (cc.use_mm) {
                     // MMClockRecovery.c:5-84 in the Gardner loop's place (the call the drivers keep commented out)
                     mm_begin(st.mm, cc.gardner_fs, cc.baud);
@@ -257,8 +271,9 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_chain_exact(const ChainArgs a
         }
 
         if (tid == 0) {
+            if (args.persist) { st.in0 = in0 + n; args.persist[cap] = st; }
             pdt_capture_stats s;
-            s.n_samples = n; s.n_symbols = st.n_sym; s.n_bits = st.n_bits; s.n_frames = st.n_frames;
+            s.n_samples = in0 + n; s.n_symbols = st.n_sym; s.n_bits = st.n_bits; s.n_frames = st.n_frames;
             s.locked = (st.pll.stage == 2); s.lock_sample = st.pll.lock_sample; s.lock_freq_hz = st.pll.lock_freq_hz;
             s.norm_factor = st.norm; s.avg_phase = st.avg_phase;
             s.final_phase = st.pll.phase; s.final_freq = st.pll.freq; s.final_gain = st.agc.gain; s.final_next = st.gar.next;

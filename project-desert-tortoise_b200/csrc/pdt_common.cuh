@@ -39,6 +39,7 @@ struct ChainConst {
     SyncParams sync;
     uint32_t max_frames;
     int      prefix_bytes;              // 2 for POES (literal ED E2), 0 for ARGOS
+    int      ring_frames;               // live mode: the frame table is a ring (slot = frame number mod max_frames)
     int      use_mm;                    // PDT_CLOCK_MM: MMClockRecovery.c:5-84 instead of the Gardner loop (exact engine)
     real_t   mm_range, mm_kp;
     int      ypad;                      // zero pad behind the interpolated chunk: Gardner's first mid-sample of a chunk reads up
