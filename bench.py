@@ -794,13 +794,18 @@ def main():
     kernels = []
     if tiled:
         d.set_profiling(True)
-        acc = {}
+        acc, passes = {}, {}
         reps = min(args.steps, 3)
         for _ in range(reps):
             d.demod_device(d_iq.data_ptr(), C_, n, pcm16=args.pcm16, stream=stream)
             torch.cuda.synchronize()
+            seen = {}
             for name, t_ms in d.kernel_times():
                 acc[name] = acc.get(name, 0.0) + t_ms / reps
+                k_occ = seen.get(name, 0)                       # launches of one name in order: [fast captures, slow captures]
+                seen[name] = k_occ + 1
+                passes.setdefault(name, []).extend([0.0] * (k_occ + 1 - len(passes.get(name, []))))
+                passes[name][k_occ] += t_ms / reps
         d.set_profiling(False)
         kernels = sorted(acc.items(), key=lambda kv: -kv[1])
         counters = d.tiled_counters(stream)
@@ -862,6 +867,13 @@ def main():
                "alg_GBps": round(C_ * n * alg[nm] / (t_ms * 1e-3) / 1e9, 1) if nm in alg and t_ms > 0 else None,
                "hbm_frac": round(C_ * n * alg[nm] / (t_ms * 1e-3) / 1e9 / peak, 4) if nm in alg and t_ms > 0 else None}
               for nm, t_ms in kernels]
+    if tiled:
+        for row in ktable:      # kernels launched once per class of captures: [latched in the first pass, slow ones]
+            if len(passes.get(row["kernel"], [])) > 1:
+                row["ms_per_launch"] = [round(v, 4) for v in passes[row["kernel"]]]
+        n_slow = int(stats["slow"].sum()) if "slow" in (stats.dtype.names or ()) else None
+        if n_slow is not None:
+            roofline["slow_captures"] = n_slow
     chain_gbps = C_ * n * bytes_per_sample / (ms_step * 1e-3) / 1e9
 
     line = {

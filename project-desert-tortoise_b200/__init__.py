@@ -174,7 +174,7 @@ EXPORTED_SYMBOLS = [
     "pdt_fetch",
     "pdt_result_tables", "pdt_format_frames", "pdt_launch_count", "pdt_synth_poes_device", "pdt_engine",
     "pdt_demod_segments_device", "pdt_stream_plan_make", "pdt_stream_segment_length", "pdt_stream_stitch", "pdt_stream_frame_checks", "pdt_synth_poes_stream_device",
-    "pdt_frame_checks", "pdt_tiled_counters", "pdt_set_profiling", "pdt_set_groups", "pdt_live_begin", "pdt_live_push_device", "pdt_live_push_host", "pdt_kernel_times", "pdt_timeline", "pdt_debug_acq_prof",
+    "pdt_frame_checks", "pdt_tiled_counters", "pdt_set_profiling", "pdt_set_groups", "pdt_live_begin", "pdt_live_push_device", "pdt_live_push_host", "pdt_kernel_times", "pdt_timeline", "pdt_debug_acq_prof", "pdt_debug_chain_prof",
     # include/pdt_legacy.h
     "FindSignalAmplitude", "Squelch", "StaticGain", "NormalizingAGC", "NormalizingAGCC", "CarrierTrackPLL", "arctan2",
     "Q_rsqrt", "LowPassFilter", "LowPassFilterInterp", "MakeLPFIR", "GardenerClockRecovery", "MMClockRecovery", "sign",

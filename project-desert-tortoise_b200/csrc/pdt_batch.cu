@@ -206,7 +206,7 @@ static bool tiled_applicable(const pdt_params &p, const ChainConst &cc, uint32_t
     if ((double)cc.chunk * cc.L > 1e9) return false;
     // one 2π wrap per sample must suffice (pdt_tiled.cuh::pll_track_step): |Δphase| <= max_freq + (alpha+beta)·3π < 2π
     PllState ps; pll_reset(ps); pll_begin(ps, cc.pll);
-    if (!((double)ps.max_freq + 10.0 * ((double)ps.alpha + (double)ps.beta) < 6.0)) return false;
+    if (!((double)ps.max_freq + 10.0 * ((double)ps.alpha + (double)ps.beta) < 4.0)) return false;     // 2π + 4 < 10.5: inside the checked range
     if (!(cc.pll.bw_track > 0) || !(cc.agc_decay > 0)) return false;
     const double S = (double)cc.gardner_fs / (double)cc.baud;            // k_gardner: the window must hold several symbols
     if (!(S > 2.0) || S > tiled::GAR_WIN / 8) return false;
@@ -720,7 +720,9 @@ pdt_ctx *pdt_create(const pdt_params *p, uint32_t max_captures, uint64_t max_sam
         int max_optin = 0;
         cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device);
         c->smem_bytes = chain_ws_reals(c->cc) * sizeof(real_t);
-        const size_t static_smem = sizeof(ChainState) + sizeof(real_t) * PDT_MAX_TAPS + 1024;
+        cudaFuncAttributes fa{};
+        if ((e = cudaFuncGetAttributes(&fa, k_chain_exact)) != cudaSuccess) return bail(e, "cudaFuncGetAttributes");
+        const size_t static_smem = fa.sharedSizeBytes + 1024;
         c->use_smem = (c->smem_bytes + static_smem <= (size_t)max_optin);
         int per_sm = 1;
         if (c->use_smem) {
@@ -730,7 +732,7 @@ pdt_ctx *pdt_create(const pdt_params *p, uint32_t max_captures, uint64_t max_sam
         } else {
             c->smem_bytes = 0;
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_chain_exact, CHAIN_THREADS, 0);
-            per_sm = std::min(per_sm, 4);
+            per_sm = std::min(per_sm, 8);
         }
         if (per_sm < 1) per_sm = 1;
         c->grid = (int)std::min<uint64_t>(max_captures, (uint64_t)c->sm_count * per_sm);
@@ -861,7 +863,7 @@ int pdt_live_push_device(pdt_ctx *c, const void *d_iq, int pcm16, uint32_t n_str
     a.n_samples = nullptr; a.n_uniform = n; a.n_captures = n_streams;
     a.workspace = c->d_live_ws; a.ws_stride = c->live_ws_stride; a.use_smem = 0;
     a.stats = c->d_stats; a.frames = c->d_frames; a.traces = nullptr; a.persist = c->d_live;
-    const int grid = (int)std::min<uint32_t>(n_streams, (uint32_t)std::max(c->sm_count, 1) * 4u);
+    const int grid = (int)std::min<uint32_t>(n_streams, (uint32_t)std::max(c->sm_count, 1) * 8u);
     k_chain_exact<<<grid, CHAIN_THREADS, 0, (cudaStream_t)stream>>>(a);
     count_launch();
     PDT_CUDA(cudaGetLastError());
@@ -962,6 +964,17 @@ int pdt_timeline(pdt_ctx *c, const char **names, int *groups, float *end_ms, int
 #else
     return 0;
 #endif
+}
+
+int pdt_debug_chain_prof(uint64_t out[16], int reset)
+{
+    if (!out) return fail(PDT_EINVAL, "bad arguments");
+    unsigned long long h[16];
+    PDT_CUDA(cudaDeviceSynchronize());
+    PDT_CUDA(cudaMemcpyFromSymbol(h, g_chain_prof, sizeof h));
+    for (int i = 0; i < 16; i++) out[i] = h[i];
+    if (reset) { unsigned long long z[16] = {}; PDT_CUDA(cudaMemcpyToSymbol(g_chain_prof, z, sizeof z)); }
+    return PDT_OK;
 }
 
 int pdt_debug_acq_prof(uint64_t out[8], int reset)

@@ -10,6 +10,7 @@
 #pragma once
 
 #include "pdt_common.cuh"
+#include "pdt_pll_pipe.cuh"
 
 namespace pdt {
 
@@ -50,12 +51,12 @@ struct ChainArgs {
 };
 
 constexpr int CHAIN_THREADS = 256;
-constexpr int IQ_TILE = 1024;       // samples staged per PLL tile
+static_assert(CHAIN_THREADS == PP_B, "the PLL block runner gives every thread of the CTA one sample of a block");
 
-// reals needed: Rext[K-1+chunk] + LOCK[chunk] (ARGOS only) + Y[chunk*L+ypad] + IQ tile[2*IQ_TILE]
+// reals needed: Rext[K-1+chunk] + LOCK[chunk] (ARGOS only) + Y[chunk*L+ypad]
 __host__ __device__ inline size_t chain_ws_reals(const ChainConst &cc)
 {
-    return (size_t)(cc.K - 1 + cc.chunk) + (cc.argos ? cc.chunk : 0) + (size_t)cc.chunk * cc.L + cc.ypad + 2 * IQ_TILE;
+    return (size_t)(cc.K - 1 + cc.chunk) + (cc.argos ? cc.chunk : 0) + (size_t)cc.chunk * cc.L + cc.ypad;
 }
 
 PDT_DEV void load_iq(const void *base, int pcm16, unsigned long long idx, real_t &a, real_t &b)
@@ -70,8 +71,28 @@ PDT_DEV void load_iq(const void *base, int pcm16, unsigned long long idx, real_t
     }
 }
 
+// What clock recovery -> Manchester -> ByteSync carry from symbol to symbol: kept in REGISTERS of the serial lane while a
+// chunk is walked (every field of the shared ChainState costs a 29-cycle LDS on the dependent path), stored back per chunk.
+struct BackState {
+    GardnerState gar; MMState mm; ManchesterState man; SyncState sync;
+    unsigned long long n_sym, n_bits;
+    uint32_t n_frames; int cur_frame;
+    uint32_t cur_bytes;                        // bytes already in the open frame (mirror of frames[cur_frame].n_bytes)
+};
+PDT_DEV void back_load(BackState &b, const ChainState &st, const pdt_frame *frames)
+{
+    b.gar = st.gar; b.mm = st.mm; b.man = st.man; b.sync = st.sync;
+    b.n_sym = st.n_sym; b.n_bits = st.n_bits; b.n_frames = st.n_frames; b.cur_frame = st.cur_frame;
+    b.cur_bytes = (st.cur_frame >= 0) ? frames[st.cur_frame].n_bytes : 0u;
+}
+PDT_DEV void back_store(ChainState &st, const BackState &b)
+{
+    st.gar = b.gar; st.mm = b.mm; st.man = b.man; st.sync = b.sync;
+    st.n_sym = b.n_sym; st.n_bits = b.n_bits; st.n_frames = b.n_frames; st.cur_frame = b.cur_frame;
+}
+
 // symbol -> Manchester -> ByteSync -> frame table; executed by the serial lane
-PDT_DEV void consume_symbol(ChainState &st, const ChainConst &cc, real_t sym, unsigned long long abs_interp_idx,
+PDT_DEV void consume_symbol(BackState &st, const ChainConst &cc, real_t sym, unsigned long long abs_interp_idx,
                             pdt_frame *frames, const pdt_traces *tr)
 {
     unsigned char bit;
@@ -81,7 +102,7 @@ PDT_DEV void consume_symbol(ChainState &st, const ChainConst &cc, real_t sym, un
     const int ev = sync_step(st.sync, cc.sync, bit, emit, byte, eol);
     if (emit && st.cur_frame >= 0) {
         pdt_frame &f = frames[st.cur_frame];
-        if (f.n_bytes < PDT_FRAME_MAX_BYTES) f.bytes[f.n_bytes++] = byte;
+        if (st.cur_bytes < PDT_FRAME_MAX_BYTES) { f.bytes[st.cur_bytes++] = byte; f.n_bytes = (uint8_t)st.cur_bytes; }
         if (eol) { f.complete = 1; st.cur_frame = -1; }
     } else if (eol) st.cur_frame = -1;
     if (ev != EV_NONE) {
@@ -90,13 +111,30 @@ PDT_DEV void consume_symbol(ChainState &st, const ChainConst &cc, real_t sym, un
             pdt_frame &f = frames[st.cur_frame];
             f.sample_index = abs_interp_idx; f.bit_index = (uint32_t)st.n_bits;
             f.inverse = (ev == EV_SYNC_INV); f.complete = 0; f.pad = 0;
-            f.n_bytes = (uint8_t)cc.prefix_bytes;
+            f.n_bytes = (uint8_t)cc.prefix_bytes; st.cur_bytes = (uint32_t)cc.prefix_bytes;
             if (cc.prefix_bytes) { f.bytes[0] = 0xED; f.bytes[1] = 0xE2; }
         } else st.cur_frame = -1;
         st.n_frames++;
     }
     st.n_bits++;
 }
+
+// The PLL block arrays double as the staging window of the other serial stages (they never run at the same time).
+constexpr int WS_REALS = (int)(sizeof(PllPipeSmem) / sizeof(real_t)) & ~3;
+constexpr int CLK_BACK = 768, CLK_WIN = 2560;            // clock recovery: look-back kept in front of every window
+static_assert(CLK_BACK + CLK_WIN <= WS_REALS, "clock-recovery window must fit the shared staging area");
+
+// chunk samples [lo, hi) from shared memory, everything else from the chunk buffer
+struct WindowView {
+    const real_t *win, *chunk; uint32_t lo, hi;
+    PDT_DEV real_t operator[](unsigned i) const { return (i >= lo && i < hi) ? win[i - lo] : chunk[i]; }
+};
+
+// cycle accounting of the exact engine (thread 0 of every CTA, summed over captures; read with pdt_debug_chain_prof):
+// [0] StaticGain  [1] PLL total  [2..6] its phases P, C, H, E, emit+control  [7] PLL blocks  [8] contradicted blocks
+// [9] FIR + history slide  [10] AGC (+squelch)  [11] clock recovery + Manchester + ByteSync  [12] whole capture  [13] samples
+// [14] PLL control (thread 0 between blocks; [6] is the emit alone)
+__device__ unsigned long long g_chain_prof[16];
 
 // ---------------------------------------------------------------------------------------------------
 // v1 chain kernel: exact-order serial loops on lane 0, FIR on all threads.
@@ -106,6 +144,8 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_chain_exact(const ChainArgs a
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ ChainState st;
     __shared__ real_t taps_s[PDT_MAX_TAPS];
+    __shared__ __align__(16) PllPipeSmem pll_blk;
+    real_t *const WS = reinterpret_cast<real_t *>(&pll_blk);
 
     const ChainConst &cc = args.cc;
     const int tid = threadIdx.x;
@@ -119,7 +159,6 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_chain_exact(const ChainArgs a
         real_t *Rext = ws;                                   // [K-1 + chunk]
         real_t *LOCK = Rext + (cc.K - 1 + cc.chunk);         // [chunk] (ARGOS)
         real_t *Y    = LOCK + (cc.argos ? cc.chunk : 0);     // [chunk*L + ypad]
-        real_t *IQT  = Y + (size_t)cc.chunk * cc.L + cc.ypad;     // [2*IQ_TILE]
         const unsigned long long n = args.n_samples ? args.n_samples[cap] : args.n_uniform;
         const unsigned long long first = (unsigned long long)cap * args.stride;
         pdt_frame *frames = args.frames + (size_t)cap * cc.max_frames;
@@ -145,54 +184,60 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_chain_exact(const ChainArgs a
         }
         __syncthreads();
         const unsigned long long in0 = st.in0;                              // absolute index of this call's first sample (0 outside live mode)
+        const bool need_norm = st.norm == 0;                                // no StaticGain override: measure it on the first chunk
+        unsigned long long pf[13] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // thread 0: [0..7] PLL phases/blocks, [8] gain [9] pll [10] fir [11] agc [12] back
+        const long long pf_begin = clock64();
 
         for (unsigned long long base = 0; base < n; base += cc.chunk) {
             const uint32_t m = (uint32_t)((n - base < cc.chunk) ? (n - base) : cc.chunk);
 
-            // ---- StaticGain on the first chunk (main.c:384-389) --------------------------------------
-            if (base == 0 && in0 == 0 && tid == 0 && st.norm == 0) {
-                real_t level; real_t a, b;
-                load_iq(args.iq, args.pcm16, first, a, b);
-                level = hypot_exact(a, b);
-                for (uint32_t i = 0; i < m; i++) {
-                    load_iq(args.iq, args.pcm16, first + i, a, b);
-                    level += hypot_exact(a, b);
-                    level /= 2.0;
-                }
-                st.norm = (real_t)1.0 / level;
-            }
-
-            // ---- PLL: tiles of IQ staged cooperatively, recurrence on lane 0 -------------------------
-            if (tid == 0) { pll_begin(st.pll, cc.pll); }
-            for (uint32_t t0 = 0; t0 < m; t0 += IQ_TILE) {
-                const uint32_t tn = (m - t0 < IQ_TILE) ? (m - t0) : IQ_TILE;
-                __syncthreads();
-                for (uint32_t i = tid; i < tn; i += CHAIN_THREADS) {
-                    real_t a, b;
-                    load_iq(args.iq, args.pcm16, first + base + t0 + i, a, b);
-                    IQT[2 * i] = a; IQT[2 * i + 1] = b;
-                }
-                __syncthreads();
-                if (tid == 0) {
-                    for (uint32_t i = 0; i < tn; i++) {
-                        const unsigned long long g = in0 + base + t0 + i;
-                        if (tr) {
-                            if (tr->pll_phase) reinterpret_cast<real_t *>(tr->pll_phase)[g] = st.pll.phase;
-                            if (tr->pll_freq)  reinterpret_cast<real_t *>(tr->pll_freq)[g]  = st.pll.freq;
-                        }
-                        real_t out, lock;
-                        pll_step(st.pll, cc.pll, IQT[2 * i], IQT[2 * i + 1], out, lock, g);
-                        Rext[cc.K - 1 + t0 + i] = out;
-                        if (cc.argos) LOCK[t0 + i] = lock;
-                        if (tr) {
-                            if (tr->pll_out) reinterpret_cast<real_t *>(tr->pll_out)[g] = out;
-                            if (tr->lock)    reinterpret_cast<real_t *>(tr->lock)[g] = lock;
+            long long pf_t = clock64();
+            // ---- StaticGain on the first chunk (main.c:384-389): magnitudes by all threads, the halving average on one -------
+            if (base == 0 && in0 == 0 && need_norm) {
+                real_t level = 0;
+                for (uint32_t t0 = 0; t0 < m; t0 += WS_REALS) {
+                    const uint32_t tn = (m - t0 < (uint32_t)WS_REALS) ? (m - t0) : (uint32_t)WS_REALS;
+                    for (uint32_t i = tid; i < tn; i += CHAIN_THREADS) {
+                        real_t a, b;
+                        load_iq(args.iq, args.pcm16, first + t0 + i, a, b);
+                        WS[i] = hypot_exact(a, b);
+                    }
+                    __syncthreads();
+                    if (tid == 0) {
+                        if (t0 == 0) level = WS[0];                      // AGC.c:58: the first sample primes the average (and is added again)
+                        for (uint32_t i = 0; i < tn; i++) {
+                            level += WS[i];
+                            level /= 2.0;
                         }
                     }
-                    st.avg_phase = st.pll.avg_phase;
+                    __syncthreads();
                 }
+                if (tid == 0) st.norm = (real_t)1.0 / level;
+            }
+
+            // ---- PLL: the whole CTA, block by block (pdt_pll_pipe.cuh); only the loop filter runs on one thread ----------
+            { const long long now = clock64(); pf[8] += now - pf_t; pf_t = now; }
+            if (tid == 0) { pll_begin(st.pll, cc.pll); }
+            __syncthreads();
+            {
+                const unsigned long long g0 = in0 + base, src0 = first + base;
+                pll_run_blocks(st.pll, cc.pll, m, g0, pll_blk,
+                    [&](unsigned long long i, real_t &a, real_t &b) { load_iq(args.iq, args.pcm16, src0 + i, a, b); },
+                    [&](unsigned long long i, real_t out, real_t lock, real_t ph_before, real_t fq_before) {
+                        Rext[cc.K - 1 + i] = out;
+                        if (cc.argos) LOCK[i] = lock;
+                        if (tr) {
+                            const unsigned long long g = g0 + i;
+                            if (tr->pll_phase) reinterpret_cast<real_t *>(tr->pll_phase)[g] = ph_before;
+                            if (tr->pll_freq)  reinterpret_cast<real_t *>(tr->pll_freq)[g]  = fq_before;
+                            if (tr->pll_out)   reinterpret_cast<real_t *>(tr->pll_out)[g] = out;
+                            if (tr->lock)      reinterpret_cast<real_t *>(tr->lock)[g] = lock;
+                        }
+                    }, pf);
+                if (tid == 0) st.avg_phase = st.pll.avg_phase;
             }
             __syncthreads();
+            { const long long now = clock64(); pf[9] += now - pf_t; pf_t = now; }
 
             // ---- FIR (all threads), exact summation order -------------------------------------------
             const unsigned long long j0 = st.fir_j;                     // absolute index of R[0] of this chunk
@@ -226,48 +271,100 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_chain_exact(const ChainArgs a
                 for (int q = 0; q < SLIDE; q++) { const int i = (int)tid + q * CHAIN_THREADS; if (i < cc.K - 1) Rext[i] = keep[q]; }
             }
 
-            // ---- AGC (+ squelch) then Gardner -> Manchester -> ByteSync on lane 0 ---------------------
+            // ---- AGC (+ squelch): windows of the chunk staged in shared memory, the gain recurrence on one thread ------------
+            { const long long now = clock64(); pf[10] += now - pf_t; pf_t = now; }
             if (tid == 0) {
                 st.fir_j = j0 + m;
                 if (!st.agc.init) { st.agc.init = 1; st.agc.gain = st.norm; }
-                for (uint32_t o = 0; o < n_out; o++) {
-                    real_t v = agc_step(st.agc, Y[o], cc.agc_attack, cc.agc_decay);
-                    if (cc.argos && LOCK[o] < cc.squelch) v = 0;                // AGC.c:24-46, ARGOS main.c:276
-                    Y[o] = v;
-                    if (tr && tr->agc) reinterpret_cast<real_t *>(tr->agc)[base * cc.L + o] = v;
+            }
+            for (uint32_t w0 = 0; w0 < n_out; w0 += WS_REALS) {
+                const uint32_t wn = (n_out - w0 < (uint32_t)WS_REALS) ? (n_out - w0) : (uint32_t)WS_REALS;
+                for (uint32_t k = tid; k < wn; k += CHAIN_THREADS) WS[k] = Y[w0 + k];
+                __syncthreads();
+                if (tid == 0) {
+                    AgcState ag = st.agc;
+                    uint32_t k = 0;
+                    for (; k + 4 <= wn; k += 4) {                        // inputs fetched ahead of the dependent gain chain
+                        const real_t x0 = WS[k], x1 = WS[k + 1], x2 = WS[k + 2], x3 = WS[k + 3];
+                        const real_t v0 = agc_step(ag, x0, cc.agc_attack, cc.agc_decay), v1 = agc_step(ag, x1, cc.agc_attack, cc.agc_decay);
+                        const real_t v2 = agc_step(ag, x2, cc.agc_attack, cc.agc_decay), v3 = agc_step(ag, x3, cc.agc_attack, cc.agc_decay);
+                        WS[k] = v0; WS[k + 1] = v1; WS[k + 2] = v2; WS[k + 3] = v3;
+                    }
+                    for (; k < wn; k++) WS[k] = agc_step(ag, WS[k], cc.agc_attack, cc.agc_decay);
+                    st.agc = ag;
                 }
-                gardner_begin(st.gar, cc.gardner_fs, cc.baud);
+                __syncthreads();
+                for (uint32_t k = tid; k < wn; k += CHAIN_THREADS) {
+                    real_t v = WS[k];
+                    if (cc.argos && LOCK[w0 + k] < cc.squelch) v = 0;            // AGC.c:24-46, ARGOS main.c:276
+                    Y[w0 + k] = v;
+                    if (tr && tr->agc) reinterpret_cast<real_t *>(tr->agc)[base * cc.L + w0 + k] = v;
+                }
+                __syncthreads();
+            }
+
+            // ---- clock recovery -> Manchester -> ByteSync on one thread; the chunk passes through shared memory in windows
+            //      with CLK_BACK samples of look-back (anything outside the window, e.g. the stale half-way index the reference
+            //      carries across a chunk boundary, is read from the chunk buffer itself) ------------------------------------
+            { const long long now = clock64(); pf[11] += now - pf_t; pf_t = now; }
+            BackState bk;
+            if (tid == 0) {
+                back_load(bk, st, frames);
+                gardner_begin(bk.gar, cc.gardner_fs, cc.baud);
+                if (cc.use_mm) mm_begin(bk.mm, cc.gardner_fs, cc.baud);              // MMClockRecovery.c:5-84 (the call the drivers keep commented out)
+            }
+            {
                 const unsigned long long ibase = (in0 + base) * (unsigned long long)cc.L;
-                if (cc.use_mm) {
-                    // MMClockRecovery.c:5-84 in the Gardner loop's place (the call the drivers keep commented out)
-                    mm_begin(st.mm, cc.gardner_fs, cc.baud);
-                    const real_t step_max = cc.gardner_fs / (cc.baud - cc.mm_range), step_min = cc.gardner_fs / (cc.baud + cc.mm_range);
-                    while (mm_rint(st.mm.next) < n_out) {
-                        real_t sym;
-                        const unsigned at = mm_step(st.mm, Y, step_min, step_max, cc.mm_kp, sym);
-                        if (tr && st.n_sym < tr->cap) {
-                            if (tr->sym)         reinterpret_cast<real_t *>(tr->sym)[st.n_sym] = sym;
-                            if (tr->gardner_idx) tr->gardner_idx[st.n_sym] = ibase + at;
+                const real_t step_max = cc.gardner_fs / (cc.baud - cc.mm_range), step_min = cc.gardner_fs / (cc.baud + cc.mm_range);
+                for (uint32_t w0 = 0; w0 < n_out; w0 += CLK_WIN) {
+                    const uint32_t w_hi = (n_out - w0 < (uint32_t)CLK_WIN) ? n_out : w0 + CLK_WIN;
+                    const uint32_t w_lo = (w0 > (uint32_t)CLK_BACK) ? w0 - CLK_BACK : 0u;
+                    __syncthreads();
+                    for (uint32_t k = w_lo + tid; k < w_hi; k += CHAIN_THREADS) WS[k - w_lo] = Y[k];
+                    __syncthreads();
+                    if (tid == 0) {
+                        const WindowView yv{WS, Y, w_lo, w_hi};
+                        if (cc.use_mm) {
+                            while (mm_rint(bk.mm.next) < w_hi) {
+                                real_t sym;
+                                const unsigned at = mm_step(bk.mm, yv, step_min, step_max, cc.mm_kp, sym);
+                                if (tr && bk.n_sym < tr->cap) {
+                                    if (tr->sym)         reinterpret_cast<real_t *>(tr->sym)[bk.n_sym] = sym;
+                                    if (tr->gardner_idx) tr->gardner_idx[bk.n_sym] = ibase + at;
+                                }
+                                bk.n_sym++;
+                                consume_symbol(bk, cc, sym, ibase + at, frames, tr);
+                            }
+                        } else {
+                            while (r_rint(bk.gar.next) < w_hi) {
+                                real_t sym, err;
+                                const unsigned at = gardner_step(bk.gar, yv, cc.g_range, cc.g_kp, sym, err);
+                                if (tr && bk.n_sym < tr->cap) {
+                                    if (tr->sym)         reinterpret_cast<real_t *>(tr->sym)[bk.n_sym] = sym;
+                                    if (tr->gardner_err) reinterpret_cast<real_t *>(tr->gardner_err)[bk.n_sym] = err;
+                                    if (tr->gardner_idx) tr->gardner_idx[bk.n_sym] = ibase + at;
+                                }
+                                bk.n_sym++;
+                                consume_symbol(bk, cc, sym, ibase + at, frames, tr);
+                            }
                         }
-                        st.n_sym++;
-                        consume_symbol(st, cc, sym, ibase + at, frames, tr);
                     }
-                    st.mm.next = st.mm.next - n_out;                             // :80
-                } else
-                while (r_rint(st.gar.next) < n_out) {
-                    real_t sym, err;
-                    const unsigned at = gardner_step(st.gar, Y, cc.g_range, cc.g_kp, sym, err);
-                    if (tr && st.n_sym < tr->cap) {
-                        if (tr->sym)         reinterpret_cast<real_t *>(tr->sym)[st.n_sym] = sym;
-                        if (tr->gardner_err) reinterpret_cast<real_t *>(tr->gardner_err)[st.n_sym] = err;
-                        if (tr->gardner_idx) tr->gardner_idx[st.n_sym] = ibase + at;
-                    }
-                    st.n_sym++;
-                    consume_symbol(st, cc, sym, ibase + at, frames, tr);
                 }
-                if (!cc.use_mm) st.gar.next = st.gar.next - n_out;               // :111
+                if (tid == 0) {
+                    if (cc.use_mm) bk.mm.next = bk.mm.next - n_out;                  // :80
+                    else           bk.gar.next = bk.gar.next - n_out;                // :111
+                    back_store(st, bk);
+                    pf[12] += clock64() - pf_t;
+                }
             }
             __syncthreads();
+        }
+        if (tid == 0) {
+            atomicAdd(&g_chain_prof[0], pf[8]); atomicAdd(&g_chain_prof[1], pf[9]);
+            for (int q = 0; q < 7; q++) atomicAdd(&g_chain_prof[2 + q], pf[q]);
+            atomicAdd(&g_chain_prof[9], pf[10]); atomicAdd(&g_chain_prof[10], pf[11]); atomicAdd(&g_chain_prof[11], pf[12]);
+            atomicAdd(&g_chain_prof[14], pf[7]);
+            atomicAdd(&g_chain_prof[12], (unsigned long long)(clock64() - pf_begin)); atomicAdd(&g_chain_prof[13], n);
         }
 
         if (tid == 0) {

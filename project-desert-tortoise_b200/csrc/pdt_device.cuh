@@ -224,6 +224,55 @@ PDT_DEV void pll_begin(PllState &s, const PllParams &p)
     s.sweep = 0.2 * (2.0 * PDT_PI / p.Fs);
 }
 
+// The pieces of one PLL sample, shared by the one-thread loop (pll_step) and the block-parallel runner (pdt_pll_pipe.cuh)
+// so that both execute the same statements.
+// loop filter + NCO advance, CarrierTrackingPLL.c:165-188
+PDT_DEV void pll_loop_core(real_t &phase, real_t &freq, real_t sample_phase, real_t alpha, real_t beta, real_t max_freq, real_t min_freq)
+{
+    real_t err;                                          // :165-170
+    if ((sample_phase - phase) > PDT_PI)        err = (sample_phase - phase) - 2 * PDT_PI;
+    else if ((sample_phase - phase) < -PDT_PI)  err = (sample_phase - phase) + 2 * PDT_PI;
+    else                                        err = sample_phase - phase;
+
+    freq  = freq + beta * err;                           // :174
+    phase = phase + freq + alpha * err;                  // :175
+    while (phase > 2 * PDT_PI)  phase = phase - 2.0 * PDT_PI;    // :178-182
+    while (phase < -2 * PDT_PI) phase = phase + 2.0 * PDT_PI;
+    if (freq > max_freq)      freq = max_freq;           // :185-188
+    else if (freq < min_freq) freq = min_freq;
+}
+
+PDT_DEV bool pll_noise_like(real_t avg_phase)
+{
+#if PDT_USE_FLOATS
+    return fabsf((float)(PDT_PI / 2.0 - avg_phase)) < 0.05;      // :232
+#else
+    return fabs(PDT_PI / 2.0 - avg_phase) < 0.05;                // :248
+#endif
+}
+
+// the acquisition sweep of a sample whose averaged phase looks like noise, :233-246
+PDT_DEV void pll_sweep_core(real_t &freq, real_t &sweep, real_t max_freq, real_t min_freq)
+{
+    freq = freq + sweep;
+    if (freq >= max_freq)       sweep = sweep * -1.0;
+    else if (freq <= min_freq)  sweep = sweep * -1.0;
+    else if (freq >= 0)         sweep = r_fabs(sweep);
+    else                        sweep = r_fabs(sweep) * -1.0;
+}
+
+// the lock latch, :266-274
+PDT_DEV void pll_latch(PllState &s, const PllParams &p, unsigned long long abs_index)
+{
+    s.lock_freq_hz = s.freq * p.Fs / (2.0 * PDT_PI);
+    s.stage = 2;
+    s.lock_sample = abs_index;
+    s.lock_event = 1;
+    const real_t bw = p.bw_track;
+    s.alpha = (4.0 * s.damp * bw) / (1.0 + 2.0 * s.damp * bw + bw * bw);
+    s.beta  = (4.0 * bw * bw) / (1.0 + 2.0 * s.damp * bw + bw * bw);
+}
+
 // one sample; `abs_index` = absolute sample index (for the lock record)
 PDT_DEV void pll_step(PllState &s, const PllParams &p, real_t a, real_t b, real_t &out, real_t &lock,
                       unsigned long long abs_index)
@@ -240,17 +289,7 @@ PDT_DEV void pll_step(PllState &s, const PllParams &p, real_t a, real_t b, real_
     s.avg_phase = s.avg_phase * (1.0 - avg_alpha) + avg_alpha * r_fabs(out_phase);   // :124
 
     const real_t sample_phase = arctan2_approx(b, a);    // :128
-    real_t err;                                          // :165-170
-    if ((sample_phase - s.phase) > PDT_PI)        err = (sample_phase - s.phase) - 2 * PDT_PI;
-    else if ((sample_phase - s.phase) < -PDT_PI)  err = (sample_phase - s.phase) + 2 * PDT_PI;
-    else                                          err = sample_phase - s.phase;
-
-    s.freq  = s.freq + s.beta * err;                     // :174
-    s.phase = s.phase + s.freq + s.alpha * err;          // :175
-    while (s.phase > 2 * PDT_PI)  s.phase = s.phase - 2.0 * PDT_PI;    // :178-182
-    while (s.phase < -2 * PDT_PI) s.phase = s.phase + 2.0 * PDT_PI;
-    if (s.freq > s.max_freq)      s.freq = s.max_freq;   // :185-188
-    else if (s.freq < s.min_freq) s.freq = s.min_freq;
+    pll_loop_core(s.phase, s.freq, sample_phase, s.alpha, s.beta, s.max_freq, s.min_freq);
 
     real_t nre = a, nim = b;                             // :193-220
     const real_t mag2 = nre * nre + nim * nim;
@@ -259,27 +298,8 @@ PDT_DEV void pll_step(PllState &s, const PllParams &p, real_t a, real_t b, real_
     s.locksig = s.locksig * (1.0 - p.lock_alpha) + p.lock_alpha * (nre * tr + nim * ti);
     lock = s.locksig;
 
-#if PDT_USE_FLOATS
-    const bool noise_like = fabsf((float)(PDT_PI / 2.0 - s.avg_phase)) < 0.05;      // :232
-#else
-    const bool noise_like = fabs(PDT_PI / 2.0 - s.avg_phase) < 0.05;                // :248
-#endif
-    if (noise_like && s.stage == 1) {
-        s.freq = s.freq + s.sweep;
-        if (s.freq >= s.max_freq)       s.sweep = s.sweep * -1.0;
-        else if (s.freq <= s.min_freq)  s.sweep = s.sweep * -1.0;
-        else if (s.freq >= 0)           s.sweep = r_fabs(s.sweep);
-        else                            s.sweep = r_fabs(s.sweep) * -1.0;
-    }
-    if (s.locksig > p.lock_thresh && s.stage == 1) {     // :266-274
-        s.lock_freq_hz = s.freq * p.Fs / (2.0 * PDT_PI);
-        s.stage = 2;
-        s.lock_sample = abs_index;
-        s.lock_event = 1;
-        const real_t bw = p.bw_track;
-        s.alpha = (4.0 * s.damp * bw) / (1.0 + 2.0 * s.damp * bw + bw * bw);
-        s.beta  = (4.0 * bw * bw) / (1.0 + 2.0 * s.damp * bw + bw * bw);
-    }
+    if (pll_noise_like(s.avg_phase) && s.stage == 1) pll_sweep_core(s.freq, s.sweep, s.max_freq, s.min_freq);
+    if (s.locksig > p.lock_thresh && s.stage == 1) pll_latch(s, p, abs_index);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -349,7 +369,9 @@ struct ManchesterState { unsigned clockmod; real_t cur, prev, prevprev; unsigned
 PDT_DEV void gardner_begin(GardnerState &s, int Fs, real_t baud) { if (!s.init) { s.step = Fs / baud; s.init = 1; } }
 
 // one symbol; returns the picked index, symbol value in `sym`, clamped error in `err`
-PDT_DEV unsigned gardner_step(GardnerState &s, const real_t *x, real_t range, real_t kp, real_t &sym, real_t &err)
+// `x`: anything indexable by an unsigned sample index (a pointer, or a window accessor)
+template <class X>
+PDT_DEV unsigned gardner_step(GardnerState &s, const X &x, real_t range, real_t kp, real_t &sym, real_t &err)
 {
     const unsigned at = (unsigned)(r_rint(s.next));
     const real_t cur = x[at];
@@ -377,7 +399,8 @@ PDT_DEV real_t mm_rint(real_t v)
 }
 PDT_DEV void mm_begin(MMState &s, int Fs, real_t baud) { if (!s.init) { s.step = Fs / (baud); s.init = 1; } }
 // one symbol at the current position (the caller checks mm_rint(next) < n first); returns the picked index
-PDT_DEV unsigned mm_step(MMState &s, const real_t *x, real_t step_min, real_t step_max, real_t kp, real_t &sym)
+template <class X>
+PDT_DEV unsigned mm_step(MMState &s, const X &x, real_t step_min, real_t step_max, real_t kp, real_t &sym)
 {
     const unsigned at = (unsigned)(mm_rint(s.next));
     const real_t cur = x[at];

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "pdt_common.cuh"
+#include "pdt_pll_pipe.cuh"
 #if PDT_USE_FLOATS
 #include "pdt_tiled.cuh"             // pll_track_step, agc_run_fast: the float-exact loop bodies the tiled engine is verified with
 #endif
@@ -70,6 +71,8 @@ void die(const char *what, cudaError_t e)
 }
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) die(#call, e_); } while (0)
 
+static int g_pll_stage_seen = 0;      // PLL stage after the last CarrierTrackPLL call (host copy: picks the kernel of the next call)
+
 __global__ void k_leg_reset(LegacyState *s)
 {
     *s = LegacyState();
@@ -100,20 +103,27 @@ __global__ void k_leg_static_gain(LegacyState *s, const real_t *iq, unsigned n, 
     s->ret = static_gain_serial(iq, n, desired);
 }
 
-__global__ void k_leg_pll(LegacyState *s, PllParams p, const real_t *iq, real_t *out, real_t *lock, unsigned n)
+// CarrierTrackPLL by one CTA, block by block (pdt_pll_pipe.cuh): the statements of the one-thread loop, only the loop filter
+// serial; acquisition and track mode, float and double.
+__global__ void __launch_bounds__(PP_B) k_leg_pll_blocks(LegacyState *s, PllParams p, const real_t *__restrict__ iq, real_t *__restrict__ out,
+                                                        real_t *__restrict__ lock, unsigned n)
 {
-    PllState st = s->pll;
-    st.lock_event = 0;
-    pll_begin(st, p);
-    for (unsigned i = 0; i < n; i++) {
-        real_t o, l;
-        pll_step(st, p, iq[2 * i], iq[2 * i + 1], o, l, st.samples_seen + i);
-        out[i] = o;
-        if (lock) lock[i] = l;
+    __shared__ PllState st;
+    __shared__ PllPipeSmem blk;
+    if (threadIdx.x == 0) {
+        st = s->pll;
+        st.lock_event = 0;
+        pll_begin(st, p);
     }
-    st.samples_seen += n;
-    s->pll = st;
-    s->ret = st.avg_phase;
+    __syncthreads();
+    pll_run_blocks(st, p, n, st.samples_seen, blk,
+        [&](unsigned long long i, real_t &a, real_t &b) { a = iq[2 * i]; b = iq[2 * i + 1]; },
+        [&](unsigned long long i, real_t o, real_t l, real_t, real_t) { out[i] = o; if (lock) lock[i] = l; });
+    if (threadIdx.x == 0) {
+        st.samples_seen += n;
+        s->pll = st;
+        s->ret = st.avg_phase;
+    }
 }
 
 #if PDT_USE_FLOATS
@@ -406,6 +416,7 @@ void pdt_legacy_reset(void)
 {
     ensure_ready();
     k_leg_reset<<<1, 1>>>(G.d_state); count_launch();
+    g_pll_stage_seen = 0;
     CK(cudaDeviceSynchronize());
     if (G.hist.p) cudaMemset(G.hist.p, 0, G.hist.cap);
     if (G.aux2.p) cudaMemset(G.aux2.p, 0, G.aux2.cap);
@@ -433,25 +444,24 @@ DECIMAL_TYPE CarrierTrackPLL(DECIMAL_TYPE *complexDataIn, DECIMAL_TYPE *realData
     real_t *d_out = (real_t *)G.out.ensure(sizeof(real_t) * (n + 1));
     real_t *d_lock = lockSignalStreamOut ? (real_t *)G.aux.ensure(sizeof(real_t) * (n + 1)) : nullptr;
     if (n) CK(cudaMemcpy(d_in, complexDataIn, sizeof(real_t) * 2 * n, cudaMemcpyHostToDevice));
+    // locked float stream: the three-stage pipeline (k_leg_pll_pipe, track mode only; it wraps the phase once per sample, valid
+    // while a step cannot move it by 2π, i.e. for any sane loop bandwidth); everything else: the block runner
+    bool piped = false;
 #if PDT_USE_FLOATS
-    // the pipelined kernel wraps the phase once per sample (pdt_tiled.cuh::pll_track_step): valid while a step cannot move it
-    // by 2π, i.e. for any sane loop bandwidth; otherwise the one-thread loop with the reference's while-loops
-    bool one_wrap = false;
-    {
+    if (g_pll_stage_seen == 2) {
         PllState ps; pll_reset(ps); pll_begin(ps, p);
         const double bw = p.bw_track, damp = ps.damp;
         const double at = (4.0 * damp * bw) / (1.0 + 2.0 * damp * bw + bw * bw), bt = (4.0 * bw * bw) / (1.0 + 2.0 * damp * bw + bw * bw);
-        one_wrap = ((double)ps.max_freq + 10.0 * ((double)ps.alpha + (double)ps.beta) < 6.0) && ((double)ps.max_freq + 10.0 * (at + bt) < 6.0);
+        piped = (double)ps.max_freq + 10.0 * (at + bt) < 6.0;
     }
-    if (one_wrap) k_leg_pll_pipe<<<1, LP_THREADS>>>(G.d_state, p, d_in, d_out, d_lock, nSamples);
-    else          k_leg_pll<<<1, 1>>>(G.d_state, p, d_in, d_out, d_lock, nSamples);
-    count_launch();
-#else
-    k_leg_pll<<<1, 1>>>(G.d_state, p, d_in, d_out, d_lock, nSamples); count_launch();
+    if (piped) k_leg_pll_pipe<<<1, LP_THREADS>>>(G.d_state, p, d_in, d_out, d_lock, nSamples);
 #endif
+    if (!piped) k_leg_pll_blocks<<<1, PP_B>>>(G.d_state, p, d_in, d_out, d_lock, nSamples);
+    count_launch();
     if (n) CK(cudaMemcpy(realDataOut, d_out, sizeof(real_t) * n, cudaMemcpyDeviceToHost));
     if (n && d_lock) CK(cudaMemcpy(lockSignalStreamOut, d_lock, sizeof(real_t) * n, cudaMemcpyDeviceToHost));
     LegacyState h = fetch_state();
+    g_pll_stage_seen = h.pll.stage;
     if (h.pll.lock_event) printf(" : PLL locked at %0.2fHz\n", h.pll.lock_freq_hz);      // CarrierTrackingPLL.c:269
     return h.ret;
 }
