@@ -299,9 +299,9 @@ int         pdt_timeline(pdt_ctx *ctx, const char **names, int *groups, float *e
  * [0] steps, [1] step cycles, [2] core-lane busy, [3] EMA-lane busy, [4] helper busy, [5] decision phase, [6] epochs. */
 int         pdt_debug_acq_prof(uint64_t out[8], int reset);
 /* cycle accounting of the exact engine (pdt_chain_kernel.cuh g_chain_prof; thread 0 of every CTA, summed over captures since the
- * last reset): [0] StaticGain [1] PLL [2..6] PLL phases P, C, H, E, emit+control [7] PLL blocks [8] contradicted blocks [9] FIR
- * [10] AGC [11] clock recovery + bits [12] whole capture [13] samples.  Diagnostics only. */
-int         pdt_debug_chain_prof(uint64_t out[16], int reset);
+ * last reset): [0] StaticGain [1] PLL [2] its P phase alone [3] C || E [4] H || P [5] C busy [6] E busy [7] PLL blocks [8] contradicted
+ * blocks [9] FIR [10] AGC [11] clock recovery + bits [12] whole capture [13] samples [14] PLL control [15] its work alone [16] lock-EMA thread busy.  Diagnostics only. */
+int         pdt_debug_chain_prof(uint64_t out[20], int reset);
 
 /* Number of kernels launched by this library since load (bench.py reports it as gpu_launches). */
 uint64_t    pdt_launch_count(void);

@@ -966,14 +966,14 @@ int pdt_timeline(pdt_ctx *c, const char **names, int *groups, float *end_ms, int
 #endif
 }
 
-int pdt_debug_chain_prof(uint64_t out[16], int reset)
+int pdt_debug_chain_prof(uint64_t out[20], int reset)
 {
     if (!out) return fail(PDT_EINVAL, "bad arguments");
-    unsigned long long h[16];
+    unsigned long long h[20];
     PDT_CUDA(cudaDeviceSynchronize());
     PDT_CUDA(cudaMemcpyFromSymbol(h, g_chain_prof, sizeof h));
-    for (int i = 0; i < 16; i++) out[i] = h[i];
-    if (reset) { unsigned long long z[16] = {}; PDT_CUDA(cudaMemcpyToSymbol(g_chain_prof, z, sizeof z)); }
+    for (int i = 0; i < 20; i++) out[i] = h[i];
+    if (reset) { unsigned long long z[20] = {}; PDT_CUDA(cudaMemcpyToSymbol(g_chain_prof, z, sizeof z)); }
     return PDT_OK;
 }
 

@@ -51,7 +51,7 @@ struct ChainArgs {
 };
 
 constexpr int CHAIN_THREADS = 256;
-static_assert(CHAIN_THREADS == PP_B, "the PLL block runner gives every thread of the CTA one sample of a block");
+static_assert(CHAIN_THREADS == PP_THREADS, "the PLL block runner assigns its roles by thread index");
 
 // reals needed: Rext[K-1+chunk] + LOCK[chunk] (ARGOS only) + Y[chunk*L+ypad]
 __host__ __device__ inline size_t chain_ws_reals(const ChainConst &cc)
@@ -121,7 +121,7 @@ PDT_DEV void consume_symbol(BackState &st, const ChainConst &cc, real_t sym, uns
 
 // The PLL block arrays double as the staging window of the other serial stages (they never run at the same time).
 constexpr int WS_REALS = (int)(sizeof(PllPipeSmem) / sizeof(real_t)) & ~3;
-constexpr int CLK_BACK = 768, CLK_WIN = 2560;            // clock recovery: look-back kept in front of every window
+constexpr int CLK_BACK = 512, CLK_WIN = 2560;            // clock recovery: look-back kept in front of every window
 static_assert(CLK_BACK + CLK_WIN <= WS_REALS, "clock-recovery window must fit the shared staging area");
 
 // chunk samples [lo, hi) from shared memory, everything else from the chunk buffer
@@ -131,10 +131,10 @@ struct WindowView {
 };
 
 // cycle accounting of the exact engine (thread 0 of every CTA, summed over captures; read with pdt_debug_chain_prof):
-// [0] StaticGain  [1] PLL total  [2..6] its phases P, C, H, E, emit+control  [7] PLL blocks  [8] contradicted blocks
+// [0] StaticGain  [1] PLL total  [2] its P alone (prologue, restarts)  [3] C ‖ E  [4] H ‖ P  [5] C busy  [6] E busy  [7] PLL blocks  [8] contradicted blocks
 // [9] FIR + history slide  [10] AGC (+squelch)  [11] clock recovery + Manchester + ByteSync  [12] whole capture  [13] samples
-// [14] PLL control (thread 0 between blocks; [6] is the emit alone)
-__device__ unsigned long long g_chain_prof[16];
+// [14] PLL control (commit / roll back between blocks)  [15] its work alone  [16] lock-EMA thread busy
+__device__ unsigned long long g_chain_prof[20];
 
 // ---------------------------------------------------------------------------------------------------
 // v1 chain kernel: exact-order serial loops on lane 0, FIR on all threads.
@@ -185,7 +185,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_chain_exact(const ChainArgs a
         __syncthreads();
         const unsigned long long in0 = st.in0;                              // absolute index of this call's first sample (0 outside live mode)
         const bool need_norm = st.norm == 0;                                // no StaticGain override: measure it on the first chunk
-        unsigned long long pf[13] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // thread 0: [0..7] PLL phases/blocks, [8] gain [9] pll [10] fir [11] agc [12] back
+        unsigned long long pf[15] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};   // thread 0: [0..9] PLL phases/blocks, [10] gain [11] pll [12] fir [13] agc [14] back
         const long long pf_begin = clock64();
 
         for (unsigned long long base = 0; base < n; base += cc.chunk) {
@@ -216,28 +216,30 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_chain_exact(const ChainArgs a
             }
 
             // ---- PLL: the whole CTA, block by block (pdt_pll_pipe.cuh); only the loop filter runs on one thread ----------
-            { const long long now = clock64(); pf[8] += now - pf_t; pf_t = now; }
+            { const long long now = clock64(); pf[10] += now - pf_t; pf_t = now; }
             if (tid == 0) { pll_begin(st.pll, cc.pll); }
             __syncthreads();
             {
                 const unsigned long long g0 = in0 + base, src0 = first + base;
                 pll_run_blocks(st.pll, cc.pll, m, g0, pll_blk,
                     [&](unsigned long long i, real_t &a, real_t &b) { load_iq(args.iq, args.pcm16, src0 + i, a, b); },
-                    [&](unsigned long long i, real_t out, real_t lock, real_t ph_before, real_t fq_before) {
+                    [&](unsigned long long i, real_t out, real_t ph_before, real_t fq_before) {
                         Rext[cc.K - 1 + i] = out;
-                        if (cc.argos) LOCK[i] = lock;
                         if (tr) {
                             const unsigned long long g = g0 + i;
                             if (tr->pll_phase) reinterpret_cast<real_t *>(tr->pll_phase)[g] = ph_before;
                             if (tr->pll_freq)  reinterpret_cast<real_t *>(tr->pll_freq)[g]  = fq_before;
                             if (tr->pll_out)   reinterpret_cast<real_t *>(tr->pll_out)[g] = out;
-                            if (tr->lock)      reinterpret_cast<real_t *>(tr->lock)[g] = lock;
                         }
+                    },
+                    [&](unsigned long long i, real_t lock) {
+                        if (cc.argos) LOCK[i] = lock;
+                        if (tr && tr->lock) reinterpret_cast<real_t *>(tr->lock)[g0 + i] = lock;
                     }, pf);
                 if (tid == 0) st.avg_phase = st.pll.avg_phase;
             }
             __syncthreads();
-            { const long long now = clock64(); pf[9] += now - pf_t; pf_t = now; }
+            { const long long now = clock64(); pf[11] += now - pf_t; pf_t = now; }
 
             // ---- FIR (all threads), exact summation order -------------------------------------------
             const unsigned long long j0 = st.fir_j;                     // absolute index of R[0] of this chunk
@@ -272,7 +274,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_chain_exact(const ChainArgs a
             }
 
             // ---- AGC (+ squelch): windows of the chunk staged in shared memory, the gain recurrence on one thread ------------
-            { const long long now = clock64(); pf[10] += now - pf_t; pf_t = now; }
+            { const long long now = clock64(); pf[12] += now - pf_t; pf_t = now; }
             if (tid == 0) {
                 st.fir_j = j0 + m;
                 if (!st.agc.init) { st.agc.init = 1; st.agc.gain = st.norm; }
@@ -286,9 +288,24 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_chain_exact(const ChainArgs a
                     uint32_t k = 0;
                     for (; k + 4 <= wn; k += 4) {                        // inputs fetched ahead of the dependent gain chain
                         const real_t x0 = WS[k], x1 = WS[k + 1], x2 = WS[k + 2], x3 = WS[k + 3];
-                        const real_t v0 = agc_step(ag, x0, cc.agc_attack, cc.agc_decay), v1 = agc_step(ag, x1, cc.agc_attack, cc.agc_decay);
-                        const real_t v2 = agc_step(ag, x2, cc.agc_attack, cc.agc_decay), v3 = agc_step(ag, x3, cc.agc_attack, cc.agc_decay);
-                        WS[k] = v0; WS[k + 1] = v1; WS[k + 2] = v2; WS[k + 3] = v3;
+                        // AGC.c:98-131 in its common regime — decay branch, no clamp: gain' = gain - (|x·gain| - 1)·decay, four
+                        // dependent operations per sample — with the conditions of the other branches evaluated beside the
+                        // chain; a group in which any of them holds is redone by the general step from the saved gain
+                        const real_t g_in = ag.gain;
+                        real_t g = g_in;
+                        bool other = false;
+                        const real_t v0 = x0 * g; { const real_t e = r_fabs(v0) - (real_t)1.0; other |= r_fabs(e) > g; g = g - e * cc.agc_decay; other |= (g < 0.0) | (g > (real_t)5000); }
+                        const real_t v1 = x1 * g; { const real_t e = r_fabs(v1) - (real_t)1.0; other |= r_fabs(e) > g; g = g - e * cc.agc_decay; other |= (g < 0.0) | (g > (real_t)5000); }
+                        const real_t v2 = x2 * g; { const real_t e = r_fabs(v2) - (real_t)1.0; other |= r_fabs(e) > g; g = g - e * cc.agc_decay; other |= (g < 0.0) | (g > (real_t)5000); }
+                        const real_t v3 = x3 * g; { const real_t e = r_fabs(v3) - (real_t)1.0; other |= r_fabs(e) > g; g = g - e * cc.agc_decay; other |= (g < 0.0) | (g > (real_t)5000); }
+                        if (!other) {
+                            ag.gain = g;
+                            WS[k] = v0; WS[k + 1] = v1; WS[k + 2] = v2; WS[k + 3] = v3;
+                        } else {
+                            ag.gain = g_in;
+                            WS[k] = agc_step(ag, x0, cc.agc_attack, cc.agc_decay); WS[k + 1] = agc_step(ag, x1, cc.agc_attack, cc.agc_decay);
+                            WS[k + 2] = agc_step(ag, x2, cc.agc_attack, cc.agc_decay); WS[k + 3] = agc_step(ag, x3, cc.agc_attack, cc.agc_decay);
+                        }
                     }
                     for (; k < wn; k++) WS[k] = agc_step(ag, WS[k], cc.agc_attack, cc.agc_decay);
                     st.agc = ag;
@@ -306,7 +323,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_chain_exact(const ChainArgs a
             // ---- clock recovery -> Manchester -> ByteSync on one thread; the chunk passes through shared memory in windows
             //      with CLK_BACK samples of look-back (anything outside the window, e.g. the stale half-way index the reference
             //      carries across a chunk boundary, is read from the chunk buffer itself) ------------------------------------
-            { const long long now = clock64(); pf[11] += now - pf_t; pf_t = now; }
+            { const long long now = clock64(); pf[13] += now - pf_t; pf_t = now; }
             BackState bk;
             if (tid == 0) {
                 back_load(bk, st, frames);
@@ -354,16 +371,16 @@ __global__ void __launch_bounds__(CHAIN_THREADS) k_chain_exact(const ChainArgs a
                     if (cc.use_mm) bk.mm.next = bk.mm.next - n_out;                  // :80
                     else           bk.gar.next = bk.gar.next - n_out;                // :111
                     back_store(st, bk);
-                    pf[12] += clock64() - pf_t;
+                    pf[14] += clock64() - pf_t;
                 }
             }
             __syncthreads();
         }
         if (tid == 0) {
-            atomicAdd(&g_chain_prof[0], pf[8]); atomicAdd(&g_chain_prof[1], pf[9]);
+            atomicAdd(&g_chain_prof[0], pf[10]); atomicAdd(&g_chain_prof[1], pf[11]);
             for (int q = 0; q < 7; q++) atomicAdd(&g_chain_prof[2 + q], pf[q]);
-            atomicAdd(&g_chain_prof[9], pf[10]); atomicAdd(&g_chain_prof[10], pf[11]); atomicAdd(&g_chain_prof[11], pf[12]);
-            atomicAdd(&g_chain_prof[14], pf[7]);
+            atomicAdd(&g_chain_prof[9], pf[12]); atomicAdd(&g_chain_prof[10], pf[13]); atomicAdd(&g_chain_prof[11], pf[14]);
+            atomicAdd(&g_chain_prof[14], pf[7]); atomicAdd(&g_chain_prof[15], pf[8]); atomicAdd(&g_chain_prof[16], pf[9]);
             atomicAdd(&g_chain_prof[12], (unsigned long long)(clock64() - pf_begin)); atomicAdd(&g_chain_prof[13], n);
         }
 

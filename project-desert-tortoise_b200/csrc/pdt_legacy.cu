@@ -105,7 +105,7 @@ __global__ void k_leg_static_gain(LegacyState *s, const real_t *iq, unsigned n, 
 
 // CarrierTrackPLL by one CTA, block by block (pdt_pll_pipe.cuh): the statements of the one-thread loop, only the loop filter
 // serial; acquisition and track mode, float and double.
-__global__ void __launch_bounds__(PP_B) k_leg_pll_blocks(LegacyState *s, PllParams p, const real_t *__restrict__ iq, real_t *__restrict__ out,
+__global__ void __launch_bounds__(PP_THREADS) k_leg_pll_blocks(LegacyState *s, PllParams p, const real_t *__restrict__ iq, real_t *__restrict__ out,
                                                         real_t *__restrict__ lock, unsigned n)
 {
     __shared__ PllState st;
@@ -118,7 +118,8 @@ __global__ void __launch_bounds__(PP_B) k_leg_pll_blocks(LegacyState *s, PllPara
     __syncthreads();
     pll_run_blocks(st, p, n, st.samples_seen, blk,
         [&](unsigned long long i, real_t &a, real_t &b) { a = iq[2 * i]; b = iq[2 * i + 1]; },
-        [&](unsigned long long i, real_t o, real_t l, real_t, real_t) { out[i] = o; if (lock) lock[i] = l; });
+        [&](unsigned long long i, real_t o, real_t, real_t) { out[i] = o; },
+        [&](unsigned long long i, real_t l) { if (lock) lock[i] = l; });
     if (threadIdx.x == 0) {
         st.samples_seen += n;
         s->pll = st;
@@ -456,7 +457,7 @@ DECIMAL_TYPE CarrierTrackPLL(DECIMAL_TYPE *complexDataIn, DECIMAL_TYPE *realData
     }
     if (piped) k_leg_pll_pipe<<<1, LP_THREADS>>>(G.d_state, p, d_in, d_out, d_lock, nSamples);
 #endif
-    if (!piped) k_leg_pll_blocks<<<1, PP_B>>>(G.d_state, p, d_in, d_out, d_lock, nSamples);
+    if (!piped) k_leg_pll_blocks<<<1, PP_THREADS>>>(G.d_state, p, d_in, d_out, d_lock, nSamples);
     count_launch();
     if (n) CK(cudaMemcpy(realDataOut, d_out, sizeof(real_t) * n, cudaMemcpyDeviceToHost));
     if (n && d_lock) CK(cudaMemcpy(lockSignalStreamOut, d_lock, sizeof(real_t) * n, cudaMemcpyDeviceToHost));

@@ -2,22 +2,25 @@
 // (pdt_device.cuh::pll_step, CarrierTrackingPLL.c:102-275), float and double builds, acquisition and track mode alike.
 //
 // One thread walking pll_step spends ~1 000 (float) to ~3 000 (double) cycles per sample on a dependent instruction
-// stream of which only the loop filter (:165-188, ~100 cycles) is a true recurrence.  Everything else either does not
-// depend on the loop state (first-order atan2 of the sample, its Q_rsqrt normalisation) or depends on it only through
-// the NCO phase of the same sample (sincos, derotation, the two averaged terms).  The loop state is fed back from those
-// only through two booleans per sample: "averaged phase looks like noise" (→ sweep the frequency, :232-246) and
-// "lock signal above threshold" (→ latch, :266-274).  So a block of up to PP_B samples runs in four phases:
+// stream of which only the loop filter (:165-188) is a true recurrence.  Everything else either does not depend on the
+// loop state (first-order atan2 of the sample, its Q_rsqrt normalisation) or depends on it only through the NCO phase
+// of the same sample (sincos, derotation, the two averaged terms).  The loop state is fed back from those only through
+// two booleans per sample: "averaged phase looks like noise" (→ sweep the frequency, :232-246) and "lock signal above
+// threshold" (→ latch, :266-274).  The call is therefore cut into blocks of up to PP_B samples and each block goes
+// through
 //
-//   P  all threads   sample k: load, sample phase, normalised sample            (state-independent)
-//   C  thread 0      loop filter over the block, keeping the state BEFORE every sample, ASSUMING the sweep flag keeps
-//                    the value it had after the previous sample and the latch does not fire
-//   H  all threads   sample k: sincos of its NCO phase, derotation, output, the two EMA terms
-//   E  threads 0/32  the two EMAs in order; each stops at the first sample that contradicts the assumption
+//   P  one thread per sample   load, sample phase, normalised sample                     (state-independent)
+//   C  thread 0                loop filter over the block, keeping the state BEFORE every sample, ASSUMING the sweep flag
+//                              keeps the value it had and the latch does not fire
+//   H  one thread per sample   sincos of its NCO phase, derotation, output, the two EMA terms
+//   E  threads 32 / 64         the two EMAs in order; each stops at the first sample that contradicts the assumption
 //
-// If sample j contradicts it, samples ≤ j are exact as computed (their phases depend on the flags of samples < j only):
-// the state before j is restored, sample j's filter step repeated with its actual flag, the latch applied, and the next
-// block starts at j + 1 — short at first, doubling while the assumption holds.  In track mode nothing is assumed.
-// Nothing here is approximate: every value is produced by the same statement as in pll_step.
+// software-pipelined over two buffers:  step k runs  C(block k) ‖ E(block k-1),  then  H(block k) ‖ P(block k+1).
+// If sample j of block k-1 contradicts the assumption, its samples ≤ j are exact as computed (their phases depend on the
+// flags of samples < j only): the loop state before j is restored, sample j's filter step repeated with its actual flag,
+// the latch applied, block k dropped, and the pipeline restarts at j + 1 — with short blocks at first, doubling while
+// the assumption holds.  In track mode nothing is assumed.  Nothing here is approximate: every value is produced by the
+// same statement as in pll_step (or by a select form of it that is bit-identical under a stated condition, below).
 #pragma once
 
 #include "pdt_device.cuh"
@@ -27,32 +30,37 @@
 
 namespace pdt {
 
-// Branch-free forms of pll_loop_core / pll_sweep_core (selects instead of if-chains and while-loops: ~65 (float) / ~100
-// (double) cycles per sample against ~320 for the branchy form, tools/chain_prof.py).  Bit-identical WHILE ONE 2π WRAP PER
-// SAMPLE SUFFICES, i.e. |Δphase| <= max_freq + |sweep| + (alpha + beta)·π < 4 (and, float build, the wrapped values stay
-// inside [3, 10.5], the range tests/test_tiled_math.py checks the float-only wrap forms over): pll_fast_ok() — the caller
-// falls back to the reference-shaped functions otherwise.
+// Branch-free forms of pll_loop_core / pll_sweep_core (selects instead of if-chains and while-loops: ~320 cycles per
+// sample for the branchy form, tools/chain_prof.py).  Bit-identical WHILE ONE 2π WRAP PER SAMPLE SUFFICES, i.e.
+// |Δphase| <= max_freq + |sweep| + (alpha + beta)·π < 4 (and, float build, the wrapped values stay inside [3, 10.5], the
+// range tests/test_tiled_math.py checks the float-only wrap forms over): pll_fast_ok() — otherwise the runner uses the
+// reference-shaped functions.
 PDT_DEV bool pll_fast_ok(const PllState &s)
 {
     return (double)s.max_freq + 10.0 * ((double)s.alpha + (double)s.beta) < 4.0 && (double)s.min_freq == -(double)s.max_freq;
 }
 
 #if PDT_USE_FLOATS
-PDT_DEV void pll_loop_fast(float &phase, float &freq, float sp, const tiled::TrackConst &k) { tiled::pll_track_step(phase, freq, sp, k); }
+typedef tiled::TrackConst PllLoopConst;
+PDT_DEV void pll_loop_fast(float &phase, float &freq, float sp, const PllLoopConst &k) { tiled::pll_track_step(phase, freq, sp, k); }
 #else
-namespace tiled { struct TrackConst { double alpha, beta, max_freq, min_freq; }; }
-PDT_DEV void pll_loop_fast(double &phase, double &freq, double sp, const tiled::TrackConst &k)
+struct PllLoopConst { double alpha, beta, max_freq, min_freq; };
+PDT_DEV void pll_loop_fast(double &phase, double &freq, double sp, const PllLoopConst &k)
 {
+    // all comparisons of a stage are taken on the same value, so they issue side by side; a value that was wrapped down
+    // (it was > π resp. > 2π) cannot satisfy the opposite condition afterwards, so one select chain equals the if-chains
     const double d = sp - phase;                                      // :165-170
-    double err = d;
-    err = (d < -PDT_PI) ? d + 2 * PDT_PI : err;
-    err = (d > PDT_PI) ? d - 2 * PDT_PI : err;
-    double f = freq + k.beta * err;                                   // :174
-    double ph = phase + f + k.alpha * err;                            // :175
-    ph = (ph > 2 * PDT_PI) ? ph - 2.0 * PDT_PI : ph;                  // :178-182, one trip each
-    ph = (ph < -2 * PDT_PI) ? ph + 2.0 * PDT_PI : ph;
-    f = (f > k.max_freq) ? k.max_freq : ((f < k.min_freq) ? k.min_freq : f);     // :185-188
-    phase = ph; freq = f;
+    const double d_dn = d - 2 * PDT_PI, d_up = d + 2 * PDT_PI;
+    double err = (d < -PDT_PI) ? d_up : d;
+    err = (d > PDT_PI) ? d_dn : err;
+    const double f = freq + k.beta * err;                             // :174
+    const double p0 = phase + f + k.alpha * err;                      // :175
+    const double p_dn = p0 - 2.0 * PDT_PI, p_up = p0 + 2.0 * PDT_PI;  // :178-182, one trip each
+    double ph = (p0 < -2 * PDT_PI) ? p_up : p0;
+    ph = (p0 > 2 * PDT_PI) ? p_dn : ph;
+    double fc = (f < k.min_freq) ? k.min_freq : f;                    // :185-188
+    fc = (f > k.max_freq) ? k.max_freq : fc;
+    phase = ph; freq = fc;
 }
 #endif
 
@@ -65,161 +73,233 @@ PDT_DEV void pll_sweep_fast(real_t &freq, real_t &sweep, real_t max_freq, real_t
     freq = f2; sweep = s2;
 }
 
-constexpr int PP_B = 256;            // samples per block = threads of the CTA that runs it
+constexpr int PP_B = 128;            // samples per block
+constexpr int PP_THREADS = 256;      // threads of the CTA that runs it: 0..127 H (and C / E on 0, 32, 64), 128..255 P
 constexpr int PP_B_MIN = 8;          // block length right after a contradicted assumption
 
-struct PllPipeSmem {
+struct PllBlockBuf {
     real_t pa[PP_B], pb[PP_B], sp[PP_B], nre[PP_B], nim[PP_B];   // P: inputs that do not depend on the loop
     real_t ph[PP_B], fq[PP_B], sw[PP_B];                         // C: loop state BEFORE each sample
-    real_t out[PP_B], at[PP_B], lt[PP_B];                        // H: derotated output, EMA terms
+    real_t at[PP_B], lt[PP_B];                                   // H: the two EMA terms
     real_t av[PP_B], lk[PP_B];                                   // E: EMA values AFTER each sample
-    real_t end_phase, end_freq, end_sweep;
-    int    ja, jl;                                               // first contradicted sweep flag / first latch (block length if none)
+};
+struct PllPipeSmem {
+    PllBlockBuf b[2];
+    int ja, jl;                      // first contradicted sweep flag / first latch of the block E just walked (its length if none)
+    int j;                           // control's verdict on that block: its first contradicted sample, or its length
+    int guess;                       // the sweep flag C assumes
+    unsigned long long prof_c, prof_e, prof_l;
 };
 
-// `load(i, a, b)`: sample i of this call;  `emit(i, out, lock, phase_before, freq_before)`: results of sample i (called by
-// one thread per sample, any order inside a block, each sample exactly once with its final values).
-// `s` lives in shared memory; all CTA threads call this with identical arguments (blockDim.x == PP_B).
-// `pf` (optional, thread 0 only): cycle accounting [0] P, [1] C, [2] H, [3] E, [4] emit, [5] blocks, [6] contradicted blocks, [7] control.
-template <class Load, class Emit>
+// `load(i, a, b)`: sample i of this call.  `emit(i, out, phase_before, freq_before)` (one thread per sample) and
+// `emit_lock(i, lock)` (one thread, in order) store the results of sample i; a sample may be emitted more than once, the
+// last time with its final values.  `s` lives in shared memory; all PP_THREADS threads call this with identical arguments.
+// `pf` (optional, thread 0 only): cycle accounting [0] P alone (prologue, restarts) [1] C ‖ E [2] H ‖ P [3] C busy [4] E busy
+// [5] blocks [6] contradicted blocks [7] control (with its barrier) [8] control, thread 0's work alone [9] lock-EMA thread busy.
+template <class Load, class Emit, class EmitLock>
 __device__ __forceinline__ void pll_run_blocks(PllState &s, const PllParams &p, unsigned long long n, unsigned long long abs0, PllPipeSmem &S,
-                                               Load load, Emit emit, unsigned long long *pf = nullptr)
+                                               Load load, Emit emit, EmitLock emit_lock, unsigned long long *pf = nullptr)
 {
     const int tid = threadIdx.x;
     const real_t avg_alpha = 0.00005;
-    int cur = PP_B;
-    unsigned long long i = 0;
-    while (i < n) {
-        const int cnt = (int)((n - i < (unsigned long long)cur) ? (n - i) : (unsigned long long)cur);
-        const bool acq = s.stage == 1;
-        const bool guess = acq && pll_noise_like(s.avg_phase);
-        const long long t0 = clock64();
-        // ---- P ----------------------------------------------------------------------------------------------------
-        if (tid < cnt) {
+
+    auto phase_P = [&](PllBlockBuf &B, unsigned long long i0, int cnt) {          // threads 128..255
+        const int k = tid - PP_B;
+        if (k >= 0 && k < cnt) {
             real_t a, b;
-            load(i + tid, a, b);
-            S.pa[tid] = a; S.pb[tid] = b;
-            S.sp[tid] = arctan2_approx(b, a);                    // :128
+            load(i0 + k, a, b);
+            B.pa[k] = a; B.pb[k] = b;
+            B.sp[k] = arctan2_approx(b, a);                      // :128
             real_t nre = a, nim = b;                             // :193-218
             const real_t mag2 = nre * nre + nim * nim;
             const real_t inv  = q_rsqrt((float)mag2);
             nre *= inv; nim *= inv;
-            S.nre[tid] = nre; S.nim[tid] = nim;
+            B.nre[k] = nre; B.nim[k] = nim;
         }
-        __syncthreads();
-        const long long t1 = clock64();
-        // ---- C ----------------------------------------------------------------------------------------------------
+    };
+
+    int a = 0, cur = PP_B;
+    unsigned long long iT = 0, iP = 0;
+    int cntT = (int)((n < (unsigned long long)cur) ? n : (unsigned long long)cur), cntP = 0;
+    bool have_prev = false;
+    long long tq = clock64();
+    if (tid == 0) { S.guess = (s.stage == 1) && pll_noise_like(s.avg_phase); S.prof_c = 0; S.prof_e = 0; S.prof_l = 0; }
+    phase_P(S.b[a], iT, cntT);
+    __syncthreads();
+    if (pf && tid == 0) { const long long now = clock64(); pf[0] += now - tq; tq = now; }
+
+    while (cntT > 0 || have_prev) {
+        const bool acq = s.stage == 1;
+        const bool guess = S.guess != 0;
+        PllBlockBuf &T = S.b[a], &Pv = S.b[a ^ 1];
+        // ---- C(T) ‖ E(prev) -----------------------------------------------------------------------------------------
         if (tid == 0) {
-            real_t phase = s.phase, freq = s.freq, sweep = s.sweep;
-            const real_t alpha = s.alpha, beta = s.beta, maxf = s.max_freq, minf = s.min_freq;
-            if (pll_fast_ok(s)) {
-                tiled::TrackConst kc; kc.alpha = alpha; kc.beta = beta; kc.max_freq = maxf; kc.min_freq = minf;
-                int k = 0;
-                for (; k + 4 <= cnt; k += 4) {                   // the four sample phases are fetched ahead of the dependent chain
-                    const real_t s0 = S.sp[k], s1 = S.sp[k + 1], s2 = S.sp[k + 2], s3 = S.sp[k + 3];
-                    S.ph[k] = phase; S.fq[k] = freq; S.sw[k] = sweep;
-                    pll_loop_fast(phase, freq, s0, kc); if (guess) pll_sweep_fast(freq, sweep, maxf, minf);
-                    S.ph[k + 1] = phase; S.fq[k + 1] = freq; S.sw[k + 1] = sweep;
-                    pll_loop_fast(phase, freq, s1, kc); if (guess) pll_sweep_fast(freq, sweep, maxf, minf);
-                    S.ph[k + 2] = phase; S.fq[k + 2] = freq; S.sw[k + 2] = sweep;
-                    pll_loop_fast(phase, freq, s2, kc); if (guess) pll_sweep_fast(freq, sweep, maxf, minf);
-                    S.ph[k + 3] = phase; S.fq[k + 3] = freq; S.sw[k + 3] = sweep;
-                    pll_loop_fast(phase, freq, s3, kc); if (guess) pll_sweep_fast(freq, sweep, maxf, minf);
-                }
-                for (; k < cnt; k++) {
-                    S.ph[k] = phase; S.fq[k] = freq; S.sw[k] = sweep;
-                    pll_loop_fast(phase, freq, S.sp[k], kc); if (guess) pll_sweep_fast(freq, sweep, maxf, minf);
-                }
-            } else {
-                for (int k = 0; k < cnt; k++) {
-                    S.ph[k] = phase; S.fq[k] = freq; S.sw[k] = sweep;
-                    pll_loop_core(phase, freq, S.sp[k], alpha, beta, maxf, minf);
-                    if (guess) pll_sweep_core(freq, sweep, maxf, minf);
-                }
-            }
-            S.end_phase = phase; S.end_freq = freq; S.end_sweep = sweep;
-        }
-        __syncthreads();
-        const long long t2 = clock64();
-        // ---- H ----------------------------------------------------------------------------------------------------
-        if (tid < cnt) {
-            real_t ti, tr;
-            sincos_exact(S.ph[tid], ti, tr);                     // :106-107
-            const real_t a = S.pa[tid], b = S.pb[tid], nti = -ti;
-            const real_t mre = a * tr - b * nti;                 // :110
-            const real_t mim = a * nti + b * tr;
-            S.out[tid] = mim;                                    // :113
-            S.at[tid] = avg_alpha * r_fabs(arctan2_approx(mim, mre));            // :117, :124
-            S.lt[tid] = p.lock_alpha * (S.nre[tid] * tr + S.nim[tid] * ti);      // :220
-        }
-        __syncthreads();
-        const long long t3 = clock64();
-        // ---- E ----------------------------------------------------------------------------------------------------
-        if (tid == 0) {
-            real_t avg = s.avg_phase;
-            int ja = cnt;
-            for (int k0 = 0; k0 < cnt && ja == cnt; k0 += 4) {
-                real_t v[4];
-#pragma unroll
-                for (int q = 0; q < 4; q++) v[q] = S.at[(k0 + q < PP_B) ? k0 + q : PP_B - 1];
-#pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const int k = k0 + q;
-                    if (k < cnt && ja == cnt) {
-                        avg = avg * (1.0 - avg_alpha) + v[q];    // :124
-                        S.av[k] = avg;
-                        if (acq && pll_noise_like(avg) != guess) ja = k;
+            if (cntT > 0) {
+                const long long c0 = clock64();
+                real_t phase = s.phase, freq = s.freq, sweep = s.sweep;
+                const real_t alpha = s.alpha, beta = s.beta, maxf = s.max_freq, minf = s.min_freq;
+                if (pll_fast_ok(s)) {
+                    PllLoopConst kc; kc.alpha = alpha; kc.beta = beta; kc.max_freq = maxf; kc.min_freq = minf;
+                    int k = 0;
+                    for (; k + 4 <= cntT; k += 4) {              // the four sample phases are fetched ahead of the dependent chain
+                        const real_t s0 = T.sp[k], s1 = T.sp[k + 1], s2 = T.sp[k + 2], s3 = T.sp[k + 3];
+                        T.ph[k] = phase; T.fq[k] = freq; T.sw[k] = sweep;
+                        pll_loop_fast(phase, freq, s0, kc); if (guess) pll_sweep_fast(freq, sweep, maxf, minf);
+                        T.ph[k + 1] = phase; T.fq[k + 1] = freq; T.sw[k + 1] = sweep;
+                        pll_loop_fast(phase, freq, s1, kc); if (guess) pll_sweep_fast(freq, sweep, maxf, minf);
+                        T.ph[k + 2] = phase; T.fq[k + 2] = freq; T.sw[k + 2] = sweep;
+                        pll_loop_fast(phase, freq, s2, kc); if (guess) pll_sweep_fast(freq, sweep, maxf, minf);
+                        T.ph[k + 3] = phase; T.fq[k + 3] = freq; T.sw[k + 3] = sweep;
+                        pll_loop_fast(phase, freq, s3, kc); if (guess) pll_sweep_fast(freq, sweep, maxf, minf);
+                    }
+                    for (; k < cntT; k++) {
+                        T.ph[k] = phase; T.fq[k] = freq; T.sw[k] = sweep;
+                        pll_loop_fast(phase, freq, T.sp[k], kc); if (guess) pll_sweep_fast(freq, sweep, maxf, minf);
+                    }
+                } else {
+                    for (int k = 0; k < cntT; k++) {
+                        T.ph[k] = phase; T.fq[k] = freq; T.sw[k] = sweep;
+                        pll_loop_core(phase, freq, T.sp[k], alpha, beta, maxf, minf);
+                        if (guess) pll_sweep_core(freq, sweep, maxf, minf);
                     }
                 }
+                s.phase = phase; s.freq = freq; s.sweep = sweep;         // the loop runs ahead of the EMAs; a contradiction restores it
+                S.prof_c += (unsigned long long)(clock64() - c0);
             }
-            S.ja = ja;
         } else if (tid == 32) {
-            real_t lks = s.locksig;
-            int jl = cnt;
-            for (int k0 = 0; k0 < cnt && jl == cnt; k0 += 4) {
-                real_t v[4];
+            if (have_prev) {
+                const long long e0 = clock64();
+                real_t avg = s.avg_phase;
+                int ja = cntP;
+                if (acq) {
+                    for (int k0 = 0; k0 < cntP && ja == cntP; k0 += 4) {
+                        real_t v[4];
 #pragma unroll
-                for (int q = 0; q < 4; q++) v[q] = S.lt[(k0 + q < PP_B) ? k0 + q : PP_B - 1];
+                        for (int q = 0; q < 4; q++) v[q] = Pv.at[(k0 + q < PP_B) ? k0 + q : PP_B - 1];
 #pragma unroll
-                for (int q = 0; q < 4; q++) {
-                    const int k = k0 + q;
-                    if (k < cnt && jl == cnt) {
-                        lks = lks * (1.0 - p.lock_alpha) + v[q]; // :220
-                        S.lk[k] = lks;
-                        if (acq && lks > p.lock_thresh) jl = k;
+                        for (int q = 0; q < 4; q++) {
+                            const int k = k0 + q;
+                            if (k < cntP && ja == cntP) {
+                                avg = avg * (1.0 - avg_alpha) + v[q];    // :124
+                                Pv.av[k] = avg;
+                                if (pll_noise_like(avg) != guess) ja = k;
+                            }
+                        }
                     }
+                } else {                                         // locked: nothing to verify, only the last value is needed
+                    int k = 0;
+                    for (; k + 4 <= cntP; k += 4) {
+                        const real_t v0 = Pv.at[k], v1 = Pv.at[k + 1], v2 = Pv.at[k + 2], v3 = Pv.at[k + 3];
+                        avg = avg * (1.0 - avg_alpha) + v0; avg = avg * (1.0 - avg_alpha) + v1;
+                        avg = avg * (1.0 - avg_alpha) + v2; avg = avg * (1.0 - avg_alpha) + v3;
+                    }
+                    for (; k < cntP; k++) avg = avg * (1.0 - avg_alpha) + Pv.at[k];
+                    Pv.av[cntP - 1] = avg;
+                }
+                S.ja = ja;
+                S.prof_e += (unsigned long long)(clock64() - e0);
+            }
+        } else if (tid == 64) {
+            if (have_prev) {
+                const long long l0 = clock64();
+                real_t lks = s.locksig;
+                int jl = cntP;
+                const auto keep = 1.0 - p.lock_alpha;            // the expression's own type (double in both builds), hoisted
+                const real_t thresh = p.lock_thresh;
+                if (acq) {
+                    for (int k0 = 0; k0 < cntP && jl == cntP; k0 += 4) {
+                        real_t v[4];
+#pragma unroll
+                        for (int q = 0; q < 4; q++) v[q] = Pv.lt[(k0 + q < PP_B) ? k0 + q : PP_B - 1];
+#pragma unroll
+                        for (int q = 0; q < 4; q++) {
+                            const int k = k0 + q;
+                            if (k < cntP && jl == cntP) {
+                                lks = lks * keep + v[q];         // :220
+                                Pv.lk[k] = lks;
+                                emit_lock(iP + k, lks);
+                                if (lks > thresh) jl = k;
+                            }
+                        }
+                    }
+                } else {
+                    int k = 0;
+                    for (; k + 4 <= cntP; k += 4) {
+                        const real_t v0 = Pv.lt[k], v1 = Pv.lt[k + 1], v2 = Pv.lt[k + 2], v3 = Pv.lt[k + 3];
+                        lks = lks * keep + v0; const real_t l0v = lks;
+                        lks = lks * keep + v1; const real_t l1v = lks;
+                        lks = lks * keep + v2; const real_t l2v = lks;
+                        lks = lks * keep + v3;
+                        emit_lock(iP + k, l0v); emit_lock(iP + k + 1, l1v); emit_lock(iP + k + 2, l2v); emit_lock(iP + k + 3, lks);
+                    }
+                    for (; k < cntP; k++) { lks = lks * keep + Pv.lt[k]; emit_lock(iP + k, lks); }
+                    Pv.lk[cntP - 1] = lks;
+                }
+                S.jl = jl;
+                S.prof_l += (unsigned long long)(clock64() - l0);
+            }
+        }
+        __syncthreads();
+        if (pf && tid == 0) { const long long now = clock64(); pf[1] += now - tq; tq = now; }
+        // ---- control: commit the previous block, or roll back to its first contradicted sample ----------------------------
+        if (tid == 0) {
+            int jj = cntP;
+            if (have_prev) {
+                jj = (S.ja < S.jl) ? S.ja : S.jl;
+                if (jj < cntP) {                                 // sample jj again, with what it really saw
+                    real_t phase = Pv.ph[jj], freq = Pv.fq[jj], sweep = Pv.sw[jj];
+                    pll_loop_core(phase, freq, Pv.sp[jj], s.alpha, s.beta, s.max_freq, s.min_freq);
+                    const bool flag = pll_noise_like(Pv.av[jj]);
+                    if (flag) pll_sweep_core(freq, sweep, s.max_freq, s.min_freq);
+                    s.phase = phase; s.freq = freq; s.sweep = sweep;
+                    s.avg_phase = Pv.av[jj]; s.locksig = Pv.lk[jj];
+                    if (Pv.lk[jj] > p.lock_thresh) pll_latch(s, p, abs0 + iP + jj);
+                    S.guess = (s.stage == 1) && flag;
+                } else {
+                    s.avg_phase = Pv.av[cntP - 1]; s.locksig = Pv.lk[cntP - 1];
                 }
             }
-            S.jl = jl;
+            S.j = jj;
+            if (pf) pf[8] += clock64() - tq;
         }
         __syncthreads();
-        const long long t4 = clock64();
-        const int j = (S.ja < S.jl) ? S.ja : S.jl;
-        const int valid = (j < cnt) ? j + 1 : cnt;
-        if (tid < valid) emit(i + tid, S.out[tid], S.lk[tid], S.ph[tid], S.fq[tid]);
-        __syncthreads();                                         // every reader of `s` and of this block's arrays is done
-        const long long t4b = clock64();
-        if (tid == 0) {
-            if (j < cnt) {                                       // sample j again, with what it really saw
-                real_t phase = S.ph[j], freq = S.fq[j], sweep = S.sw[j];
-                pll_loop_core(phase, freq, S.sp[j], s.alpha, s.beta, s.max_freq, s.min_freq);
-                if (pll_noise_like(S.av[j])) pll_sweep_core(freq, sweep, s.max_freq, s.min_freq);
-                s.phase = phase; s.freq = freq; s.sweep = sweep;
-                s.avg_phase = S.av[j]; s.locksig = S.lk[j];
-                if (S.lk[j] > p.lock_thresh) pll_latch(s, p, abs0 + i + j);
-            } else {
-                s.phase = S.end_phase; s.freq = S.end_freq; s.sweep = S.end_sweep;
-                s.avg_phase = S.av[cnt - 1]; s.locksig = S.lk[cnt - 1];
-            }
+        const int j = S.j;                                       // (rewritten only behind the next C ‖ E barrier)
+        const bool rolled = have_prev && j < cntP;
+        if (pf && tid == 0) { pf[5] += have_prev; pf[6] += rolled; }
+        if (rolled) {                                            // drop block T, restart behind sample j of the previous block
+            iT = iP + j + 1;
+            cur = PP_B_MIN;
+            cntT = (iT < n) ? (int)((n - iT < (unsigned long long)cur) ? (n - iT) : (unsigned long long)cur) : 0;
+            have_prev = false;
+            if (pf && tid == 0) { const long long now = clock64(); pf[7] += now - tq; tq = now; }
+            phase_P(S.b[a], iT, cntT);
+            __syncthreads();
+            if (pf && tid == 0) { const long long now = clock64(); pf[0] += now - tq; tq = now; }
+            continue;
         }
-        cur = (j < cnt) ? PP_B_MIN : ((cur * 2 < PP_B) ? cur * 2 : PP_B);
-        i += valid;
+        if (pf && tid == 0) { const long long now = clock64(); pf[7] += now - tq; tq = now; }
+        // ---- H(T) ‖ P(next) -----------------------------------------------------------------------------------------
+        if (have_prev) cur = (cur * 2 < PP_B) ? cur * 2 : PP_B;
+        const unsigned long long iU = iT + (unsigned long long)cntT;
+        const int cntU = (cntT > 0 && iU < n) ? (int)((n - iU < (unsigned long long)cur) ? (n - iU) : (unsigned long long)cur) : 0;
+        if (tid < cntT) {
+            real_t ti, tr;
+            const real_t ph = T.ph[tid];
+            sincos_exact(ph, ti, tr);                            // :106-107
+            const real_t x = T.pa[tid], y = T.pb[tid], nti = -ti;
+            const real_t mre = x * tr - y * nti;                 // :110
+            const real_t mim = x * nti + y * tr;
+            T.at[tid] = avg_alpha * r_fabs(arctan2_approx(mim, mre));            // :117, :124
+            T.lt[tid] = p.lock_alpha * (T.nre[tid] * tr + T.nim[tid] * ti);      // :220
+            emit(iT + tid, mim, ph, T.fq[tid]);                  // :113
+        }
+        phase_P(Pv, iU, cntU);
         __syncthreads();
-        if (pf && tid == 0) {
-            const long long t5 = clock64();
-            pf[0] += t1 - t0; pf[1] += t2 - t1; pf[2] += t3 - t2; pf[3] += t4 - t3; pf[4] += t4b - t4; pf[5] += 1; pf[6] += (j < cnt); pf[7] += t5 - t4b;
-        }
+        if (pf && tid == 0) { const long long now = clock64(); pf[2] += now - tq; tq = now; }
+        have_prev = cntT > 0; iP = iT; cntP = cntT;
+        iT = iU; cntT = cntU; a ^= 1;
     }
+    if (pf && tid == 0) { pf[3] += S.prof_c; pf[4] += S.prof_e; pf[9] += S.prof_l; }
 }
 
 } // namespace pdt

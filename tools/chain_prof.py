@@ -18,14 +18,14 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import torch  # noqa: E402
 
 pdt = importlib.import_module("project-desert-tortoise_b200")
-NAMES = ["static_gain", "pll", "pll_P", "pll_C", "pll_H", "pll_E", "pll_emit", "pll_blocks", "pll_contradicted", "fir", "agc",
-         "clock_bits", "capture_total", "samples", "pll_ctl"]
+NAMES = ["static_gain", "pll", "pll_P_alone", "pll_C||E", "pll_H||P", "pll_C_busy", "pll_E_busy", "pll_blocks", "pll_contradicted", "fir", "agc",
+         "clock_bits", "capture_total", "samples", "pll_ctl", "pll_ctl_work", "pll_L_busy"]
 
 
 def prof(prec, reset=1):
     L = pdt.load(prec)
-    L.pdt_debug_chain_prof.argtypes = [C.POINTER(C.c_uint64 * 16), C.c_int]
-    out = (C.c_uint64 * 16)()
+    L.pdt_debug_chain_prof.argtypes = [C.POINTER(C.c_uint64 * 20), C.c_int]
+    out = (C.c_uint64 * 20)()
     assert L.pdt_debug_chain_prof(C.byref(out), reset) == 0
     return [int(v) for v in out]
 
@@ -34,7 +34,7 @@ def report(tag, prec, ms, caps):
     v = prof(prec)
     n = max(v[13], 1)
     row = {"case": tag, "captures": caps, "kernel_ms": round(ms, 3), "samples": v[13],
-           "cycles_per_sample": {NAMES[i]: round(v[i] / n, 1) for i in (0, 1, 2, 3, 4, 5, 6, 14, 9, 10, 11, 12)},
+           "cycles_per_sample": {NAMES[i]: round(v[i] / n, 1) for i in (0, 1, 2, 3, 4, 5, 6, 16, 14, 15, 9, 10, 11, 12)},
            "pll_blocks": v[7], "pll_contradicted_blocks": v[8], "samples_per_block": round(n / max(v[7], 1), 1)}
     print(json.dumps(row), flush=True)
     return row
