@@ -71,8 +71,6 @@ void die(const char *what, cudaError_t e)
 }
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) die(#call, e_); } while (0)
 
-static int g_pll_stage_seen = 0;      // PLL stage after the last CarrierTrackPLL call (host copy: picks the kernel of the next call)
-
 __global__ void k_leg_reset(LegacyState *s)
 {
     *s = LegacyState();
@@ -128,98 +126,6 @@ __global__ void __launch_bounds__(PP_THREADS) k_leg_pll_blocks(LegacyState *s, P
 }
 
 #if PDT_USE_FLOATS
-// CarrierTrackPLL of the float build as a small pipeline (one CTA): until the lock latch the loop is the reference's, sample
-// by sample on one thread (sweep and latch feed back into it); behind the latch nothing feeds back, and the call splits into
-//     thread 0          phase / frequency recurrence of block t            (pll_track_step: CarrierTrackingPLL.c:128-188)
-//     warps 2, 3        block t-1: NCO sincos, derotation -> realOut, the two EMA inputs; block t+1: loads, approx-atan2
-//     threads 32, 33    block t-2: the two EMAs (:124, :220) -> averagePhase, lockSignalStream
-// the same stage split (and the same arithmetic, statement for statement) as k_acquire of the batch engine.  One thread
-// took 5.4 ms per 10 000-sample chunk (profiles/r02l_dropin_launches_before.csv); the recurrence alone is 0.35 ms.
-constexpr int LP_B = 128, LP_THREADS = 128;
-__global__ void __launch_bounds__(LP_THREADS) k_leg_pll_pipe(LegacyState *s, PllParams p, const float *__restrict__ iq, float *__restrict__ out,
-                                                              float *__restrict__ lock, unsigned n)
-{
-    using namespace pdt::tiled;
-    __shared__ PllState st;
-    __shared__ unsigned i0s;
-    __shared__ float sp[3][LP_B], pa[3][LP_B], pb[3][LP_B], ph[3][LP_B], aterm[3][LP_B], lterm[3][LP_B];
-    __shared__ float ema_out[2];
-    const int tid = threadIdx.x;
-    if (tid == 0) {
-        st = s->pll;
-        st.lock_event = 0;
-        pll_begin(st, p);
-        unsigned i = 0;
-        for (; i < n && st.stage != 2; i++) {                      // acquisition: the reference loop as it is
-            float o, l;
-            pll_step(st, p, iq[2 * i], iq[2 * i + 1], o, l, st.samples_seen + i);
-            out[i] = o;
-            if (lock) lock[i] = l;
-        }
-        i0s = i;
-    }
-    __syncthreads();
-    const unsigned i0 = i0s;
-    if (i0 < n) {
-        const unsigned m = n - i0, n_blk = (m + LP_B - 1) / LP_B;
-        TrackConst k; k.alpha = st.alpha; k.beta = st.beta; k.max_freq = st.max_freq; k.min_freq = st.min_freq;
-        const float avg_alpha = 0.00005f;
-        const double c_avg = 1.0 - avg_alpha, c_lks = 1.0 - p.lock_alpha;
-        auto cnt_of = [&](int j) -> int { return (j < 0 || (unsigned)j >= n_blk) ? 0 : (int)((m - (unsigned)j * LP_B < (unsigned)LP_B) ? (m - (unsigned)j * LP_B) : (unsigned)LP_B); };
-        auto stage_in = [&](int j) {                               // warps 2, 3: inputs of block j
-            const int cnt = cnt_of(j), slot = j % 3;
-            for (int i = tid - 64; i < cnt; i += 64) {
-                const unsigned g = i0 + (unsigned)j * LP_B + (unsigned)i;
-                const float a = iq[2 * g], b = iq[2 * g + 1];
-                pa[slot][i] = a; pb[slot][i] = b; sp[slot][i] = arctan2_approx(b, a);                 // :128
-            }
-        };
-        if (tid >= 64) stage_in(0);
-        float phase = st.phase, freq = st.freq;                    // thread 0
-        float ema = (tid == 32) ? st.avg_phase : st.locksig;       // threads 32 / 33
-        __syncthreads();
-        for (int t = 0; t < (int)n_blk + 2; t++) {
-            if (tid == 0) {
-                const int cnt = cnt_of(t), slot = t % 3;
-                for (int i = 0; i < cnt; i++) { ph[slot][i] = phase; pll_track_step(phase, freq, sp[slot][i], k); }
-            } else if (tid == 32 || tid == 33) {
-                const int j = t - 2, cnt = cnt_of(j), slot = (j + 3) % 3;
-                const bool is_avg = tid == 32;
-                const float *term = is_avg ? aterm[slot] : lterm[slot];
-                const double c = is_avg ? c_avg : c_lks;
-                for (int i = 0; i < cnt; i++) {
-                    ema = (float)((double)ema * c + (double)term[i]);                                // :124 / :220
-                    if (!is_avg && lock) lock[i0 + (unsigned)j * LP_B + (unsigned)i] = ema;          // :222-223
-                }
-            } else if (tid >= 64) {
-                const int j = t - 1, cnt = cnt_of(j), slot = (j + 3) % 3;
-                for (int i = tid - 64; i < cnt; i += 64) {
-                    float ti, tr;
-                    sincos_exact(ph[slot][i], ti, tr);                                               // :106-107
-                    const float a = pa[slot][i], b = pb[slot][i], nti = -ti;
-                    const float mre = a * tr - b * nti, mim = a * nti + b * tr;                      // :110
-                    out[i0 + (unsigned)j * LP_B + (unsigned)i] = mim;                                // :113
-                    aterm[slot][i] = avg_alpha * fabsf(arctan2_approx(mim, mre));                    // :117,:124
-                    const float mag2 = a * a + b * b;                                                // :193-220
-                    const float inv = q_rsqrt(mag2);
-                    const float nre = a * inv, nim = b * inv;
-                    lterm[slot][i] = p.lock_alpha * (nre * tr + nim * ti);
-                }
-                stage_in(t + 1);
-            }
-            __syncthreads();
-        }
-        if (tid == 32 || tid == 33) ema_out[tid - 32] = ema;
-        __syncthreads();
-        if (tid == 0) { st.phase = phase; st.freq = freq; st.avg_phase = ema_out[0]; st.locksig = ema_out[1]; }
-    }
-    if (tid == 0) {
-        st.samples_seen += n;
-        s->pll = st;
-        s->ret = st.avg_phase;
-    }
-}
-
 // NormalizingAGC of the float build: the proven fast regime of the batch engine (four dependent operations per sample and a
 // side proof that no clamp / attack branch would have fired, pdt_tiled.cuh), the general recurrence if the proof fails.
 __global__ void k_leg_agc_fast(LegacyState *s, const float *__restrict__ x, float *__restrict__ z, unsigned long long n, float initial,
@@ -417,7 +323,6 @@ void pdt_legacy_reset(void)
 {
     ensure_ready();
     k_leg_reset<<<1, 1>>>(G.d_state); count_launch();
-    g_pll_stage_seen = 0;
     CK(cudaDeviceSynchronize());
     if (G.hist.p) cudaMemset(G.hist.p, 0, G.hist.cap);
     if (G.aux2.p) cudaMemset(G.aux2.p, 0, G.aux2.cap);
@@ -445,24 +350,11 @@ DECIMAL_TYPE CarrierTrackPLL(DECIMAL_TYPE *complexDataIn, DECIMAL_TYPE *realData
     real_t *d_out = (real_t *)G.out.ensure(sizeof(real_t) * (n + 1));
     real_t *d_lock = lockSignalStreamOut ? (real_t *)G.aux.ensure(sizeof(real_t) * (n + 1)) : nullptr;
     if (n) CK(cudaMemcpy(d_in, complexDataIn, sizeof(real_t) * 2 * n, cudaMemcpyHostToDevice));
-    // locked float stream: the three-stage pipeline (k_leg_pll_pipe, track mode only; it wraps the phase once per sample, valid
-    // while a step cannot move it by 2π, i.e. for any sane loop bandwidth); everything else: the block runner
-    bool piped = false;
-#if PDT_USE_FLOATS
-    if (g_pll_stage_seen == 2) {
-        PllState ps; pll_reset(ps); pll_begin(ps, p);
-        const double bw = p.bw_track, damp = ps.damp;
-        const double at = (4.0 * damp * bw) / (1.0 + 2.0 * damp * bw + bw * bw), bt = (4.0 * bw * bw) / (1.0 + 2.0 * damp * bw + bw * bw);
-        piped = (double)ps.max_freq + 10.0 * (at + bt) < 6.0;
-    }
-    if (piped) k_leg_pll_pipe<<<1, LP_THREADS>>>(G.d_state, p, d_in, d_out, d_lock, nSamples);
-#endif
-    if (!piped) k_leg_pll_blocks<<<1, PP_THREADS>>>(G.d_state, p, d_in, d_out, d_lock, nSamples);
+    k_leg_pll_blocks<<<1, PP_THREADS>>>(G.d_state, p, d_in, d_out, d_lock, nSamples);
     count_launch();
     if (n) CK(cudaMemcpy(realDataOut, d_out, sizeof(real_t) * n, cudaMemcpyDeviceToHost));
     if (n && d_lock) CK(cudaMemcpy(lockSignalStreamOut, d_lock, sizeof(real_t) * n, cudaMemcpyDeviceToHost));
     LegacyState h = fetch_state();
-    g_pll_stage_seen = h.pll.stage;
     if (h.pll.lock_event) printf(" : PLL locked at %0.2fHz\n", h.pll.lock_freq_hz);      // CarrierTrackingPLL.c:269
     return h.ret;
 }
