@@ -258,7 +258,7 @@ static int tiled_setup(pdt_ctx *c)
     TA(t.pll_ckpt, np * t.pll_nck * sizeof(LoopState2));
     TA(t.agc_start, na * sizeof(LoopState2)); TA(t.agc_end, na * sizeof(LoopState2));
     TA(t.counters, 4 * sizeof(uint32_t));
-    TA(t.slow_list, (size_t)c->max_captures * sizeof(uint32_t)); TA(t.slow_count, sizeof(uint32_t));
+    TA(t.slow_list, 2 * (size_t)c->max_captures * sizeof(uint32_t)); TA(t.slow_count, 2 * sizeof(uint32_t));
     // work lists of the persistent lane-stream kernels: one region per pass (fast groups / slow captures run concurrently)
     t.pll_tasks_per_cap = (t.pll.max_tiles + 31) / 32;
     t.agc_tasks_per_cap = (t.agc_max_tiles + 31) / 32;
@@ -311,6 +311,7 @@ static void tiled_free(pdt_ctx *c)
 // that latched within the first acquisition pass, 1: the rest, after their second acquisition pass).
 struct GroupLaunch {
     pdt_ctx *c; tiled::TiledArgs t; uint32_t cnt; tiled::u64 n_max; bool marks; int gid = 0;
+    bool slow_listed = false;            // acquire_rest has built the list of this launch group's slow captures
     static unsigned blocks(tiled::u64 items, unsigned per) { return (unsigned)((items + per - 1) / per); }
     void mark(cudaStream_t s, const char *name)
     {
@@ -347,12 +348,12 @@ struct GroupLaunch {
     void acquire_rest(cudaStream_t s)
     {
         using namespace tiled;
-        if (c->acq_packed) {
-            cudaMemsetAsync(t.slow_count, 0, sizeof(uint32_t), s);
-            k_slow_list<<<blocks(cnt, 128), 128, 0, s>>>(t, t.slow_list, t.slow_count);
-            k_acquire_packed<<<blocks(cnt, AQ), AP_THREADS, sizeof(AcqPackSmem), s>>>(t, 1, t.slow_list, t.slow_count);
-            count_launch(1);
-        } else k_acquire<<<std::max(1u, cnt), ACQ_THREADS_SLOW, 0, s>>>(t, 1);
+        cudaMemsetAsync(t.slow_count, 0, 2 * sizeof(uint32_t), s);
+        k_slow_list<<<blocks(cnt, 128), 128, 0, s>>>(t, t.slow_list, t.slow_count);
+        slow_listed = true;
+        count_launch(1);
+        if (c->acq_packed) k_acquire_packed<<<blocks(cnt, AQ), AP_THREADS, sizeof(AcqPackSmem), s>>>(t, 1, t.slow_list, t.slow_count);
+        else k_acquire<<<std::max(1u, cnt), ACQ_THREADS_SLOW, 0, s>>>(t, 1);
         mark(s, "k_acquire");
         count_launch(1);
     }
@@ -393,10 +394,15 @@ struct GroupLaunch {
         k_pll_fix<<<blocks(cnt, 128), 128, 0, s>>>(q);
         mark(s, "k_pll_fix");
         if (dbg_skip("k_front")) {
+        } else if (c->front_packed && slow_pass && slow_listed) {
+            q.cap_list = t.slow_list + t.n_captures; q.cap_list_count = t.slow_count + 1;
+            dim3 g(blocks(n_max, F1_SPAN), std::max(1u, blocks(cnt, 8)));         // rows stride over the list: any count is covered
+            if (q.pcm16) k_front1<true, true><<<g, F1_THREADS, 0, s>>>(q, c->taps_pair);
+            else         k_front1<false, true><<<g, F1_THREADS, 0, s>>>(q, c->taps_pair);
         } else if (c->front_packed) {
             dim3 g(blocks(n_max, F1_SPAN), cnt);
-            if (q.pcm16) k_front1<true><<<g, F1_THREADS, 0, s>>>(q, c->taps_pair);
-            else         k_front1<false><<<g, F1_THREADS, 0, s>>>(q, c->taps_pair);
+            if (q.pcm16) k_front1<true, false><<<g, F1_THREADS, 0, s>>>(q, c->taps_pair);
+            else         k_front1<false, false><<<g, F1_THREADS, 0, s>>>(q, c->taps_pair);
         } else {
             dim3 g(blocks(n_max, front_span(L)), cnt);
             front_kernel(L)<<<g, front_threads(L), c->front_smem, s>>>(q, c->taps_rev);

@@ -47,6 +47,7 @@ struct TiledArgs {
     uint32_t    prelock_from;// captures >= this index skip the acquisition sweep and start in track mode from a carrier
                              // estimate (k_prelock): segments of one stream behind the first (pdt_demod_segments_device)
     uint32_t   *slow_list, *slow_count;  // captures the second acquisition pass continues (k_slow_list -> k_acquire_packed)
+    const uint32_t *cap_list, *cap_list_count;   // k_front1<., true>: compact launch over this capture list (the slow captures) or nullptr
     LaneTask   *pll_tasks, *agc_tasks;   // compact work lists of the persistent lane-stream kernels (built on the device)
     uint32_t   *task_counts; // [0] PLL tasks, [1] AGC tasks
     unsigned    pll_tasks_per_cap, agc_tasks_per_cap;
@@ -593,6 +594,7 @@ __global__ void __launch_bounds__(128) k_slow_list(const TiledArgs a, uint32_t *
     if (cap >= a.n_captures) return;
     const AcqResult &r = a.acq[cap];
     if (r.slow && r.resume_at < cap_len(a, cap)) list[atomicAdd(count, 1u)] = cap;
+    if (r.slow) list[a.n_captures + atomicAdd(count + 1, 1u)] = cap;       // second list: every capture of the slow pipeline
 }
 
 __device__ __forceinline__ void acq_step_sel(float &phase, float &freq, float &sweep, float sp, const TrackConst &k, bool on)
@@ -1488,16 +1490,21 @@ __device__ __forceinline__ void f1_stage(float2 *__restrict__ P, float2 (*__rest
     }
 }
 
-template <bool PCM>
+// LIST: the launch covers a.cap_list (the slow captures, ~9 % of a batch) with blockIdx.y striding over it, instead of one
+// grid row per capture of which 91 % would exit at once (0.24 ms of empty CTAs per batch, profiles/r02z_bench.json)
+template <bool PCM, bool LIST>
 __global__ void __launch_bounds__(F1_THREADS, 7) k_front1(const TiledArgs a, const __grid_constant__ TapsPair taps)
 {
     __shared__ __align__(128) float2 P[F1_PAIRS];          // staged operand pairs; re-used as the output tile (6656 floats)
     __shared__ __align__(16) float2 RP[4][F1_THREADS];     // per-thread landing slots of the phase prefetch: two sets of (low, high half)
-    const uint32_t cap = blockIdx.y;
     const int tid = threadIdx.x;
-    const long long n = (long long)cap_len(a, cap);
     const long long base = (long long)blockIdx.x * F1_SPAN;
-    if (base >= n || !cap_selected(a, cap)) return;
+    const uint32_t n_list = LIST ? *a.cap_list_count : 0u;
+  for (uint32_t li = blockIdx.y; !LIST || li < n_list; li += gridDim.y) {
+    const uint32_t cap = LIST ? a.cap_list[li] : li;
+    const long long n = (long long)cap_len(a, cap);
+    if (!LIST && (base >= n || !cap_selected(a, cap))) return;
+    if (LIST && base >= n) continue;                       // (uniform over the CTA; nothing of this capture touched shared memory)
     const float *__restrict__ ph = a.ph + (u64)cap * a.ws_stride;
     const void *__restrict__ iq_cap = PCM ? (const void *)(reinterpret_cast<const short2 *>(a.iq) + (u64)cap * a.stride)
                                           : (const void *)(reinterpret_cast<const float2 *>(a.iq) + (u64)cap * a.stride);
@@ -1565,6 +1572,9 @@ __global__ void __launch_bounds__(F1_THREADS, 7) k_front1(const TiledArgs a, con
         __syncthreads();
         for (unsigned o = tid; o < span; o += F1_THREADS) y[o] = ys[o];
     }
+    if (!LIST) return;
+    __syncthreads();                                       // the tile has left (thread 0 waited for the bulk read): next capture
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------
