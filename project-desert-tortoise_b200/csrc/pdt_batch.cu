@@ -729,17 +729,21 @@ pdt_ctx *pdt_create(const pdt_params *p, uint32_t max_captures, uint64_t max_sam
         cudaFuncAttributes fa{};
         if ((e = cudaFuncGetAttributes(&fa, k_chain_exact)) != cudaSuccess) return bail(e, "cudaFuncGetAttributes");
         const size_t static_smem = fa.sharedSizeBytes + 1024;
-        c->use_smem = (c->smem_bytes + static_smem <= (size_t)max_optin);
-        int per_sm = 1;
-        if (c->use_smem) {
+        // the chain is latency-bound on a few serial threads per CTA: what buys throughput is the number of resident CTAs.  The
+        // chunk buffers go to shared memory only when that does not cost residency (ARGOS: 58 KB of chunk per CTA would leave
+        // 2 CTAs per SM where the per-CTA global workspace, L1/L2-resident and touched by the parallel phases only, allows 6).
+        const bool fits = (c->smem_bytes + static_smem <= (size_t)max_optin);
+        int per_smem = 0, per_glob = 0;
+        if (fits) {
             if ((e = cudaFuncSetAttribute(k_chain_exact, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->smem_bytes)) != cudaSuccess)
                 return bail(e, "cudaFuncSetAttribute");
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_chain_exact, CHAIN_THREADS, c->smem_bytes);
-        } else {
-            c->smem_bytes = 0;
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_chain_exact, CHAIN_THREADS, 0);
-            per_sm = std::min(per_sm, 8);
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_smem, k_chain_exact, CHAIN_THREADS, c->smem_bytes);
         }
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_glob, k_chain_exact, CHAIN_THREADS, 0);
+        per_glob = std::min(per_glob, 8);
+        c->use_smem = fits && per_smem >= per_glob;
+        int per_sm = c->use_smem ? per_smem : per_glob;
+        if (!c->use_smem) c->smem_bytes = 0;
         if (per_sm < 1) per_sm = 1;
         c->grid = (int)std::min<uint64_t>(max_captures, (uint64_t)c->sm_count * per_sm);
         if (!c->use_smem) {

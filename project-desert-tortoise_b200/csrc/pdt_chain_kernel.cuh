@@ -50,7 +50,8 @@ struct ChainArgs {
                                     // survive between pushes like the reference's static buffers do) and the frame table a ring.
 };
 
-constexpr int CHAIN_THREADS = 256;
+constexpr int CHAIN_THREADS = 128;      // narrow CTAs: the chain is latency-bound on a few serial threads, throughput comes from resident CTAs
+constexpr int CHAIN_MIN_CTAS = 6;       // register budget asked of the compiler (65536 / (128 · 6) = 85 per thread)
 static_assert(CHAIN_THREADS == PP_THREADS, "the PLL block runner assigns its roles by thread index");
 
 // reals needed: Rext[K-1+chunk] + LOCK[chunk] (ARGOS only) + Y[chunk*L+ypad]
@@ -139,7 +140,7 @@ __device__ unsigned long long g_chain_prof[20];
 // ---------------------------------------------------------------------------------------------------
 // v1 chain kernel: exact-order serial loops on lane 0, FIR on all threads.
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CHAIN_THREADS) k_chain_exact(const ChainArgs args)
+__global__ void __launch_bounds__(CHAIN_THREADS, CHAIN_MIN_CTAS) k_chain_exact(const ChainArgs args)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ ChainState st;

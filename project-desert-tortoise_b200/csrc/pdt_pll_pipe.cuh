@@ -15,7 +15,7 @@
 //   H  one thread per sample   sincos of its NCO phase, derotation, output, the two EMA terms
 //   E  threads 32 / 64         the two EMAs in order; each stops at the first sample that contradicts the assumption
 //
-// software-pipelined over two buffers:  step k runs  C(block k) ‖ E(block k-1),  then  H(block k) ‖ P(block k+1).
+// software-pipelined over two buffers:  step k runs  C(block k) ‖ E(block k-1),  then  H(block k) and P(block k+1).
 // If sample j of block k-1 contradicts the assumption, its samples ≤ j are exact as computed (their phases depend on the
 // flags of samples < j only): the loop state before j is restored, sample j's filter step repeated with its actual flag,
 // the latch applied, block k dropped, and the pipeline restarts at j + 1 — with short blocks at first, doubling while
@@ -74,7 +74,8 @@ PDT_DEV void pll_sweep_fast(real_t &freq, real_t &sweep, real_t max_freq, real_t
 }
 
 constexpr int PP_B = 128;            // samples per block
-constexpr int PP_THREADS = 256;      // threads of the CTA that runs it: 0..127 H (and C / E on 0, 32, 64), 128..255 P
+constexpr int PP_THREADS = 128;      // threads of the CTA that runs it: one per sample in P and H; C on thread 0, the EMAs on 32 and 64
+                                     // (a narrow CTA on purpose: the runner is latency-bound, residency is what buys throughput)
 constexpr int PP_B_MIN = 8;          // block length right after a contradicted assumption
 
 struct PllBlockBuf {
@@ -91,9 +92,9 @@ struct PllPipeSmem {
     unsigned long long prof_c, prof_e, prof_l;
 };
 
-// `load(i, a, b)`: sample i of this call.  `emit(i, out, phase_before, freq_before)` (one thread per sample) and
-// `emit_lock(i, lock)` (one thread, in order) store the results of sample i; a sample may be emitted more than once, the
-// last time with its final values.  `s` lives in shared memory; all PP_THREADS threads call this with identical arguments.
+// `load(i, a, b)`: sample i of this call.  `emit(i, out, phase_before, freq_before)` and `emit_lock(i, lock)` (one thread per
+// sample each) store the results of sample i; `emit` may see a sample more than once, the last time with its final values,
+// `emit_lock` sees verified values only.  `s` lives in shared memory; all PP_THREADS threads call this with identical arguments.
 // `pf` (optional, thread 0 only): cycle accounting [0] P alone (prologue, restarts) [1] C ‖ E [2] H ‖ P [3] C busy [4] E busy
 // [5] blocks [6] contradicted blocks [7] control (with its barrier) [8] control, thread 0's work alone [9] lock-EMA thread busy.
 template <class Load, class Emit, class EmitLock>
@@ -103,9 +104,9 @@ __device__ __forceinline__ void pll_run_blocks(PllState &s, const PllParams &p, 
     const int tid = threadIdx.x;
     const real_t avg_alpha = 0.00005;
 
-    auto phase_P = [&](PllBlockBuf &B, unsigned long long i0, int cnt) {          // threads 128..255
-        const int k = tid - PP_B;
-        if (k >= 0 && k < cnt) {
+    auto phase_P = [&](PllBlockBuf &B, unsigned long long i0, int cnt) {
+        const int k = tid;
+        if (k < cnt) {
             real_t a, b;
             load(i0 + k, a, b);
             B.pa[k] = a; B.pb[k] = b;
@@ -217,7 +218,6 @@ __device__ __forceinline__ void pll_run_blocks(PllState &s, const PllParams &p, 
                             if (k < cntP && jl == cntP) {
                                 lks = lks * keep + v[q];         // :220
                                 Pv.lk[k] = lks;
-                                emit_lock(iP + k, lks);
                                 if (lks > thresh) jl = k;
                             }
                         }
@@ -226,14 +226,12 @@ __device__ __forceinline__ void pll_run_blocks(PllState &s, const PllParams &p, 
                     int k = 0;
                     for (; k + 4 <= cntP; k += 4) {
                         const real_t v0 = Pv.lt[k], v1 = Pv.lt[k + 1], v2 = Pv.lt[k + 2], v3 = Pv.lt[k + 3];
-                        lks = lks * keep + v0; const real_t l0v = lks;
-                        lks = lks * keep + v1; const real_t l1v = lks;
-                        lks = lks * keep + v2; const real_t l2v = lks;
-                        lks = lks * keep + v3;
-                        emit_lock(iP + k, l0v); emit_lock(iP + k + 1, l1v); emit_lock(iP + k + 2, l2v); emit_lock(iP + k + 3, lks);
+                        lks = lks * keep + v0; Pv.lk[k] = lks;
+                        lks = lks * keep + v1; Pv.lk[k + 1] = lks;
+                        lks = lks * keep + v2; Pv.lk[k + 2] = lks;
+                        lks = lks * keep + v3; Pv.lk[k + 3] = lks;
                     }
-                    for (; k < cntP; k++) { lks = lks * keep + Pv.lt[k]; emit_lock(iP + k, lks); }
-                    Pv.lk[cntP - 1] = lks;
+                    for (; k < cntP; k++) { lks = lks * keep + Pv.lt[k]; Pv.lk[k] = lks; }
                 }
                 S.jl = jl;
                 S.prof_l += (unsigned long long)(clock64() - l0);
@@ -266,6 +264,7 @@ __device__ __forceinline__ void pll_run_blocks(PllState &s, const PllParams &p, 
         const int j = S.j;                                       // (rewritten only behind the next C ‖ E barrier)
         const bool rolled = have_prev && j < cntP;
         if (pf && tid == 0) { pf[5] += have_prev; pf[6] += rolled; }
+        if (have_prev && tid < (rolled ? j + 1 : cntP)) emit_lock(iP + tid, Pv.lk[tid]);    // the verified part of the previous block
         if (rolled) {                                            // drop block T, restart behind sample j of the previous block
             iT = iP + j + 1;
             cur = PP_B_MIN;
@@ -278,7 +277,7 @@ __device__ __forceinline__ void pll_run_blocks(PllState &s, const PllParams &p, 
             continue;
         }
         if (pf && tid == 0) { const long long now = clock64(); pf[7] += now - tq; tq = now; }
-        // ---- H(T) ‖ P(next) -----------------------------------------------------------------------------------------
+        // ---- H(T), P(next) ------------------------------------------------------------------------------------------
         if (have_prev) cur = (cur * 2 < PP_B) ? cur * 2 : PP_B;
         const unsigned long long iU = iT + (unsigned long long)cntT;
         const int cntU = (cntT > 0 && iU < n) ? (int)((n - iU < (unsigned long long)cur) ? (n - iU) : (unsigned long long)cur) : 0;
