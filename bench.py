@@ -597,6 +597,7 @@ def main():
     ap.add_argument("--pcm16", action="store_true", help="feed int16 PCM (4 B/sample) instead of cf32")
     ap.add_argument("--pll-tile-frac", type=float, default=0.0, help="--stream: PLL tile length as a fraction of the warm-up length "
                                                                      "(default 1: T = W)")
+    ap.add_argument("--agc-min-tile", type=int, default=0, help="experiment knob: pdt_params.agc_min_tile")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-single", action="store_true")
@@ -651,6 +652,11 @@ def main():
     if rc != 0:
         raise SystemExit("synth failed: " + L.pdt_last_error().decode())
     params = pdt.default_params("f32", pdt.PDT_MODE_POES, FS)
+    if args.pll_tile_frac > 0:                # experiment knob: PLL tile length as a multiple of the warm-up length (default 1)
+        w_pll = 17.0 / (params.pll_track_gain * 2.0 * np.pi / FS)
+        params.pll_tile = max(1024, int(w_pll * args.pll_tile_frac) // 4 * 4)
+    if args.agc_min_tile > 0:
+        params.agc_min_tile = args.agc_min_tile
     max_frames = int(n / FS * 10) + 8
     row_bytes = max_frames * 120
 

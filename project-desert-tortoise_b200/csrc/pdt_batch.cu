@@ -230,6 +230,7 @@ static int tiled_setup(pdt_ctx *c)
     t.pll.W = W; t.pll.T = T; t.pll.T0 = W + T;
     t.pll.max_tiles = 1 + (unsigned)((stride + T - 1) / T);
     t.agc_min_tile = c->params.agc_min_tile ? ((c->params.agc_min_tile + 3) & ~3u) : 4096u * (unsigned)cc.L;
+    { const char *e = getenv("PDT_AGC_TILE_HALVES"); t.agc_tile_halves = e ? (unsigned)std::max(1, std::min(atoi(e), 16)) : 1u; }   // experiment knob
     {
         const u64 t_min = ((t.agc_min_tile / 2) + 3) & ~3ull;       // agc_plan: T = W/2 >= agc_min_tile/2
         t.agc_max_tiles = 2 + (unsigned)((stride * cc.L + t_min - 1) / t_min);

@@ -51,6 +51,7 @@ struct TiledArgs {
     LaneTask   *pll_tasks, *agc_tasks;   // compact work lists of the persistent lane-stream kernels (built on the device)
     uint32_t   *task_counts; // [0] PLL tasks, [1] AGC tasks
     unsigned    pll_tasks_per_cap, agc_tasks_per_cap;
+    unsigned    agc_tile_halves;         // AGC tile length in halves of the warm-up length (1: T = W/2)
     float      *sym;         // [captures][sym_cap]     Gardner symbol stream
     u64        *gidx;        // [captures][sym_cap]     absolute interpolated-sample index of every pick
     GarRecord  *gar;         // [captures]
@@ -83,7 +84,7 @@ PDT_DEV TilePlan agc_plan(const TiledArgs &a, const AcqResult &acq)
     if (w < (double)a.agc_min_tile) w = (double)a.agc_min_tile;
     if (w > 1e15) w = 1e15;
     p.W = ((u64)w + 3) & ~3ull;
-    p.T = (p.W / 2 + 3) & ~3ull; p.T0 = p.W + p.T; p.max_tiles = a.agc_max_tiles;
+    p.T = (p.W * a.agc_tile_halves / 2 + 3) & ~3ull; p.T0 = p.W + p.T; p.max_tiles = a.agc_max_tiles;
     return p;
 }
 

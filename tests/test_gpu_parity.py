@@ -703,6 +703,31 @@ def test_argos_synthetic_bursts(torch_cuda, oracle64):
     _frames_text_equal_bytes(d.format_frames(fr[0], int(st[0]["n_frames"])), want["text"])
 
 
+@pytest.mark.parametrize("prec,mode,fs,taps", [("f64", pdt.PDT_MODE_ARGOS, 5000, 600), ("f32", pdt.PDT_MODE_POES, 50000, 3 * 300)])
+def test_exact_engine_long_fir_history_across_chunks(torch_cuda, oracle32, oracle64, prec, mode, fs, taps):
+    """the FIR history (K - 1 samples carried from chunk to chunk) may be longer than the CTA — K - 1 = 599
+    (plain 600-tap filter) and 299 (900 taps over L = 3) against 128 threads.  The filtered stream of the exact engine over
+    five chunks must equal the oracle's stateful filter run over the engine's own PLL output, bit for bit."""
+    o = oracle64 if prec == "f64" else oracle32
+    n = 12000
+    if mode == pdt.PDT_MODE_ARGOS:
+        pcm, _ = make_argos_capture(n, float(fs), seed=11, n_bursts=1, snr_db=20.0)
+    else:
+        pcm, _ = make_poes_capture(n, fs, 12, esn0_db=14.0, doppler_hz=300.0, amplitude=0.25)
+    iq = o.pcm16_to_complex(pcm)
+    d, st, fr, tr = _run_batch_with_traces(torch_cuda, prec, mode, fs, iq, chunk=2400, engine="exact", taps=taps)
+    L = max(d.params.interp, 1)
+    assert d.params.taps == taps and (taps // L) - 1 > 128
+    h = d.taps()
+    pll_out = tr.host("pll_out", n)
+    if mode == pdt.PDT_MODE_ARGOS:
+        want = o.fir(o.new_state("fir"), pll_out, h)
+    else:
+        want = o.fir_interp(o.new_state("fir"), np.arange(n + 1, dtype=pll_out.dtype), pll_out, h, L)[0]
+    got = tr.host("lpf", n * L)
+    assert np.array_equal(got, np.asarray(want).ravel()[: n * L])
+
+
 # ------------------------------------------------------------------------------------------------------
 # legacy ABI: the reference's own function signatures, stage by stage, against the golden stage vectors
 # ------------------------------------------------------------------------------------------------------
