@@ -398,12 +398,21 @@ struct GroupLaunch {
         } else if (c->front_packed && slow_pass && slow_listed) {
             q.cap_list = t.slow_list + t.n_captures; q.cap_list_count = t.slow_count + 1;
             dim3 g(blocks(n_max, F1_SPAN), std::max(1u, blocks(cnt, 8)));         // rows stride over the list: any count is covered
-            if (q.pcm16) k_front1<true, true><<<g, F1_THREADS, 0, s>>>(q, c->taps_pair);
-            else         k_front1<false, true><<<g, F1_THREADS, 0, s>>>(q, c->taps_pair);
+            if (q.pcm16) k_front1<true, 1><<<g, F1_THREADS, 0, s>>>(q, c->taps_pair);
+            else         k_front1<false, 1><<<g, F1_THREADS, 0, s>>>(q, c->taps_pair);
         } else if (c->front_packed) {
-            dim3 g(blocks(n_max, F1_SPAN), cnt);
-            if (q.pcm16) k_front1<true, false><<<g, F1_THREADS, 0, s>>>(q, c->taps_pair);
-            else         k_front1<false, false><<<g, F1_THREADS, 0, s>>>(q, c->taps_pair);
+            static int persist = -1;                      // PDT_FRONT_PERSIST=k: experiment — k resident CTAs per SM stride over the items
+            if (persist < 0) { const char *e = getenv("PDT_FRONT_PERSIST"); persist = e ? std::max(0, std::min(atoi(e), 7)) : 0; }
+            q.front_tiles = blocks(n_max, F1_SPAN);
+            if (persist) {
+                const unsigned gp = (unsigned)std::min<u64>((u64)cnt * q.front_tiles, (u64)persist * (unsigned)std::max(c->sm_count, 1));
+                if (q.pcm16) k_front1<true, 2><<<gp, F1_THREADS, 0, s>>>(q, c->taps_pair);
+                else         k_front1<false, 2><<<gp, F1_THREADS, 0, s>>>(q, c->taps_pair);
+            } else {
+                dim3 g(q.front_tiles, cnt);
+                if (q.pcm16) k_front1<true, 0><<<g, F1_THREADS, 0, s>>>(q, c->taps_pair);
+                else         k_front1<false, 0><<<g, F1_THREADS, 0, s>>>(q, c->taps_pair);
+            }
         } else {
             dim3 g(blocks(n_max, front_span(L)), cnt);
             front_kernel(L)<<<g, front_threads(L), c->front_smem, s>>>(q, c->taps_rev);

@@ -52,6 +52,7 @@ struct TiledArgs {
     uint32_t   *task_counts; // [0] PLL tasks, [1] AGC tasks
     unsigned    pll_tasks_per_cap, agc_tasks_per_cap;
     unsigned    agc_tile_halves;         // AGC tile length in halves of the warm-up length (1: T = W/2)
+    unsigned    front_tiles;             // k_front1 tiles per capture of this launch (persistent mode)
     float      *sym;         // [captures][sym_cap]     Gardner symbol stream
     u64        *gidx;        // [captures][sym_cap]     absolute interpolated-sample index of every pick
     GarRecord  *gar;         // [captures]
@@ -1491,21 +1492,27 @@ __device__ __forceinline__ void f1_stage(float2 *__restrict__ P, float2 (*__rest
     }
 }
 
-// LIST: the launch covers a.cap_list (the slow captures, ~9 % of a batch) with blockIdx.y striding over it, instead of one
-// grid row per capture of which 91 % would exit at once (0.24 ms of empty CTAs per batch, profiles/r02z_bench.json)
-template <bool PCM, bool LIST>
+// MODE 0: one CTA per (tile, capture) cell of the grid.
+// MODE 1: the launch covers a.cap_list (the slow captures, ~9 % of a batch) with blockIdx.y striding over it, instead of one
+//         grid row per capture of which 91 % would exit at once (0.24 ms of empty CTAs per batch, profiles/r02z3_bench.json).
+// MODE 2: persistent — a 1-D grid of resident CTAs strides over all (capture, tile) items of this pass (experiment: PDT_FRONT_PERSIST).
+template <bool PCM, int MODE>
 __global__ void __launch_bounds__(F1_THREADS, 7) k_front1(const TiledArgs a, const __grid_constant__ TapsPair taps)
 {
     __shared__ __align__(128) float2 P[F1_PAIRS];          // staged operand pairs; re-used as the output tile (6656 floats)
     __shared__ __align__(16) float2 RP[4][F1_THREADS];     // per-thread landing slots of the phase prefetch: two sets of (low, high half)
     const int tid = threadIdx.x;
-    const long long base = (long long)blockIdx.x * F1_SPAN;
-    const uint32_t n_list = LIST ? *a.cap_list_count : 0u;
-  for (uint32_t li = blockIdx.y; !LIST || li < n_list; li += gridDim.y) {
-    const uint32_t cap = LIST ? a.cap_list[li] : li;
+    const uint32_t n_list = MODE == 1 ? *a.cap_list_count : 0u;
+    const unsigned long long n_items = MODE == 2 ? (unsigned long long)a.n_captures * a.front_tiles : 0ull;
+  for (unsigned long long it = (MODE == 2) ? blockIdx.x : blockIdx.y; MODE == 0 || (MODE == 1 ? it < n_list : it < n_items);
+       it += (MODE == 2) ? gridDim.x : gridDim.y) {
+    uint32_t cap; long long base;
+    if (MODE == 2) { cap = (uint32_t)(it / a.front_tiles); base = (long long)(it - (unsigned long long)cap * a.front_tiles) * F1_SPAN; }
+    else           { cap = MODE == 1 ? a.cap_list[it] : (uint32_t)it; base = (long long)blockIdx.x * F1_SPAN; }
     const long long n = (long long)cap_len(a, cap);
-    if (!LIST && (base >= n || !cap_selected(a, cap))) return;
-    if (LIST && base >= n) continue;                       // (uniform over the CTA; nothing of this capture touched shared memory)
+    if (MODE == 0 && (base >= n || !cap_selected(a, cap))) return;
+    if (MODE == 1 && base >= n) continue;                  // (uniform over the CTA; nothing of this capture touched shared memory)
+    if (MODE == 2 && (base >= n || !cap_selected(a, cap))) continue;
     const float *__restrict__ ph = a.ph + (u64)cap * a.ws_stride;
     const void *__restrict__ iq_cap = PCM ? (const void *)(reinterpret_cast<const short2 *>(a.iq) + (u64)cap * a.stride)
                                           : (const void *)(reinterpret_cast<const float2 *>(a.iq) + (u64)cap * a.stride);
@@ -1573,8 +1580,8 @@ __global__ void __launch_bounds__(F1_THREADS, 7) k_front1(const TiledArgs a, con
         __syncthreads();
         for (unsigned o = tid; o < span; o += F1_THREADS) y[o] = ys[o];
     }
-    if (!LIST) return;
-    __syncthreads();                                       // the tile has left (thread 0 waited for the bulk read): next capture
+    if (MODE == 0) return;
+    __syncthreads();                                       // the tile has left (thread 0 waited for the bulk read): next item
   }
 }
 
