@@ -703,6 +703,34 @@ def test_argos_synthetic_bursts(torch_cuda, oracle64):
     _frames_text_equal_bytes(d.format_frames(fr[0], int(st[0]["n_frames"])), want["text"])
 
 
+@pytest.mark.parametrize("prec", ["f32", "f64"])
+@pytest.mark.parametrize("bw_acq,bw_track,thresh", [(0.3, 0.05, 0.2), (0.9, 0.4, 0.03), (0.02, 0.002, 0.1)])
+def test_pll_block_runner_any_loop_bandwidth(torch_cuda, oracle32, oracle64, prec, bw_acq, bw_track, thresh):
+    """The block runner (pdt_pll_pipe.cuh) uses select forms of the loop filter only while one 2π wrap per sample suffices;
+    loop bandwidths far outside any sane setting take the reference-shaped while-loops.  Both paths, acquisition, latch and
+    track mode, call after call with carried state, against the oracle's CarrierTrackPLL: float bit for bit."""
+    o = oracle64 if prec == "f64" else oracle32
+    fs = 50000
+    pcm, _ = make_poes_capture(30000, fs, 21, esn0_db=16.0, doppler_hz=900.0, amplitude=0.3)
+    iq = o.pcm16_to_complex(pcm)
+    args = (float(fs), 4500.0, thresh, 0.002, bw_acq, bw_track)
+    lg = pdt.Legacy(prec)
+    lg.reset()
+    st = o.new_state("pll")
+    cuts = [0, 7001, 7002, 15000, 15129, 30000]              # odd call lengths: partial blocks, a one-sample call
+    locked_seen = False
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        got_o, got_l, got_avg = lg.CarrierTrackPLL(iq[2 * a: 2 * b], *args, want_lock=True)
+        want_o, want_l, want_avg, _, _ = o.pll(st, iq[2 * a: 2 * b], *args, want_lock=True)
+        if prec == "f32":
+            assert np.array_equal(got_o, want_o) and np.array_equal(got_l, want_l) and got_avg == want_avg
+        else:
+            np.testing.assert_allclose(got_o, want_o, rtol=1e-11, atol=1e-14)
+            np.testing.assert_allclose(got_l, want_l, rtol=1e-11, atol=1e-14)
+        locked_seen |= bool((want_l > thresh).any())
+    assert locked_seen                                         # the latch fired somewhere: both modes were exercised
+
+
 @pytest.mark.parametrize("prec,mode,fs,taps", [("f64", pdt.PDT_MODE_ARGOS, 5000, 600), ("f32", pdt.PDT_MODE_POES, 50000, 3 * 300)])
 def test_exact_engine_long_fir_history_across_chunks(torch_cuda, oracle32, oracle64, prec, mode, fs, taps):
     """the FIR history (K - 1 samples carried from chunk to chunk) may be longer than the CTA — K - 1 = 599
