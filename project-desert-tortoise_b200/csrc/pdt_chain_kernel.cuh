@@ -1,12 +1,16 @@
 // pdt_chain_kernel.cuh — the fused whole-chain kernel: one CTA per IQ capture, the capture is walked in
 // reference-sized chunks (the chunk length is part of the reference's numerical behaviour: Gardner works
-// in chunk-relative float coordinates), all intermediate streams live in shared memory
-// (or a per-CTA global workspace when the chunk does not fit).
+// in chunk-relative float coordinates).  The chunk-sized intermediate streams live in a per-CTA
+// workspace — global memory (L1/L2-resident, touched by the parallel phases only) or shared memory, whichever keeps
+// more CTAs resident (pdt_create decides) — and every serial phase works on a window of it staged in shared memory.
 //
 // Data flow per chunk (reference: POESTIPdemod/main.c:379-454, ARGOSdemod/main.c:252-284):
 //   IQ (HBM, cf32/cf64 or int16 PCM) --PLL--> R[chunk] --FIR(+×L interp)--> Y[chunk·L] --AGC(+squelch)--> Y
 //   --Gardner--> symbols --Manchester--> bits --ByteSync--> frame table (HBM)
-// Only the IQ read and the (tiny) frame table touch HBM: 8 B (float) / 16 B (double) / 4 B (pcm16) per sample.
+//   PLL: the whole CTA, in speculated and verified blocks (pdt_pll_pipe.cuh); FIR: all threads; StaticGain, AGC: one thread
+//   over staged windows (magnitudes / squelch by all threads); clock recovery -> bits: one thread, state in registers.
+// HBM sees the IQ read and the (tiny) frame table: 8 B (float) / 16 B (double) / 4 B (pcm16) per sample.  The kernel is
+// latency-bound by design (a handful of dependent chains per capture): CTAs are narrow and many.
 #pragma once
 
 #include "pdt_common.cuh"
@@ -138,7 +142,7 @@ struct WindowView {
 __device__ unsigned long long g_chain_prof[20];
 
 // ---------------------------------------------------------------------------------------------------
-// v1 chain kernel: exact-order serial loops on lane 0, FIR on all threads.
+// the exact engine's kernel: one CTA walks one capture (or live stream) chunk by chunk
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(CHAIN_THREADS, CHAIN_MIN_CTAS) k_chain_exact(const ChainArgs args)
 {

@@ -3,9 +3,10 @@
 // POESTIPdemod/main.c and ARGOSdemod/main.c link unmodified against these symbols.  Like the
 // reference, the state of every stage is a process-wide singleton that is latched on first use; here it
 // lives in device memory.  Each call stages the caller's host buffers to the GPU, runs the stage kernel
-// and copies the result back before returning.  The serial recurrences (PLL, AGC, Gardner, Manchester,
-// ByteSync) run in the reference's exact operation order on one lane; the FIRs are data-parallel with the
-// reference's exact (rotating) summation order.  The time-axis arrays are pure index bookkeeping and are
+// and copies the result back before returning.  CarrierTrackPLL runs on one CTA through the block runner of the exact
+// engine (pdt_pll_pipe.cuh: only the loop filter is serial), the float AGC through the proved common-regime chain of the
+// batch engine; Gardner / M&M, Manchester and ByteSync run in the reference's exact operation order on one thread; the
+// FIRs are data-parallel with the reference's exact (rotating) summation order.  The time-axis arrays are pure index bookkeeping and are
 // compacted on the host from the pick indices the kernels return.
 #include <cmath>
 #include <vector>
