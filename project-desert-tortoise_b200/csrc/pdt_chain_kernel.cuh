@@ -249,22 +249,31 @@ __global__ void __launch_bounds__(CHAIN_THREADS, CHAIN_MIN_CTAS) k_chain_exact(c
             // ---- FIR (all threads), exact summation order -------------------------------------------
             const unsigned long long j0 = st.fir_j;                     // absolute index of R[0] of this chunk
             const uint32_t n_out = m * (uint32_t)cc.L;
-            if (!cc.argos) {
-                for (uint32_t o = tid; o < n_out; o += CHAIN_THREADS) {
-                    const uint32_t jl = o / cc.L; const int p = (int)(o - jl * cc.L);
-                    const int k0 = (int)((j0 + jl) % (unsigned)cc.K);
-                    const real_t y = fir_interp_exact(taps_s, Rext + (cc.K - 1) + jl, cc.N, cc.L, cc.K, p, k0);
-                    Y[o] = y;
-                    if (tr && tr->lpf) reinterpret_cast<real_t *>(tr->lpf)[base * cc.L + o] = y;
+            // tiles of inputs (with their K-1 samples of history in front) pass through the shared staging area: the chunk buffer
+            // itself may live in global memory, and every output reads K inputs
+            const uint32_t fir_tile = (uint32_t)(WS_REALS - (cc.K - 1)) & ~127u;          // K - 1 <= 1023 < WS_REALS
+            for (uint32_t t0 = 0; t0 < m; t0 += fir_tile) {
+                const uint32_t tn = (m - t0 < fir_tile) ? (m - t0) : fir_tile;
+                for (uint32_t i = tid; i < tn + (uint32_t)cc.K - 1; i += CHAIN_THREADS) WS[i] = Rext[t0 + i];
+                __syncthreads();
+                const uint32_t o_lo = t0 * (uint32_t)cc.L, o_hi = (t0 + tn) * (uint32_t)cc.L;
+                if (!cc.argos) {
+                    for (uint32_t o = o_lo + tid; o < o_hi; o += CHAIN_THREADS) {
+                        const uint32_t jl = o / cc.L; const int p = (int)(o - jl * cc.L);
+                        const int k0 = (int)((j0 + jl) % (unsigned)cc.K);
+                        const real_t y = fir_interp_exact(taps_s, WS + (cc.K - 1) + (jl - t0), cc.N, cc.L, cc.K, p, k0);
+                        Y[o] = y;
+                        if (tr && tr->lpf) reinterpret_cast<real_t *>(tr->lpf)[base * cc.L + o] = y;
+                    }
+                } else {
+                    for (uint32_t o = o_lo + tid; o < o_hi; o += CHAIN_THREADS) {
+                        const real_t y = fir_plain_exact(taps_s, WS + (cc.K - 1) + (o - t0), cc.N);
+                        Y[o] = y;
+                        if (tr && tr->lpf) reinterpret_cast<real_t *>(tr->lpf)[base + o] = y;
+                    }
                 }
-            } else {
-                for (uint32_t o = tid; o < n_out; o += CHAIN_THREADS) {
-                    const real_t y = fir_plain_exact(taps_s, Rext + (cc.K - 1) + o, cc.N);
-                    Y[o] = y;
-                    if (tr && tr->lpf) reinterpret_cast<real_t *>(tr->lpf)[base + o] = y;
-                }
+                __syncthreads();
             }
-            __syncthreads();
             // slide the FIR history: keep the last K-1 inputs
             {
                 // K - 1 <= 1023 (build_chain_const) may exceed the CTA: every thread carries up to 4 elements through registers,
