@@ -126,8 +126,11 @@ PDT_DEV void consume_symbol(BackState &st, const ChainConst &cc, real_t sym, uns
 
 // The PLL block arrays double as the staging window of the other serial stages (they never run at the same time).
 constexpr int WS_REALS = (int)(sizeof(PllPipeSmem) / sizeof(real_t)) & ~3;
-constexpr int CLK_BACK = 512, CLK_WIN = 2560;            // clock recovery: look-back kept in front of every window
-static_assert(CLK_BACK + CLK_WIN <= WS_REALS, "clock-recovery window must fit the shared staging area");
+constexpr int CLK_BACK = 512, CLK_WIN = 1536;            // clock recovery: look-back kept in front of every window
+constexpr int CLK_Q = 256;                               // symbols per queue (two queues: values as reals, pick indices as uint32)
+static_assert(CLK_BACK + CLK_WIN + 2 * CLK_Q + (2 * CLK_Q * 4 + sizeof(real_t) - 1) / sizeof(real_t) <= WS_REALS,
+              "clock-recovery window and symbol queues must fit the shared staging area");
+struct ClkQueueCtl { int cnt[2], more[2]; };
 
 // chunk samples [lo, hi) from shared memory, everything else from the chunk buffer
 struct WindowView {
@@ -150,6 +153,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, CHAIN_MIN_CTAS) k_chain_exact(c
     __shared__ ChainState st;
     __shared__ real_t taps_s[PDT_MAX_TAPS];
     __shared__ __align__(16) PllPipeSmem pll_blk;
+    __shared__ ClkQueueCtl clk_q;
     real_t *const WS = reinterpret_cast<real_t *>(&pll_blk);
 
     const ChainConst &cc = args.cc;
@@ -334,61 +338,85 @@ __global__ void __launch_bounds__(CHAIN_THREADS, CHAIN_MIN_CTAS) k_chain_exact(c
                 __syncthreads();
             }
 
-            // ---- clock recovery -> Manchester -> ByteSync on one thread; the chunk passes through shared memory in windows
-            //      with CLK_BACK samples of look-back (anything outside the window, e.g. the stale half-way index the reference
-            //      carries across a chunk boundary, is read from the chunk buffer itself) ------------------------------------
+            // ---- clock recovery (thread 0) -> symbol queue -> Manchester + ByteSync (thread 32).  The chunk passes through shared
+            //      memory in windows with CLK_BACK samples of look-back (anything outside the window, e.g. the stale half-way index
+            //      the reference carries across a chunk boundary, is read from the chunk buffer itself); thread 0 fills one
+            //      symbol queue while thread 32 drains the other ----------------------------------------------------------------
             { const long long now = clock64(); pf[13] += now - pf_t; pf_t = now; }
-            BackState bk;
+            BackState bk;                                   // thread 0 owns gar / mm / n_sym, thread 32 the rest
+            if (tid == 0 || tid == 32) back_load(bk, st, frames);
             if (tid == 0) {
-                back_load(bk, st, frames);
                 gardner_begin(bk.gar, cc.gardner_fs, cc.baud);
                 if (cc.use_mm) mm_begin(bk.mm, cc.gardner_fs, cc.baud);              // MMClockRecovery.c:5-84 (the call the drivers keep commented out)
             }
             {
                 const unsigned long long ibase = (in0 + base) * (unsigned long long)cc.L;
                 const real_t step_max = cc.gardner_fs / (cc.baud - cc.mm_range), step_min = cc.gardner_fs / (cc.baud + cc.mm_range);
+                real_t   *const q_sym = WS + CLK_BACK + CLK_WIN;                                       // [2][CLK_Q]
+                uint32_t *const q_at  = reinterpret_cast<uint32_t *>(q_sym + 2 * CLK_Q);               // [2][CLK_Q]
+                int fill = 0;                               // queue being filled; the other one (if `pending`) is being drained
+                bool pending = false;
+                auto drain = [&](int qi) {                  // thread 32
+                    const int cnt = clk_q.cnt[qi];
+                    const real_t *qs = q_sym + qi * CLK_Q; const uint32_t *qa = q_at + qi * CLK_Q;
+                    for (int k = 0; k < cnt; k++) consume_symbol(bk, cc, qs[k], ibase + qa[k], frames, tr);
+                };
                 for (uint32_t w0 = 0; w0 < n_out; w0 += CLK_WIN) {
                     const uint32_t w_hi = (n_out - w0 < (uint32_t)CLK_WIN) ? n_out : w0 + CLK_WIN;
                     const uint32_t w_lo = (w0 > (uint32_t)CLK_BACK) ? w0 - CLK_BACK : 0u;
                     __syncthreads();
                     for (uint32_t k = w_lo + tid; k < w_hi; k += CHAIN_THREADS) WS[k - w_lo] = Y[k];
                     __syncthreads();
-                    if (tid == 0) {
-                        const WindowView yv{WS, Y, w_lo, w_hi};
-                        if (cc.use_mm) {
-                            while (mm_rint(bk.mm.next) < w_hi) {
-                                real_t sym;
-                                const unsigned at = mm_step(bk.mm, yv, step_min, step_max, cc.mm_kp, sym);
-                                if (tr && bk.n_sym < tr->cap) {
-                                    if (tr->sym)         reinterpret_cast<real_t *>(tr->sym)[bk.n_sym] = sym;
-                                    if (tr->gardner_idx) tr->gardner_idx[bk.n_sym] = ibase + at;
+                    bool more = true;
+                    while (more) {                          // one trip per window unless a queue fills up (very short symbols)
+                        if (tid == 0) {
+                            const WindowView yv{WS, Y, w_lo, w_hi};
+                            real_t *qs = q_sym + fill * CLK_Q; uint32_t *qa = q_at + fill * CLK_Q;
+                            int cnt = 0;
+                            if (cc.use_mm) {
+                                while (cnt < CLK_Q && mm_rint(bk.mm.next) < w_hi) {
+                                    real_t sym;
+                                    const unsigned at = mm_step(bk.mm, yv, step_min, step_max, cc.mm_kp, sym);
+                                    if (tr && bk.n_sym < tr->cap) {
+                                        if (tr->sym)         reinterpret_cast<real_t *>(tr->sym)[bk.n_sym] = sym;
+                                        if (tr->gardner_idx) tr->gardner_idx[bk.n_sym] = ibase + at;
+                                    }
+                                    bk.n_sym++;
+                                    qs[cnt] = sym; qa[cnt] = at; cnt++;
                                 }
-                                bk.n_sym++;
-                                consume_symbol(bk, cc, sym, ibase + at, frames, tr);
-                            }
-                        } else {
-                            while (r_rint(bk.gar.next) < w_hi) {
-                                real_t sym, err;
-                                const unsigned at = gardner_step(bk.gar, yv, cc.g_range, cc.g_kp, sym, err);
-                                if (tr && bk.n_sym < tr->cap) {
-                                    if (tr->sym)         reinterpret_cast<real_t *>(tr->sym)[bk.n_sym] = sym;
-                                    if (tr->gardner_err) reinterpret_cast<real_t *>(tr->gardner_err)[bk.n_sym] = err;
-                                    if (tr->gardner_idx) tr->gardner_idx[bk.n_sym] = ibase + at;
+                                clk_q.more[fill] = mm_rint(bk.mm.next) < w_hi;
+                            } else {
+                                while (cnt < CLK_Q && r_rint(bk.gar.next) < w_hi) {
+                                    real_t sym, err;
+                                    const unsigned at = gardner_step(bk.gar, yv, cc.g_range, cc.g_kp, sym, err);
+                                    if (tr && bk.n_sym < tr->cap) {
+                                        if (tr->sym)         reinterpret_cast<real_t *>(tr->sym)[bk.n_sym] = sym;
+                                        if (tr->gardner_err) reinterpret_cast<real_t *>(tr->gardner_err)[bk.n_sym] = err;
+                                        if (tr->gardner_idx) tr->gardner_idx[bk.n_sym] = ibase + at;
+                                    }
+                                    bk.n_sym++;
+                                    qs[cnt] = sym; qa[cnt] = at; cnt++;
                                 }
-                                bk.n_sym++;
-                                consume_symbol(bk, cc, sym, ibase + at, frames, tr);
+                                clk_q.more[fill] = r_rint(bk.gar.next) < w_hi;
                             }
-                        }
+                            clk_q.cnt[fill] = cnt;
+                        } else if (tid == 32 && pending) drain(fill ^ 1);
+                        __syncthreads();
+                        more = clk_q.more[fill] != 0;       // (rewritten two barriers from here at the earliest)
+                        pending = true; fill ^= 1;
                     }
                 }
+                if (tid == 32 && pending) drain(fill ^ 1);
                 if (tid == 0) {
                     if (cc.use_mm) bk.mm.next = bk.mm.next - n_out;                  // :80
                     else           bk.gar.next = bk.gar.next - n_out;                // :111
-                    back_store(st, bk);
-                    pf[14] += clock64() - pf_t;
+                    st.gar = bk.gar; st.mm = bk.mm; st.n_sym = bk.n_sym;
+                } else if (tid == 32) {
+                    st.man = bk.man; st.sync = bk.sync; st.n_bits = bk.n_bits; st.n_frames = bk.n_frames; st.cur_frame = bk.cur_frame;
                 }
             }
             __syncthreads();
+            if (tid == 0) pf[14] += clock64() - pf_t;
         }
         if (tid == 0) {
             atomicAdd(&g_chain_prof[0], pf[10]); atomicAdd(&g_chain_prof[1], pf[11]);
