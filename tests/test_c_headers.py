@@ -25,3 +25,12 @@ def test_c_example_links_and_fails_cleanly_without_arguments(tmp_path):
                     "-Wl,-rpath," + PKG, "-lm"], check=True)
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 1 and "usage:" in r.stderr and "pdt-b200" in r.stderr      # pdt_version() came from the library
+
+
+def test_c_live_example_links_and_fails_cleanly_without_arguments(tmp_path):
+    exe = tmp_path / "live_stdin"
+    subprocess.run(["gcc", *CFLAGS, "-o", str(exe), os.path.join(ROOT, "examples", "live_stdin.c"), "-L" + PKG, "-lpdt_f32",
+                    "-Wl,-rpath," + PKG, "-lm"], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 1 and "usage:" in r.stderr and "pdt-b200" in r.stderr
+

@@ -112,3 +112,21 @@ def test_live_restart_gives_the_same_result_again():
         runs.append((rows, live.stats.copy()))
     live.close()
     assert runs[0][0] == runs[1][0] and len(runs[0][0]) >= 3 and np.array_equal(runs[0][1], runs[1][1])
+
+
+def test_live_c_example_prints_the_golden_frames(tmp_path):
+    """examples/live_stdin.c (plain C99 against include/pdt.h): 5sec_clip.wav's PCM piped through it in blocks of 10000."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "project-desert-tortoise_b200")
+    exe = tmp_path / "live_stdin"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-I" + os.path.join(root, "include"), "-o", str(exe),
+                    os.path.join(root, "examples", "live_stdin.c"), "-L" + pkg, "-lpdt_f32", "-Wl,-rpath," + pkg, "-lm"], check=True)
+    rate, pcm = po.read_wav_pcm16(os.path.join(GOLDEN, "5sec_clip.wav"))
+    r = subprocess.run([str(exe), str(rate), "10000"], input=np.ascontiguousarray(pcm, np.int16).tobytes(), capture_output=True)
+    assert r.returncode == 0, r.stderr.decode()
+    golden = _rows(open(os.path.join(GOLDEN, "poes_5sec_clip_frames.txt")).read())
+    got = _rows(r.stdout.decode())
+    full = [g for g in golden if len(g[1]) == 104]                            # the trailing partial frame is never completed
+    assert len(full) >= 45 and got == full
+
