@@ -306,24 +306,9 @@ __global__ void __launch_bounds__(CHAIN_THREADS, CHAIN_MIN_CTAS) k_chain_exact(c
                     uint32_t k = 0;
                     for (; k + 4 <= wn; k += 4) {                        // inputs fetched ahead of the dependent gain chain
                         const real_t x0 = WS[k], x1 = WS[k + 1], x2 = WS[k + 2], x3 = WS[k + 3];
-                        // AGC.c:98-131 in its common regime — decay branch, no clamp: gain' = gain - (|x·gain| - 1)·decay, four
-                        // dependent operations per sample — with the conditions of the other branches evaluated beside the
-                        // chain; a group in which any of them holds is redone by the general step from the saved gain
-                        const real_t g_in = ag.gain;
-                        real_t g = g_in;
-                        bool other = false;
-                        const real_t v0 = x0 * g; { const real_t e = r_fabs(v0) - (real_t)1.0; other |= r_fabs(e) > g; g = g - e * cc.agc_decay; other |= (g < 0.0) | (g > (real_t)5000); }
-                        const real_t v1 = x1 * g; { const real_t e = r_fabs(v1) - (real_t)1.0; other |= r_fabs(e) > g; g = g - e * cc.agc_decay; other |= (g < 0.0) | (g > (real_t)5000); }
-                        const real_t v2 = x2 * g; { const real_t e = r_fabs(v2) - (real_t)1.0; other |= r_fabs(e) > g; g = g - e * cc.agc_decay; other |= (g < 0.0) | (g > (real_t)5000); }
-                        const real_t v3 = x3 * g; { const real_t e = r_fabs(v3) - (real_t)1.0; other |= r_fabs(e) > g; g = g - e * cc.agc_decay; other |= (g < 0.0) | (g > (real_t)5000); }
-                        if (!other) {
-                            ag.gain = g;
-                            WS[k] = v0; WS[k + 1] = v1; WS[k + 2] = v2; WS[k + 3] = v3;
-                        } else {
-                            ag.gain = g_in;
-                            WS[k] = agc_step(ag, x0, cc.agc_attack, cc.agc_decay); WS[k + 1] = agc_step(ag, x1, cc.agc_attack, cc.agc_decay);
-                            WS[k + 2] = agc_step(ag, x2, cc.agc_attack, cc.agc_decay); WS[k + 3] = agc_step(ag, x3, cc.agc_attack, cc.agc_decay);
-                        }
+                        real_t v0, v1, v2, v3;
+                        agc_step4(ag, x0, x1, x2, x3, cc.agc_attack, cc.agc_decay, v0, v1, v2, v3);   // common-regime chain, verified
+                        WS[k] = v0; WS[k + 1] = v1; WS[k + 2] = v2; WS[k + 3] = v3;
                     }
                     for (; k < wn; k++) WS[k] = agc_step(ag, WS[k], cc.agc_attack, cc.agc_decay);
                     st.agc = ag;

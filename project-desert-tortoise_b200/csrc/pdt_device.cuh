@@ -322,6 +322,26 @@ PDT_DEV real_t agc_step(AgcState &s, real_t x, real_t attack, real_t decay)
     return x;
 }
 
+// Four samples of AGC.c:98-131 in its common regime — decay branch, no clamp: gain' = gain - (|x·gain| - 1)·decay, four dependent
+// operations per sample — with the conditions of the other branches evaluated beside the chain; a group in which any of them
+// holds is redone by the general step from the saved gain.  Same results as four agc_step calls, always
+// (tests/host/loop_forms.cu compares the two on the host).
+PDT_DEV void agc_step4(AgcState &s, real_t x0, real_t x1, real_t x2, real_t x3, real_t attack, real_t decay,
+                       real_t &v0, real_t &v1, real_t &v2, real_t &v3)
+{
+    const real_t g_in = s.gain;
+    real_t g = g_in;
+    bool other = false;
+    v0 = x0 * g; { const real_t e = r_fabs(v0) - (real_t)1.0; other |= r_fabs(e) > g; g = g - e * decay; other |= (g < 0.0) | (g > (real_t)5000); }
+    v1 = x1 * g; { const real_t e = r_fabs(v1) - (real_t)1.0; other |= r_fabs(e) > g; g = g - e * decay; other |= (g < 0.0) | (g > (real_t)5000); }
+    v2 = x2 * g; { const real_t e = r_fabs(v2) - (real_t)1.0; other |= r_fabs(e) > g; g = g - e * decay; other |= (g < 0.0) | (g > (real_t)5000); }
+    v3 = x3 * g; { const real_t e = r_fabs(v3) - (real_t)1.0; other |= r_fabs(e) > g; g = g - e * decay; other |= (g < 0.0) | (g > (real_t)5000); }
+    if (!other) { s.gain = g; return; }
+    s.gain = g_in;
+    v0 = agc_step(s, x0, attack, decay); v1 = agc_step(s, x1, attack, decay);
+    v2 = agc_step(s, x2, attack, decay); v3 = agc_step(s, x3, attack, decay);
+}
+
 PDT_DEV real_t static_gain_serial(const real_t *iq, unsigned long long n, real_t desired)
 {
     real_t level = hypot_exact(iq[0], iq[1]);
