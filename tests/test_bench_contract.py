@@ -1,4 +1,4 @@
-"""bench.py --impl reference needs no GPU: it times the reference's own CPU path (oracle/_ref when the reference compiled here,
+"""The JSON lines bench.py prints are a contract with the driver.  bench.py --impl reference needs no GPU: it times the reference's own CPU path (oracle/_ref when the reference compiled here,
 else the oracle port).  The JSON line it prints is a contract with the driver — checked here on a tiny sample."""
 import json
 import os
@@ -41,3 +41,27 @@ def test_other_ranks_of_a_reference_run_exit_quietly():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"],
                        capture_output=True, text=True, cwd=ROOT, timeout=120, env=env)
     assert r.returncode == 0 and not [l for l in r.stdout.splitlines() if l.startswith("{")]
+
+
+@pytest.mark.gpu
+def test_our_arm_line_on_a_small_batch():
+    """The product arm's JSON line on a small batch (64 captures x 300 k samples): every key of the contract, the roofline and
+    cpu_baseline objects, a positive launch count, the frame-bytes check of the sampled captures against the reference."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--captures", "64", "--samples", "300000", "--steps", "4", "--warmup", "3",
+                        "--no-single", "--cpu-captures", "4"], capture_output=True, text=True, cwd=ROOT, timeout=900)
+    assert r.returncode == 0, r.stderr[-800:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    b = json.loads(lines[0])
+    need = (REQUIRED - {"impl"}) | {"gpu_launches", "roofline", "clocks"}
+    assert need <= set(b), need - set(b)
+    assert b["value"] > 0 and b["n_gpus"] == 1 and b["gpu_launches"] > 0 and b["dtype"] == "f32" and b["scaling"] == "weak"
+    rf = b["roofline"]
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic"} <= set(rf) and rf["bound"] == "hbm" and 0 < rf["frac"] < 1.2
+    assert abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9
+    e = b["e2e"]
+    assert e["value"] > 0 and e["h2d_bytes_per_step"] == 64 * 300000 * 8 and e["d2h_bytes_per_step"] > 0
+    cb = b["cpu_baseline"]
+    assert cb["kind"] in ("reference", "port") and cb["value"] > 0 and cb["cores"] >= 1
+    assert cb.get("frame_bytes_check", {}).get("equal") is True
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(b["clocks"])
