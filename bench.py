@@ -363,13 +363,11 @@ ARGOS_FS, ARGOS_N = 5000, 40_000
 def argos_captures(count):
     """`count` float64 [2n] captures: 64 distinct seeded two-burst recordings (8 s @ 5 ksps each, SNR 14…25 dB, the set
     tests/test_gpu_parity.py::test_config2 checks against the oracle), repeated with a constant carrier-phase rotation."""
-    import pyoracle as po
     from tests.synth_ref import make_argos_capture
-    o = po.Oracle("f64")
     base = []
     for c in range(min(count, 64)):
         pcm, _ = make_argos_capture(ARGOS_N, float(ARGOS_FS), seed=40 + c, n_bursts=2, snr_db=14.0 + (c % 12))
-        base.append(o.pcm16_to_complex(pcm).view(np.complex128))
+        base.append((np.ascontiguousarray(pcm, np.int16).astype(np.float64) / 32768.0).view(np.complex128))   # wave.c:151-156
     out = np.empty((count, ARGOS_N), np.complex128)
     for c in range(count):
         out[c] = base[c % len(base)] * np.exp(1j * 0.37 * (c // len(base)))
