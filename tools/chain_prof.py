@@ -14,7 +14,6 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import torch  # noqa: E402
 
 pdt = importlib.import_module("project-desert-tortoise_b200")
@@ -66,13 +65,11 @@ def main():
     del d, d_iq
     # POES float, exact engine, 50 ksps (L = 3)
     from tests.synth_ref import make_poes_capture
-    import pyoracle as po
-    o = po.Oracle("f32")
     caps, n = 256, 250_000
     base = []
     for c in range(8):
         pcm, _ = make_poes_capture(n, 50000, 100 + c, esn0_db=12.0, doppler_hz=-800.0 + 200 * c, amplitude=0.25)
-        base.append(o.pcm16_to_complex(pcm).view(np.complex64))
+        base.append((np.ascontiguousarray(pcm, np.int16) / np.float32(32768)).astype(np.float32).view(np.complex64))   # wave.c:151-156
     host = np.stack([base[c % 8] for c in range(caps)]).view(np.float32).reshape(caps, 2 * n)
     d_iq = torch.from_numpy(host).cuda()
     p = pdt.default_params("f32", pdt.PDT_MODE_POES, 50000)

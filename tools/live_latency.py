@@ -3,7 +3,7 @@
 for 1 … 1024 simultaneous streams, POES at 50 ksps (the reference's sound-card rates are 32–48 kHz) with its default chunk."""
 import importlib, json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, ROOT)
 import numpy as np
 pdt = importlib.import_module("project-desert-tortoise_b200")
 from tests.synth_ref import make_poes_capture
